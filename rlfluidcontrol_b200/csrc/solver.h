@@ -1,0 +1,93 @@
+// solver.h -- device data layout and kernel launch interface of the batched BDIM solver.
+//
+// Layout in HBM (all fp32):
+//   * every per-environment field is an (n x P) pitched array (i = x outer, j = y contiguous, ghost
+//     ring included, P = m rounded up to 8 floats so rows are 32 B-sector aligned), and the batch is
+//     struct-of-arrays: field[e] = base + e * stride, stride = n*P rounded up to 32 floats;
+//   * static geometry / coefficient fields are stored once (shared by the whole batch, L2-resident).
+// Velocity lives in three rotating buffers A (step-start u, doubles as u0), B (predictor result,
+// doubles as `us`), C (corrector result); see BDIM.pde:79-107 for the data flow reproduced.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+
+namespace rlfc {
+
+constexpr int kMaxLevels = 16;
+
+struct DevLevel {
+  int n, m, P;              // dims incl. ghosts, pitch
+  size_t stride;            // per-env stride (floats) of r/x/d at this level
+  const float *lx, *ly, *inv, *diag;   // static, pitched
+  float *r, *r2, *x, *d;    // per-env batch arrays (level 0: x = p; r2 = ping-pong residual)
+};
+
+struct BandFace {           // a face where the BDIM blend differs from the identity
+  int i, j;
+  float del, del1, wnx, wny;
+};
+
+struct SamplePt { int i, j; float s, t; };
+struct ForcePt { int i, j; float s, t, l, nx, ny; };
+
+// Per-env scalar state (struct of arrays on the device)
+struct EnvScalars {
+  float *xi;        // [B][2] current action (xi1, xi2)
+  float *t;         // [B]    AFCCylinder.t
+  float *force;     // [B][2] last raw force (-pressForce)
+  float *probes;    // [B][32]
+  int   *callLearn; // [B]    draw() accumulators (clientCFD.pde:11-13)
+  float *Cd, *Cl;   // [B]
+  float *obs;       // [B][2] last produced (Cl, Cd)
+  int   *active;    // [B]    MG: env still iterating
+  int   *iters;     // [B][2] MG iterations of the last predictor/corrector solve
+  double *rr_part;  // [B][rr_blocks] partial sums of r.r
+  float *psum;      // [B]    serial interior sum of p
+  int   *any_active;// [1]
+};
+
+struct SolverParams {
+  int B;                    // environments in the batch
+  int n, m, P;              // level-0 dims
+  size_t stride;            // level-0 per-env stride
+  float dt, nu, dRD;        // dRD = dR*D (AFCCylinder.pde:48)
+  float dt_over_res;        // dt/resolution (AFCCylinder.pde:56)
+  float action_scale;       // 5
+  float inv_cells;          // (float)((n-2)*(m-2))
+  float mg_tol;
+  int   nlevels;
+  int   resolution, substeps, mg_max_iters;
+  float init_time, episode_time;
+  DevLevel lev[kMaxLevels];
+  // static level-0 fields
+  const float *c_x, *c_y;
+  const float *w1_x, *w2_x, *ry1_x, *ry2_x, *w1_y, *w2_y, *rx1_y, *rx2_y;
+  const BandFace *band_x, *band_y;
+  int nband_x, nband_y;
+  float *band_tmp;          // [B][nband_x + nband_y]
+  const ForcePt *force_pts; int nforce;
+  const SamplePt *probe_pts; int nprobe;
+  int rr_blocks;            // number of per-env partial sums written by the increment kernel
+  EnvScalars sc;
+};
+
+// ---- launch wrappers (solver_kernels.cu).  All enqueue on `st`; return number of launches. ----
+int launch_advdif(const SolverParams& P, const float* srcx, const float* srcy, const float* u0x, const float* u0y,
+                  float* dstx, float* dsty, cudaStream_t st);
+int launch_band_bc(const SolverParams& P, float* ux, float* uy, cudaStream_t st);
+int launch_residual(const SolverParams& P, const float* ux, const float* uy, float* r, int which, cudaStream_t st);
+// one MG iteration (V-cycle + smooth(4)) on active envs; r_in/r_out are the level-0 ping-pong buffers
+int launch_mg_iteration(const SolverParams& P, float* r_in, float* r_out, int which, cudaStream_t st);
+int launch_psum(const SolverParams& P, cudaStream_t st);
+int launch_project(const SolverParams& P, float* ux, float* uy, cudaStream_t st);
+int launch_bc(const SolverParams& P, float* ux, float* uy, cudaStream_t st);
+int launch_heun(const SolverParams& P, const float* ucx, const float* ucy, const float* ubx, const float* uby,
+                float* uax, float* uay, cudaStream_t st);
+// force + probes + time advance; accumulate != 0 applies the clientCFD.draw() accumulation
+int launch_force(const SolverParams& P, int accumulate, cudaStream_t st);
+int launch_set_actions(const SolverParams& P, const float* d_actions, cudaStream_t st);
+int launch_emit_obs(const SolverParams& P, const float* d_actions, float* d_obs, float* d_reward, int* d_done,
+                    cudaStream_t st);
+
+}  // namespace rlfc

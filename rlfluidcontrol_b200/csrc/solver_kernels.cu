@@ -1,0 +1,727 @@
+// solver_kernels.cu -- hand-written sm_100a kernels of the batched BDIM solver (exact mode).
+//
+// Compiled with --fmad=false: the reference is Java `float` (one IEEE binary32 rounding per
+// operation, no contraction); every expression below keeps the reference's association order so the
+// device results are bit-identical to the reference arithmetic.  Reference citations are into
+// clientLilypad/.
+//
+// Kernel inventory (one launch handles the whole batch; blockIdx.z / blockIdx.x = environment):
+//   k_advdif      VectorField.AdvDif (QUICK, median-limited)            VectorField.pde:170-222
+//   k_band_bc     BDIM blend + mu1 term on the body band, then u.setBC   BDIM.pde:109-122, Field.pde:209-234
+//   k_residual    r = div(u) - A p                                      VectorField.pde:56-65, PoissonMatrix.pde:53-68
+//   k_mg_down0    level-0 smooth(0) + increment + residual restriction  MG.pde:68-70,79-97,124-137
+//   k_mg_coarse   levels >= 1 of the V-cycle in one CTA per env          MG.pde:68-97,124-152
+//   k_mg_up0      level-0 prolongation + increment                       MG.pde:75-76,139-152
+//   k_gs0         level-0 smooth(4): lexicographic Gauss-Seidel wavefronts MG.pde:79-89
+//   k_inc0        level-0 d.setBC + increment + partial r.r              MG.pde:90-97, Field.pde:302-310
+//   k_conv        r.r < tol test, per-env iteration bookkeeping          MG.pde:30-38
+//   k_psum        serial float interior sum of p                        Field.pde:311-318
+//   k_project     mean shift, gradient, velocity correction             VectorField.pde:136-139
+//   k_bc          u.setBC after the projection                          VectorField.pde:140
+//   k_heun        u = (u + us) * 0.5                                     BDIM.pde:95-96
+//   k_force       pressForce + probes + time + draw() accumulation       Body.pde:296-303, SaveScalar.pde:61-72, clientCFD.pde:39-47
+#include "solver.h"
+
+namespace rlfc {
+namespace {
+
+#define IDX(i, j) ((i) * P + (j))
+
+__device__ __forceinline__ float pmin(float a, float b) { return (a < b) ? a : b; }   // PApplet.min
+__device__ __forceinline__ float pmax(float a, float b) { return (a > b) ? a : b; }   // PApplet.max
+__device__ __forceinline__ float med3(float a, float b, float c) {                    // VectorField.pde:221
+  return pmax(pmin(a, b), pmin(pmax(a, b), c));
+}
+
+// ------------------------------------------------------------------------------------------------
+// AdvDif
+// ------------------------------------------------------------------------------------------------
+// VectorField.bho VectorField.pde:202-219, direction (D1,D2) resolved at compile time
+template <int D1, int D2>
+__device__ __forceinline__ float bho(const float* __restrict__ b, int P, int n, int m, int i, int j, float uf) {
+  const float CF = 1.f / 6.f, S = 10.f;
+  float bf = 0.5f * (b[IDX(i + D1, j + D2)] + b[IDX(i, j)]);
+  int d1 = D1, d2 = D2;
+  if (D1 != 0 && D1 * uf < 0) { i += D1; d1 = -D1; }
+  if (D2 != 0 && D2 * uf < 0) { j += D2; d2 = -D2; }
+  if (i > n - 2 || i < 2 || j > m - 2 || j < 2) return bf;
+  float bc = b[IDX(i, j)];
+  float bd = b[IDX(i + d1, j + d2)];
+  float bu = b[IDX(i - d1, j - d2)];
+  bf -= CF * (bd - 2 * bc + bu);
+  float b1 = bu + S * (bc - bu);
+  return med3(bf, bc, med3(bc, bd, b1));
+}
+
+// VectorField.diffusion VectorField.pde:198-200
+__device__ __forceinline__ float diffusion(const float* __restrict__ b, int P, int i, int j) {
+  return b[IDX(i + 1, j)] + b[IDX(i, j + 1)] - 4 * b[IDX(i, j)] + b[IDX(i - 1, j)] + b[IDX(i, j - 1)];
+}
+
+__global__ void __launch_bounds__(256)
+k_advdif(const float* __restrict__ srcx, const float* __restrict__ srcy, const float* __restrict__ u0x,
+         const float* __restrict__ u0y, float* __restrict__ dstx, float* __restrict__ dsty, int n, int m, int P,
+         size_t stride, float dt, float nu) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= n || j >= m) return;
+  const size_t eo = (size_t)blockIdx.z * stride;
+  const float* x = srcx + eo;
+  const float* y = srcy + eo;
+  const int k = IDX(i, j);
+  if (i == 0 || j == 0 || i == n - 1 || j == m - 1) {   // ghosts of F keep u's values (VectorField.pde:171)
+    dstx[eo + k] = x[k];
+    dsty[eo + k] = y[k];
+    return;
+  }
+  // x component (btype 1) VectorField.pde:183-188,195
+  float uo = 0.5f * (x[IDX(i - 1, j)] + x[k]);
+  float ue = 0.5f * (x[IDX(i + 1, j)] + x[k]);
+  float vs = 0.5f * (y[k] + y[IDX(i - 1, j)]);
+  float vn = 0.5f * (y[IDX(i, j + 1)] + y[IDX(i - 1, j + 1)]);
+  float advx = ((uo * bho<-1, 0>(x, P, n, m, i, j, uo) - ue * bho<1, 0>(x, P, n, m, i, j, ue)) +
+                (vs * bho<0, -1>(x, P, n, m, i, j, vs) - vn * bho<0, 1>(x, P, n, m, i, j, vn)));
+  float rx = (advx + nu * diffusion(x, P, i, j)) * dt + u0x[eo + k];
+  // y component (btype 2) VectorField.pde:189-195
+  uo = 0.5f * (x[IDX(i, j - 1)] + x[k]);
+  ue = 0.5f * (x[IDX(i + 1, j - 1)] + x[IDX(i + 1, j)]);
+  vs = 0.5f * (y[IDX(i, j - 1)] + y[k]);
+  vn = 0.5f * (y[k] + y[IDX(i, j + 1)]);
+  float advy = ((uo * bho<-1, 0>(y, P, n, m, i, j, uo) - ue * bho<1, 0>(y, P, n, m, i, j, ue)) +
+                (vs * bho<0, -1>(y, P, n, m, i, j, vs) - vn * bho<0, 1>(y, P, n, m, i, j, vn)));
+  float ry = (advy + nu * diffusion(y, P, i, j)) * dt + u0y[eo + k];
+  dstx[eo + k] = rx;
+  dsty[eo + k] = ry;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Field.setBC executed by one CTA (Field.pde:209-234, loop structure and statement order kept)
+// ------------------------------------------------------------------------------------------------
+__device__ void cta_setBC(float* a, int n, int m, int P, int btype, float bval, bool gexit, float* scol) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ float s_mean;
+  for (int j = tid; j < m; j += nt) {
+    a[IDX(0, j)] = a[IDX(1, j)];
+    float e = a[IDX(n - 2, j)];
+    a[IDX(n - 1, j)] = e;
+    if (btype == 1) {
+      a[IDX(1, j)] = bval;
+      if (gexit) scol[j] = e; else a[IDX(n - 1, j)] = bval;
+    }
+  }
+  __syncthreads();
+  if (gexit && tid == 0) {
+    float s = 0;
+    for (int j = 1; j < m - 1; j++) s += scol[j];      // serial float sum in j order
+    s_mean = s / (float)(m - 2);
+  }
+  for (int i = tid; i < n; i += nt) {
+    a[IDX(i, 0)] = a[IDX(i, 1)];
+    a[IDX(i, m - 1)] = a[IDX(i, m - 2)];
+    if (btype == 2) { a[IDX(i, 1)] = bval; a[IDX(i, m - 1)] = bval; }
+  }
+  __syncthreads();
+  if (gexit) {
+    const float s = s_mean;
+    for (int j = 1 + tid; j < m - 1; j += nt) a[IDX(n - 1, j)] += bval - s;
+  }
+  __syncthreads();
+}
+
+// body velocity from the static basis (BodyUnion.velocity BodyUnion.pde:84-92, Body.velocity Body.pde:234-240)
+__device__ __forceinline__ float ub_x(const SolverParams& q, int k, float dphi1, float dphi2) {
+  float u1 = (0.f - q.ry1_x[k] * dphi1) / q.dt;
+  float u2 = (0.f - q.ry2_x[k] * dphi2) / q.dt;
+  float v = 0.f + u1 * q.w1_x[k];
+  return v + u2 * q.w2_x[k];
+}
+__device__ __forceinline__ float ub_y(const SolverParams& q, int k, float dphi1, float dphi2) {
+  float u1 = (0.f + q.rx1_y[k] * dphi1) / q.dt;
+  float u2 = (0.f + q.rx2_y[k] * dphi2) / q.dt;
+  float v = 0.f + u1 * q.w1_y[k];
+  return v + u2 * q.w2_y[k];
+}
+
+// BDIM.updateUP blend on the body band (everywhere else it is the identity), then u.setBC()
+__global__ void __launch_bounds__(1024)
+k_band_bc(const __grid_constant__ SolverParams q, float* ux_all, float* uy_all) {
+  extern __shared__ float scol[];
+  const int e = blockIdx.x, P = q.P;
+  float* ux = ux_all + (size_t)e * q.stride;
+  float* uy = uy_all + (size_t)e * q.stride;
+  float* tmp = q.band_tmp + (size_t)e * (q.nband_x + q.nband_y);
+  // AFCCylinder.pde:48-49
+  const float xi1_m = q.action_scale * q.sc.xi[2 * e], xi2_m = q.action_scale * q.sc.xi[2 * e + 1];
+  const float dphi1 = (2 * xi1_m * q.dt) / q.dRD, dphi2 = (2 * xi2_m * q.dt) / q.dRD;
+  for (int b = threadIdx.x; b < q.nband_x; b += blockDim.x) {
+    const BandFace f = q.band_x[b];
+    const int k = IDX(f.i, f.j);
+    float R = ux[k], ub = ub_x(q, k, dphi1, dphi2);
+    float v = f.del * R - ub * (f.del + (-1.f));
+    float duE = ux[k + P] - ub_x(q, k + P, dphi1, dphi2), duW = ux[k - P] - ub_x(q, k - P, dphi1, dphi2);
+    float duN = ux[k + 1] - ub_x(q, k + 1, dphi1, dphi2), duS = ux[k - 1] - ub_x(q, k - 1, dphi1, dphi2);
+    float g = 0.5f * (f.wnx * (duE - duW) + f.wny * (duN - duS));       // VectorField.pde:50
+    tmp[b] = v + f.del1 * g;
+  }
+  for (int b = threadIdx.x; b < q.nband_y; b += blockDim.x) {
+    const BandFace f = q.band_y[b];
+    const int k = IDX(f.i, f.j);
+    float R = uy[k], ub = ub_y(q, k, dphi1, dphi2);
+    float v = f.del * R - ub * (f.del + (-1.f));
+    float duE = uy[k + P] - ub_y(q, k + P, dphi1, dphi2), duW = uy[k - P] - ub_y(q, k - P, dphi1, dphi2);
+    float duN = uy[k + 1] - ub_y(q, k + 1, dphi1, dphi2), duS = uy[k - 1] - ub_y(q, k - 1, dphi1, dphi2);
+    float g = 0.5f * (f.wnx * (duE - duW) + f.wny * (duN - duS));       // VectorField.pde:51
+    tmp[q.nband_x + b] = v + f.del1 * g;
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < q.nband_x; b += blockDim.x) ux[IDX(q.band_x[b].i, q.band_x[b].j)] = tmp[b];
+  for (int b = threadIdx.x; b < q.nband_y; b += blockDim.x) uy[IDX(q.band_y[b].i, q.band_y[b].j)] = tmp[q.nband_x + b];
+  __syncthreads();
+  cta_setBC(ux, q.n, q.m, P, 1, 1.f, true, scol);     // u.x: btype 1, bval 1, gradientExit (BDIM.pde:52)
+  cta_setBC(uy, q.n, q.m, P, 2, 0.f, false, scol);
+}
+
+__global__ void __launch_bounds__(1024)
+k_bc(const __grid_constant__ SolverParams q, float* ux_all, float* uy_all) {
+  extern __shared__ float scol[];
+  const int e = blockIdx.x;
+  cta_setBC(ux_all + (size_t)e * q.stride, q.n, q.m, q.P, 1, 1.f, true, scol);
+  cta_setBC(uy_all + (size_t)e * q.stride, q.n, q.m, q.P, 2, 0.f, false, scol);
+}
+
+// ------------------------------------------------------------------------------------------------
+// residual r = div(u) - A p   (VectorField.pde:56-65, PoissonMatrix.pde:53-68); also opens the solve
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float apply_A(const float* x, const float* __restrict__ lx, const float* __restrict__ ly,
+                                         const float* __restrict__ diag, int P, int k) {
+  return x[k] * diag[k] + x[k - P] * lx[k] + x[k + P] * lx[k + P] + x[k - 1] * ly[k] + x[k + 1] * ly[k + 1];
+}
+
+__global__ void __launch_bounds__(256)
+k_residual(const __grid_constant__ SolverParams q, const float* __restrict__ ux_all, const float* __restrict__ uy_all,
+           float* __restrict__ r_all, int which) {
+  const int P = q.P;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  const int e = blockIdx.z;
+  if (i == 0 && j == 0) { q.sc.active[e] = 1; q.sc.iters[2 * e + which] = 0; }
+  if (i < 1 || j < 1 || i > q.n - 2 || j > q.m - 2) return;
+  const size_t eo = (size_t)e * q.stride;
+  const float* ux = ux_all + eo;
+  const float* uy = uy_all + eo;
+  const float* p = q.lev[0].x + eo;
+  const int k = IDX(i, j);
+  float s = ux[k + P] - ux[k] + uy[k + 1] - uy[k];
+  r_all[eo + k] = s - apply_A(p, q.lev[0].lx, q.lev[0].ly, q.lev[0].diag, P, k);
+}
+
+// ------------------------------------------------------------------------------------------------
+// level 0, down: smooth(0) -> d = r*inv, d.setBC, x += d, r -= A d; then restrict r (MG.pde:68-70)
+// one thread per coarse cell = 2x2 fine block
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_mg_down0(const __grid_constant__ SolverParams q, const float* __restrict__ rin_all, float* __restrict__ rout_all) {
+  const int e = blockIdx.z;
+  if (!q.sc.active[e]) return;
+  const DevLevel& L0 = q.lev[0];
+  const DevLevel& L1 = q.lev[1];
+  const int P = L0.P, n = L0.n, m = L0.m;
+  const int J = blockIdx.x * blockDim.x + threadIdx.x + 1;   // coarse interior indices
+  const int I = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (I > L1.n - 2 || J > L1.m - 2) return;
+  const size_t eo = (size_t)e * L0.stride;
+  const float* rin = rin_all + eo;
+  float* rout = rout_all + eo;
+  float* x = L0.x + eo;
+  const int i0 = (I - 1) * 2 + 1, j0 = (J - 1) * 2 + 1;
+  // d on the 4x4 neighbourhood (corners unused), ghost = clamped interior (d.setBC, btype 0)
+  float d[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      if ((a == 0 || a == 3) && (b == 0 || b == 3)) { d[a][b] = 0.f; continue; }
+      int ci = min(max(i0 - 1 + a, 1), n - 2), cj = min(max(j0 - 1 + b, 1), m - 2);
+      d[a][b] = rin[IDX(ci, cj)] * L0.inv[IDX(ci, cj)];
+    }
+  float rn[2][2];
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      const int i = i0 + a, j = j0 + b, k = IDX(i, j);
+      const float dc = d[a + 1][b + 1];
+      float Ad = dc * L0.diag[k] + d[a][b + 1] * L0.lx[k] + d[a + 2][b + 1] * L0.lx[k + P] + d[a + 1][b] * L0.ly[k] +
+                 d[a + 1][b + 2] * L0.ly[k + 1];
+      rn[a][b] = rin[k] - Ad;
+      rout[k] = rn[a][b];
+      x[k] += dc;
+      // ghosts of x receive the clamped d (x.plusEq(d) runs over all cells, MG.pde:95)
+      const int di = (i == 1) ? -1 : (i == n - 2 ? 1 : 0), dj = (j == 1) ? -1 : (j == m - 2 ? 1 : 0);
+      if (di) x[IDX(i + di, j)] += dc;
+      if (dj) x[IDX(i, j + dj)] += dc;
+      if (di && dj) x[IDX(i + di, j + dj)] += dc;
+    }
+  // MG.restrict(Field) MG.pde:128-133
+  L1.r[(size_t)e * L1.stride + I * L1.P + J] = rn[0][0] + rn[0][1] + rn[1][0] + rn[1][1];
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-wide building blocks for one level held in (L2-resident) global scratch
+// ------------------------------------------------------------------------------------------------
+__device__ void cta_bc0(float* a, int n, int m, int P) {   // Field.setBC, btype 0
+  for (int j = threadIdx.x; j < m; j += blockDim.x) { a[IDX(0, j)] = a[IDX(1, j)]; a[IDX(n - 1, j)] = a[IDX(n - 2, j)]; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { a[IDX(i, 0)] = a[IDX(i, 1)]; a[IDX(i, m - 1)] = a[IDX(i, m - 2)]; }
+  __syncthreads();
+}
+
+// d = r.times(A.inv) over all cells (MG.pde:80)
+__device__ void cta_dinit(float* d, const float* r, const float* __restrict__ inv, int n, int m, int P) {
+  for (int c = threadIdx.x; c < n * m; c += blockDim.x) {
+    int i = c / m, j = c - i * m;
+    d[IDX(i, j)] = r[IDX(i, j)] * inv[IDX(i, j)];
+  }
+  __syncthreads();
+}
+
+// MG.increment MG.pde:94-97 (x over all cells, r over the interior; A d is 0 on ghosts)
+__device__ void cta_increment(const DevLevel& L, float* x, float* r, const float* d, bool x_zero, bool update_r) {
+  const int n = L.n, m = L.m, P = L.P;
+  for (int c = threadIdx.x; c < n * m; c += blockDim.x) {
+    int i = c / m, j = c - i * m, k = IDX(i, j);
+    x[k] = (x_zero ? 0.f : x[k]) + d[k];
+    if (update_r && i >= 1 && j >= 1 && i <= n - 2 && j <= m - 2) r[k] -= apply_A(d, L.lx, L.ly, L.diag, P, k);
+  }
+  __syncthreads();
+}
+
+// itmx in-place lexicographic Gauss-Seidel sweeps (MG.pde:81-89) as anti-diagonal wavefronts: cells
+// with equal i+j are independent; sweep s trails sweep s-1 by two diagonals, so all four sweeps run
+// concurrently and every cell sees exactly the operands the serial i-outer/j-inner loop gives it.
+__device__ void cta_gs(const DevLevel& L, float* d, const float* r, int sweeps) {
+  const int n = L.n, m = L.m, P = L.P;
+  const int ni = n - 2, mj = m - 2, W = min(ni, mj), nd = ni + mj - 1;
+  const float* __restrict__ lx = L.lx;
+  const float* __restrict__ ly = L.ly;
+  const float* __restrict__ inv = L.inv;
+  const int steps = nd + 2 * (sweeps - 1);
+  for (int step = 0; step < steps; step++) {
+    for (int c = threadIdx.x; c < sweeps * W; c += blockDim.x) {
+      const int s = c / W, a = c - s * W;
+      const int qd = step - 2 * s;
+      if (qd < 0 || qd >= nd) continue;
+      const int ii = max(0, qd - (mj - 1)) + a;
+      if (ii > min(ni - 1, qd)) continue;
+      const int i = ii + 1, j = qd - ii + 1, k = IDX(i, j);
+      d[k] = -(d[k - P] * lx[k] + d[k + P] * lx[k + P] + d[k - 1] * ly[k] + d[k + 1] * ly[k + 1] - r[k]) * inv[k];
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// levels >= 1: the rest of the V-cycle, one CTA per environment (MG.pde:68-77)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_mg_coarse(const __grid_constant__ SolverParams q) {
+  const int e = blockIdx.x;
+  if (!q.sc.active[e]) return;
+  const int last = q.nlevels - 1;
+  // ---- down ----
+  for (int l = 1; l <= last; l++) {
+    const DevLevel& L = q.lev[l];
+    float* r = L.r + (size_t)e * L.stride;
+    float* x = L.x + (size_t)e * L.stride;
+    float* d = L.d + (size_t)e * L.stride;
+    cta_bc0(r, L.n, L.m, L.P);                     // restrict(Field) ends with b.setBC() (MG.pde:135)
+    if (l == last) break;
+    // smooth(0): d = r*inv; d.setBC(); increment (x starts at 0, MG.pde:56)
+    cta_dinit(d, r, L.inv, L.n, L.m, L.P);
+    cta_bc0(d, L.n, L.m, L.P);
+    cta_increment(L, x, r, d, true, true);
+    // restrict r -> next level interior (MG.pde:124-134)
+    const DevLevel& C = q.lev[l + 1];
+    float* rc = C.r + (size_t)e * C.stride;
+    const int P = L.P;
+    const int nci = C.n - 2, ncj = C.m - 2;
+    for (int c = threadIdx.x; c < nci * ncj; c += blockDim.x) {
+      int I = c / ncj + 1, J = c % ncj + 1;
+      int ii = (I - 1) * 2 + 1, jj = (J - 1) * 2 + 1;
+      rc[I * C.P + J] = r[IDX(ii, jj)] + r[IDX(ii, jj + 1)] + r[IDX(ii + 1, jj)] + r[IDX(ii + 1, jj + 1)];
+    }
+    __syncthreads();
+  }
+  // ---- coarsest level: smooth(its) only (MG.pde:72-73) ----
+  {
+    const DevLevel& L = q.lev[last];
+    float* r = L.r + (size_t)e * L.stride;
+    float* x = L.x + (size_t)e * L.stride;
+    float* d = L.d + (size_t)e * L.stride;
+    cta_dinit(d, r, L.inv, L.n, L.m, L.P);
+    cta_gs(L, d, r, 4);
+    cta_bc0(d, L.n, L.m, L.P);
+    cta_increment(L, x, r, d, true, false);
+  }
+  // ---- up: prolongate + increment, then smooth(its) (MG.pde:73-76) ----
+  for (int l = last - 1; l >= 1; l--) {
+    const DevLevel& L = q.lev[l];
+    const DevLevel& C = q.lev[l + 1];
+    float* r = L.r + (size_t)e * L.stride;
+    float* x = L.x + (size_t)e * L.stride;
+    float* d = L.d + (size_t)e * L.stride;
+    const float* xc = C.x + (size_t)e * C.stride;
+    const int n = L.n, m = L.m, P = L.P;
+    // d = prolongate(coarse.x) incl. its setBC: ghost = adjacent interior (MG.pde:139-152)
+    for (int c = threadIdx.x; c < n * m; c += blockDim.x) {
+      int i = c / m, j = c - i * m;
+      int ci = min(max(i, 1), n - 2), cj = min(max(j, 1), m - 2);
+      d[IDX(i, j)] = xc[((ci - 1) / 2 + 1) * C.P + ((cj - 1) / 2 + 1)];
+    }
+    __syncthreads();
+    cta_increment(L, x, r, d, false, true);
+    cta_dinit(d, r, L.inv, n, m, P);
+    cta_gs(L, d, r, 4);
+    cta_bc0(d, n, m, P);
+    cta_increment(L, x, r, d, false, false);       // the residual update is dead on coarse levels
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// level 0, up: d = prolongate(x1) (+setBC), x += d, r -= A d   (MG.pde:75-76)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_mg_up0(const __grid_constant__ SolverParams q, float* __restrict__ r_all) {
+  const int e = blockIdx.z;
+  if (!q.sc.active[e]) return;
+  const DevLevel& L0 = q.lev[0];
+  const DevLevel& L1 = q.lev[1];
+  const int P = L0.P, n = L0.n, m = L0.m;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= n || j >= m) return;
+  const float* xc = L1.x + (size_t)e * L1.stride;
+  const size_t eo = (size_t)e * L0.stride;
+  auto dval = [&](int a, int b) {
+    int ci = min(max(a, 1), n - 2), cj = min(max(b, 1), m - 2);
+    return xc[((ci - 1) / 2 + 1) * L1.P + ((cj - 1) / 2 + 1)];
+  };
+  const int k = IDX(i, j);
+  const float dc = dval(i, j);
+  L0.x[eo + k] += dc;
+  if (i >= 1 && j >= 1 && i <= n - 2 && j <= m - 2) {
+    float Ad = dc * L0.diag[k] + dval(i - 1, j) * L0.lx[k] + dval(i + 1, j) * L0.lx[k + P] + dval(i, j - 1) * L0.ly[k] +
+               dval(i, j + 1) * L0.ly[k + 1];
+    r_all[eo + k] -= Ad;
+  }
+}
+
+// level 0 smooth(4), part 1: d = r*inv, then the four Gauss-Seidel sweeps; one CTA per env
+__global__ void __launch_bounds__(1024)
+k_gs0(const __grid_constant__ SolverParams q, const float* r_all) {
+  const int e = blockIdx.x;
+  if (!q.sc.active[e]) return;
+  const DevLevel& L = q.lev[0];
+  const float* r = r_all + (size_t)e * L.stride;
+  float* d = L.d + (size_t)e * L.stride;
+  cta_dinit(d, r, L.inv, L.n, L.m, L.P);
+  cta_gs(L, d, r, 4);
+}
+
+// level 0 smooth(4), part 2: d.setBC (clamped reads), x += d, r -= A d, partial sums of r.r
+__global__ void __launch_bounds__(256)
+k_inc0(const __grid_constant__ SolverParams q, float* __restrict__ r_all) {
+  const int e = blockIdx.z;
+  if (!q.sc.active[e]) return;
+  const DevLevel& L0 = q.lev[0];
+  const int P = L0.P, n = L0.n, m = L0.m;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  const size_t eo = (size_t)e * L0.stride;
+  const float* d = L0.d + eo;
+  double rr = 0.0;
+  if (i < n && j < m) {
+    auto dval = [&](int a, int b) { return d[IDX(min(max(a, 1), n - 2), min(max(b, 1), m - 2))]; };
+    const int k = IDX(i, j);
+    const float dc = dval(i, j);
+    L0.x[eo + k] += dc;
+    if (i >= 1 && j >= 1 && i <= n - 2 && j <= m - 2) {
+      float Ad = dc * L0.diag[k] + dval(i - 1, j) * L0.lx[k] + dval(i + 1, j) * L0.lx[k + P] +
+                 dval(i, j - 1) * L0.ly[k] + dval(i, j + 1) * L0.ly[k + 1];
+      float rn = r_all[eo + k] - Ad;
+      r_all[eo + k] = rn;
+      float prod = rn * rn;                       // float product, double accumulation (Field.pde:304-307)
+      rr = (double)prod;
+    }
+  }
+  // deterministic block reduction
+  __shared__ double sred[256];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  sred[tid] = rr;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) sred[tid] += sred[tid + s];
+    __syncthreads();
+  }
+  if (tid == 0) q.sc.rr_part[(size_t)e * q.rr_blocks + blockIdx.y * gridDim.x + blockIdx.x] = sred[0];
+}
+
+// MGsolver loop test (MG.pde:32-35): iter++, stop when r.r < tol or iter reaches itmx
+__global__ void k_conv(const __grid_constant__ SolverParams q, int which, int itmx) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= q.B || !q.sc.active[e]) return;
+  double s = 0;
+  for (int b = 0; b < q.rr_blocks; b++) s += q.sc.rr_part[(size_t)e * q.rr_blocks + b];
+  const int it = ++q.sc.iters[2 * e + which];
+  if ((float)s < q.mg_tol || it >= itmx) q.sc.active[e] = 0;
+  else atomicExch(q.sc.any_active, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Field.sum (Field.pde:311-318): a serial float accumulation over the interior in i-major order.
+// One warp per env: lanes load 32 consecutive values (coalesced), every lane then replays the same
+// 32 dependent adds on broadcast values, so the chain is pure FADD latency.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+k_psum(const __grid_constant__ SolverParams q) {
+  const int e = blockIdx.x, lane = threadIdx.x;
+  const int P = q.P, n = q.n, m = q.m;
+  const float* p = q.lev[0].x + (size_t)e * q.stride;
+  const int len = m - 2, cpr = (len + 31) / 32, total = (n - 2) * cpr;   // chunks of 32 along a row
+  constexpr int G = 8;                                                  // chunks per prefetch group
+  auto load = [&](int g) -> float {
+    if (g >= total) return 0.f;
+    const int i = 1 + g / cpr, j = (g % cpr) * 32 + lane;
+    return (j < len) ? p[IDX(i, 1 + j)] : 0.f;
+  };
+  float cur[G], nxt[G];
+#pragma unroll
+  for (int u = 0; u < G; u++) cur[u] = load(u);
+  float s = 0.f;
+  for (int g0 = 0; g0 < total; g0 += G) {
+#pragma unroll
+    for (int u = 0; u < G; u++) nxt[u] = load(g0 + G + u);              // in flight during the add chain
+#pragma unroll
+    for (int u = 0; u < G; u++) {
+      const int g = g0 + u;
+      if (g < total) {
+        const int cnt = min(32, len - (g % cpr) * 32);
+        if (cnt == 32) {
+#pragma unroll
+          for (int l = 0; l < 32; l++) s += __shfl_sync(0xffffffffu, cur[u], l);
+        } else {
+          for (int l = 0; l < cnt; l++) s += __shfl_sync(0xffffffffu, cur[u], l);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < G; u++) cur[u] = nxt[u];
+  }
+  if (lane == 0) q.sc.psum[e] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// projection tail (VectorField.pde:136-139): p += -sum/N on all cells; dp = grad p with its setBC
+// (dp.x[1][*] = dp.y[*][1] = 0); u += c * (dp * -1) on the interior.  u.setBC follows in k_bc.
+// ------------------------------------------------------------------------------------------------
+// p must not be shifted in place while neighbouring blocks still read the unshifted values, so the
+// velocity correction (k_project_u) and the shift itself (k_shift_p) are separate passes
+__global__ void __launch_bounds__(256)
+k_project_u(const __grid_constant__ SolverParams q, float* __restrict__ ux_all, float* __restrict__ uy_all) {
+  const int P = q.P, n = q.n, m = q.m;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  const int e = blockIdx.z;
+  if (i < 1 || j < 1 || i > n - 2 || j > m - 2) return;
+  const size_t eo = (size_t)e * q.stride;
+  const float* p = q.lev[0].x + eo;
+  const float shift = -1 * q.sc.psum[e] / q.inv_cells;
+  const int k = IDX(i, j);
+  const float pc = p[k] + shift;
+  if (i >= 2) {
+    float dpx = pc - (p[k - P] + shift);
+    ux_all[eo + k] += q.c_x[k] * (dpx * -1);
+  }
+  if (j >= 2) {
+    float dpy = pc - (p[k - 1] + shift);
+    uy_all[eo + k] += q.c_y[k] * (dpy * -1);
+  }
+}
+__global__ void __launch_bounds__(256)
+k_shift_p(const __grid_constant__ SolverParams q) {
+  const int P = q.P;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  const int e = blockIdx.z;
+  if (i >= q.n || j >= q.m) return;
+  float* p = q.lev[0].x + (size_t)e * q.stride;
+  const float shift = -1 * q.sc.psum[e] / q.inv_cells;
+  p[IDX(i, j)] += shift;
+}
+
+// BDIM.update2: u.plusEq(us); u.timesEq(0.5) over all cells (BDIM.pde:95-96)
+__global__ void __launch_bounds__(256)
+k_heun(const float* __restrict__ ucx, const float* __restrict__ ucy, const float* __restrict__ ubx,
+       const float* __restrict__ uby, float* __restrict__ uax, float* __restrict__ uay, int n, int m, int P,
+       size_t stride) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= n || j >= m) return;
+  const size_t k = (size_t)blockIdx.z * stride + IDX(i, j);
+  uax[k] = (ucx[k] + ubx[k]) * 0.5f;
+  uay[k] = (ucy[k] + uby[k]) * 0.5f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// readout: pressForce on body 0 (serial edge-order accumulation), probes, time, draw() accumulation
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sample_linear(const float* a, int P, int i, int j, float s, float t) {
+  if (s == 0 && t == 0) return a[IDX(i, j)];                                     // Field.pde:184-185
+  return s * (t * a[IDX(i + 1, j + 1)] + (1 - t) * a[IDX(i + 1, j)]) + (1 - s) * (t * a[IDX(i, j + 1)] + (1 - t) * a[IDX(i, j)]);
+}
+
+__global__ void __launch_bounds__(64)
+k_force(const __grid_constant__ SolverParams q, int accumulate) {
+  const int e = blockIdx.x, tid = threadIdx.x, P = q.P;
+  const float* p = q.lev[0].x + (size_t)e * q.stride;
+  __shared__ float sx[64], sy[64];
+  if (tid < q.nforce) {
+    const ForcePt f = q.force_pts[tid];
+    float pdl = sample_linear(p, P, f.i, f.j, f.s, f.t) * f.l;                   // Body.pde:299
+    sx[tid] = pdl * f.nx;
+    sy[tid] = pdl * f.ny;
+  }
+  if (tid < q.nprobe) {
+    const SamplePt s = q.probe_pts[tid];
+    q.sc.probes[(size_t)e * q.nprobe + tid] = sample_linear(p, P, s.i, s.j, s.s, s.t);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float pvx = 0, pvy = 0;
+    for (int k = 0; k < q.nforce; k++) { pvx += sx[k]; pvy += sy[k]; }           // Body.pde:300
+    const float fx = pvx * -1, fy = pvy * -1;                                     // AFCCylinder.pde:58
+    q.sc.force[2 * e] = fx;
+    q.sc.force[2 * e + 1] = fy;
+    const float t = q.sc.t[e] + q.dt_over_res;                                    // AFCCylinder.pde:56
+    q.sc.t[e] = t;
+    if (accumulate && t > q.init_time) {                                          // clientCFD.pde:39-47
+      int cl = q.sc.callLearn[e] - 1;
+      float Cd = q.sc.Cd[e] + fx, Cl = q.sc.Cl[e] + fy;
+      if (cl <= 0) {
+        cl = q.substeps;
+        Cd = Cd / cl * 2 / q.resolution;
+        Cl = Cl / cl * 2 / q.resolution;
+        q.sc.obs[2 * e] = Cl;
+        q.sc.obs[2 * e + 1] = Cd;
+      }
+      q.sc.callLearn[e] = cl;
+      q.sc.Cd[e] = Cd;
+      q.sc.Cl[e] = Cl;
+    }
+  }
+}
+
+__global__ void k_set_actions(const __grid_constant__ SolverParams q, const float* __restrict__ act) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < 2 * q.B) q.sc.xi[k] = act[k];
+}
+
+// obs/reward/done of one RL step; reward = server/server.py:61-65 evaluated in double
+__global__ void k_emit_obs(const __grid_constant__ SolverParams q, const float* __restrict__ act, float* obs, float* reward,
+                           int* done) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= q.B) return;
+  const float Cl = q.sc.obs[2 * e], Cd = q.sc.obs[2 * e + 1];
+  if (obs) { obs[2 * e] = Cl; obs[2 * e + 1] = Cd; }
+  if (reward) {
+    double a1 = fabs((double)act[2 * e]), a2 = fabs((double)act[2 * e + 1]);
+    double pen = 3.141592653589793 * (1.0 / 8) * 0.0097 * (3.66 * 3.66 * 3.66) * (a1 * a1 * a1 + a2 * a2 * a2);
+    reward[e] = (float)(-(double)Cd - pen);
+  }
+  if (done) done[e] = q.sc.t[e] >= q.episode_time ? 1 : 0;
+}
+
+inline dim3 grid2d(int m, int n, int B, dim3 blk) { return dim3((m + blk.x - 1) / blk.x, (n + blk.y - 1) / blk.y, B); }
+
+}  // namespace
+
+// ================================================================================================
+// launch wrappers
+// ================================================================================================
+int launch_advdif(const SolverParams& q, const float* srcx, const float* srcy, const float* u0x, const float* u0y,
+                  float* dstx, float* dsty, cudaStream_t st) {
+  dim3 blk(32, 8);
+  k_advdif<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(srcx, srcy, u0x, u0y, dstx, dsty, q.n, q.m, q.P, q.stride, q.dt, q.nu);
+  return 1;
+}
+
+int launch_band_bc(const SolverParams& q, float* ux, float* uy, cudaStream_t st) {
+  k_band_bc<<<q.B, 1024, sizeof(float) * q.m, st>>>(q, ux, uy);
+  return 1;
+}
+
+int launch_bc(const SolverParams& q, float* ux, float* uy, cudaStream_t st) {
+  k_bc<<<q.B, 512, sizeof(float) * q.m, st>>>(q, ux, uy);
+  return 1;
+}
+
+int launch_residual(const SolverParams& q, const float* ux, const float* uy, float* r, int which, cudaStream_t st) {
+  dim3 blk(32, 8);
+  k_residual<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, ux, uy, r, which);
+  return 1;
+}
+
+int launch_mg_iteration(const SolverParams& q, float* r_in, float* r_out, int which, cudaStream_t st) {
+  int launches = 0;
+  cudaMemsetAsync(q.sc.any_active, 0, sizeof(int), st);
+  dim3 blk(32, 8);
+  const DevLevel& L1 = q.lev[1];
+  k_mg_down0<<<grid2d(L1.m - 2, L1.n - 2, q.B, blk), blk, 0, st>>>(q, r_in, r_out); launches++;
+  k_mg_coarse<<<q.B, 1024, 0, st>>>(q); launches++;
+  k_mg_up0<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, r_out); launches++;
+  {
+    const int W = min(q.n - 2, q.m - 2);
+    int threads = min(1024, ((4 * W + 31) / 32) * 32);
+    k_gs0<<<q.B, threads, 0, st>>>(q, r_out); launches++;
+  }
+  k_inc0<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, r_out); launches++;
+  k_conv<<<(q.B + 127) / 128, 128, 0, st>>>(q, which, q.mg_max_iters); launches++;
+  return launches;
+}
+
+int launch_psum(const SolverParams& q, cudaStream_t st) {
+  k_psum<<<q.B, 32, 0, st>>>(q);
+  return 1;
+}
+
+int launch_project(const SolverParams& q, float* ux, float* uy, cudaStream_t st) {
+  dim3 blk(32, 8);
+  k_project_u<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, ux, uy);
+  k_shift_p<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q);
+  return 2;
+}
+
+int launch_heun(const SolverParams& q, const float* ucx, const float* ucy, const float* ubx, const float* uby,
+                float* uax, float* uay, cudaStream_t st) {
+  dim3 blk(32, 8);
+  k_heun<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(ucx, ucy, ubx, uby, uax, uay, q.n, q.m, q.P, q.stride);
+  return 1;
+}
+
+int launch_force(const SolverParams& q, int accumulate, cudaStream_t st) {
+  k_force<<<q.B, 64, 0, st>>>(q, accumulate);
+  return 1;
+}
+
+int launch_set_actions(const SolverParams& q, const float* d_actions, cudaStream_t st) {
+  k_set_actions<<<(2 * q.B + 127) / 128, 128, 0, st>>>(q, d_actions);
+  return 1;
+}
+
+int launch_emit_obs(const SolverParams& q, const float* d_actions, float* d_obs, float* d_reward, int* d_done,
+                    cudaStream_t st) {
+  k_emit_obs<<<(q.B + 127) / 128, 128, 0, st>>>(q, d_actions, d_obs, d_reward, d_done);
+  return 1;
+}
+
+}  // namespace rlfc
