@@ -120,6 +120,13 @@ int  rlfc_env_num_levels(const rlfc_env *env);
    Needs no GPU; used by the CPU-side tests of the host logic. */
 int  rlfc_geometry_static(const rlfc_config *cfg, const char *name, int level, float *out,
                           int *n, int *m, int *nlevels);
+/* Per-kernel device timing with CUDA events on the handle's stream.  While profiling is on every
+   kernel launch is bracketed by an event pair; rlfc_env_get_profile(idx) returns the idx-th kernel's
+   name, accumulated milliseconds, launch count and its ALGORITHMIC bytes per launch (per-env arrays
+   only, one read per input / one write per output, whole batch); it returns 1 past the last entry. */
+int  rlfc_env_set_profiling(rlfc_env *env, int on);
+int  rlfc_env_get_profile(rlfc_env *env, int idx, char *name, int name_cap, double *ms_total,
+                          long long *launches, double *algorithmic_bytes_per_launch);
 /* The stream the handle enqueues on (cudaStream_t), for event timing by the caller. */
 void *rlfc_env_stream(rlfc_env *env);
 /* Number of kernel launches (incl. those inside replayed CUDA graphs) issued so far. */

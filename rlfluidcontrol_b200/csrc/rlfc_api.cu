@@ -55,6 +55,44 @@ struct rlfc_env {
   int *h_done = nullptr, *h_any = nullptr;
   long long launches = 0;
   long long mg_iter_launch_rounds = 0;
+  // optional per-kernel CUDA-event timing (rlfc_env_set_profiling)
+  bool profiling = false;
+  struct ProfRec { int id; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> event_pool;
+  struct ProfAgg { std::string name; double ms = 0; long long count = 0; double floats_per_cell = 0; };
+  std::vector<ProfAgg> prof;
+
+  int prof_id(const char* name, double floats_per_cell) {
+    for (size_t k = 0; k < prof.size(); k++) if (prof[k].name == name) return (int)k;
+    prof.push_back({name, 0.0, 0, floats_per_cell});
+    return (int)prof.size() - 1;
+  }
+  cudaEvent_t get_event() {
+    if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  // run one kernel launch, optionally bracketed by events on the handle's stream
+  template <typename F>
+  void run(const char* name, double floats_per_cell, F&& launch) {
+    if (!profiling) { launches += launch(); return; }
+    ProfRec r{prof_id(name, floats_per_cell), get_event(), get_event()};
+    cudaEventRecord(r.e0, stream);
+    launches += launch();
+    cudaEventRecord(r.e1, stream);
+    prof_recs.push_back(r);
+  }
+  void prof_collect() {
+    if (prof_recs.empty()) return;
+    cudaStreamSynchronize(stream);
+    for (auto& r : prof_recs) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, r.e0, r.e1);
+      prof[r.id].ms += ms; prof[r.id].count++;
+      event_pool.push_back(r.e0); event_pool.push_back(r.e1);
+    }
+    prof_recs.clear();
+  }
 
   template <typename T>
   int dmalloc(T** p, size_t count, bool zero = true) {
@@ -116,24 +154,32 @@ int broadcast_field(rlfc_env* E, float* batch, const float* one, const int* ids,
 }
 
 // ---- one MG-projected half step on velocity buffer U (BDIM.updateUP tail + VectorField.project) ----
+// The floats-per-interior-cell figures are each kernel's ALGORITHMIC traffic per env (SURVEY 8d
+// convention: per-env arrays only, one read per input and one write per output).
 int project(rlfc_env* E, float* Ux, float* Uy, int which) {
   SolverParams& sp = E->sp;
   cudaStream_t st = E->stream;
   float* r_in = sp.lev[0].r;
   float* r_out = sp.lev[0].r2;
-  E->launches += launch_residual(sp, Ux, Uy, r_in, which, st);
+  E->run("k_residual", 4, [&] { return launch_residual(sp, Ux, Uy, r_in, which, st); });
   for (int it = 0; it < sp.mg_max_iters; it++) {
-    E->launches += launch_mg_iteration(sp, r_in, r_out, which, st);
+    E->run("k_mg_down0", 4.25, [&] { return launch_mg_down0(sp, r_in, r_out, st); });
+    E->run("k_mg_coarse", 0.5, [&] { return launch_mg_coarse(sp, st); });
+    E->run("k_mg_up0", 4.25, [&] { return launch_mg_up0(sp, r_out, st); });
+    E->run("k_gs0", 2, [&] { return launch_gs0(sp, r_out, st); });
+    E->run("k_inc0", 5, [&] { return launch_inc0(sp, r_out, st); });
+    E->run("k_conv", 0, [&] { return launch_conv(sp, which, st); });
     std::swap(r_in, r_out);
-    // data-dependent loop exit (MG.pde:34): one 4-byte readback per extra iteration
+    // data-dependent loop exit (MG.pde:34): one 4-byte readback per iteration
     CU(cudaMemcpyAsync(E->h_any, sp.sc.any_active, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     E->mg_iter_launch_rounds++;
     if (!*E->h_any) break;
   }
-  E->launches += launch_psum(sp, st);
-  E->launches += launch_project(sp, Ux, Uy, st);
-  E->launches += launch_bc(sp, Ux, Uy, st);
+  E->run("k_psum", 1, [&] { return launch_psum(sp, st); });
+  E->run("k_project_u", 5, [&] { return launch_project_u(sp, Ux, Uy, st); });
+  E->run("k_shift_p", 2, [&] { return launch_shift_p(sp, st); });
+  E->run("k_bc", 0, [&] { return launch_bc(sp, Ux, Uy, st); });
   return RLFC_OK;
 }
 
@@ -143,15 +189,15 @@ int solver_step(rlfc_env* E, int accumulate) {
   cudaStream_t st = E->stream;
   int rc;
   // predictor BDIM.update(): u0 = u (buffer A), F = AdvDif(u) -> B, updateUP
-  E->launches += launch_advdif(sp, E->uAx, E->uAy, E->uAx, E->uAy, E->uBx, E->uBy, st);
-  E->launches += launch_band_bc(sp, E->uBx, E->uBy, st);
+  E->run("k_advdif", 5, [&] { return launch_advdif(sp, E->uAx, E->uAy, E->uAx, E->uAy, E->uBx, E->uBy, st); });
+  E->run("k_band_bc", 0, [&] { return launch_band_bc(sp, E->uBx, E->uBy, st); });
   if ((rc = project(E, E->uBx, E->uBy, 0))) return rc;
   // corrector BDIM.update2(): us = u (B), F = AdvDif(u; + u0) -> C, updateUP, u = (u + us)/2 -> A
-  E->launches += launch_advdif(sp, E->uBx, E->uBy, E->uAx, E->uAy, E->uCx, E->uCy, st);
-  E->launches += launch_band_bc(sp, E->uCx, E->uCy, st);
+  E->run("k_advdif", 5, [&] { return launch_advdif(sp, E->uBx, E->uBy, E->uAx, E->uAy, E->uCx, E->uCy, st); });
+  E->run("k_band_bc", 0, [&] { return launch_band_bc(sp, E->uCx, E->uCy, st); });
   if ((rc = project(E, E->uCx, E->uCy, 1))) return rc;
-  E->launches += launch_heun(sp, E->uCx, E->uCy, E->uBx, E->uBy, E->uAx, E->uAy, st);
-  E->launches += launch_force(sp, accumulate, st);
+  E->run("k_heun", 6, [&] { return launch_heun(sp, E->uCx, E->uCy, E->uBx, E->uBy, E->uAx, E->uAy, st); });
+  E->run("k_force", 0, [&] { return launch_force(sp, accumulate, st); });
   CU(cudaGetLastError());
   return RLFC_OK;
 }
@@ -203,6 +249,8 @@ void rlfc_env_destroy(rlfc_env* E) {
   if (!E) return;
   cudaSetDevice(E->device);
   if (E->stream) cudaStreamSynchronize(E->stream);
+  E->prof_collect();
+  for (cudaEvent_t ev : E->event_pool) cudaEventDestroy(ev);
   for (void* p : E->allocs) cudaFree(p);
   for (void* p : {(void*)E->h_actions, (void*)E->h_obs, (void*)E->h_reward, (void*)E->h_force, (void*)E->h_probes,
                   (void*)E->h_done, (void*)E->h_any})
@@ -560,6 +608,28 @@ int rlfc_geometry_static(const rlfc_config* cfg, const char* name, int level, fl
   if (rc) return fail(rc, err);
   if (nlevels) *nlevels = (int)g.levels.size();
   return static_lookup(g, name, level, out, n, m);
+}
+
+int rlfc_env_set_profiling(rlfc_env* E, int on) {
+  if (!E) return fail(RLFC_EINVAL, "null handle");
+  E->prof_collect();
+  E->profiling = on != 0;
+  if (on) for (auto& a : E->prof) { a.ms = 0; a.count = 0; }
+  return RLFC_OK;
+}
+
+int rlfc_env_get_profile(rlfc_env* E, int idx, char* name, int name_cap, double* ms_total, long long* launches,
+                         double* algorithmic_bytes_per_launch) {
+  if (!E) return fail(RLFC_EINVAL, "null handle");
+  E->prof_collect();
+  if (idx < 0 || idx >= (int)E->prof.size()) return 1;   // end of list
+  const auto& a = E->prof[idx];
+  if (name && name_cap > 0) { std::strncpy(name, a.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (ms_total) *ms_total = a.ms;
+  if (launches) *launches = a.count;
+  if (algorithmic_bytes_per_launch)
+    *algorithmic_bytes_per_launch = 4.0 * a.floats_per_cell * (double)(E->sp.n - 2) * (E->sp.m - 2) * E->sp.B;
+  return RLFC_OK;
 }
 
 void* rlfc_env_stream(rlfc_env* E) { return E ? (void*)E->stream : nullptr; }

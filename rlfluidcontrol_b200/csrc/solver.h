@@ -77,10 +77,17 @@ int launch_advdif(const SolverParams& P, const float* srcx, const float* srcy, c
                   float* dstx, float* dsty, cudaStream_t st);
 int launch_band_bc(const SolverParams& P, float* ux, float* uy, cudaStream_t st);
 int launch_residual(const SolverParams& P, const float* ux, const float* uy, float* r, int which, cudaStream_t st);
-// one MG iteration (V-cycle + smooth(4)) on active envs; r_in/r_out are the level-0 ping-pong buffers
-int launch_mg_iteration(const SolverParams& P, float* r_in, float* r_out, int which, cudaStream_t st);
+// one MG iteration (V-cycle + smooth(4)) on active envs = down0, coarse, up0, gs0, inc0, conv;
+// r_in/r_out are the level-0 ping-pong residual buffers
+int launch_mg_down0(const SolverParams& P, const float* r_in, float* r_out, cudaStream_t st);
+int launch_mg_coarse(const SolverParams& P, cudaStream_t st);
+int launch_mg_up0(const SolverParams& P, float* r, cudaStream_t st);
+int launch_gs0(const SolverParams& P, const float* r, cudaStream_t st);
+int launch_inc0(const SolverParams& P, float* r, cudaStream_t st);
+int launch_conv(const SolverParams& P, int which, cudaStream_t st);
 int launch_psum(const SolverParams& P, cudaStream_t st);
-int launch_project(const SolverParams& P, float* ux, float* uy, cudaStream_t st);
+int launch_project_u(const SolverParams& P, float* ux, float* uy, cudaStream_t st);
+int launch_shift_p(const SolverParams& P, cudaStream_t st);
 int launch_bc(const SolverParams& P, float* ux, float* uy, cudaStream_t st);
 int launch_heun(const SolverParams& P, const float* ucx, const float* ucy, const float* ubx, const float* uby,
                 float* uax, float* uay, cudaStream_t st);

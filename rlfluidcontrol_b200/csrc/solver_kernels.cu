@@ -16,7 +16,8 @@
 //   k_inc0        level-0 d.setBC + increment + partial r.r              MG.pde:90-97, Field.pde:302-310
 //   k_conv        r.r < tol test, per-env iteration bookkeeping          MG.pde:30-38
 //   k_psum        serial float interior sum of p                        Field.pde:311-318
-//   k_project     mean shift, gradient, velocity correction             VectorField.pde:136-139
+//   k_project_u   gradient of the mean-shifted p, velocity correction   VectorField.pde:136-139
+//   k_shift_p     p += -sum(p)/N on all cells                            VectorField.pde:136
 //   k_bc          u.setBC after the projection                          VectorField.pde:140
 //   k_heun        u = (u + us) * 0.5                                     BDIM.pde:95-96
 //   k_force       pressForce + probes + time + draw() accumulation       Body.pde:296-303, SaveScalar.pde:61-72, clientCFD.pde:39-47
@@ -671,22 +672,41 @@ int launch_residual(const SolverParams& q, const float* ux, const float* uy, flo
   return 1;
 }
 
-int launch_mg_iteration(const SolverParams& q, float* r_in, float* r_out, int which, cudaStream_t st) {
-  int launches = 0;
+int launch_mg_down0(const SolverParams& q, const float* r_in, float* r_out, cudaStream_t st) {
   cudaMemsetAsync(q.sc.any_active, 0, sizeof(int), st);
   dim3 blk(32, 8);
   const DevLevel& L1 = q.lev[1];
-  k_mg_down0<<<grid2d(L1.m - 2, L1.n - 2, q.B, blk), blk, 0, st>>>(q, r_in, r_out); launches++;
-  k_mg_coarse<<<q.B, 1024, 0, st>>>(q); launches++;
-  k_mg_up0<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, r_out); launches++;
-  {
-    const int W = min(q.n - 2, q.m - 2);
-    int threads = min(1024, ((4 * W + 31) / 32) * 32);
-    k_gs0<<<q.B, threads, 0, st>>>(q, r_out); launches++;
-  }
-  k_inc0<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, r_out); launches++;
-  k_conv<<<(q.B + 127) / 128, 128, 0, st>>>(q, which, q.mg_max_iters); launches++;
-  return launches;
+  k_mg_down0<<<grid2d(L1.m - 2, L1.n - 2, q.B, blk), blk, 0, st>>>(q, r_in, r_out);
+  return 1;
+}
+
+int launch_mg_coarse(const SolverParams& q, cudaStream_t st) {
+  k_mg_coarse<<<q.B, 1024, 0, st>>>(q);
+  return 1;
+}
+
+int launch_mg_up0(const SolverParams& q, float* r, cudaStream_t st) {
+  dim3 blk(32, 8);
+  k_mg_up0<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, r);
+  return 1;
+}
+
+int launch_gs0(const SolverParams& q, const float* r, cudaStream_t st) {
+  const int W = min(q.n - 2, q.m - 2);
+  int threads = min(1024, ((4 * W + 31) / 32) * 32);
+  k_gs0<<<q.B, threads, 0, st>>>(q, r);
+  return 1;
+}
+
+int launch_inc0(const SolverParams& q, float* r, cudaStream_t st) {
+  dim3 blk(32, 8);
+  k_inc0<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, r);
+  return 1;
+}
+
+int launch_conv(const SolverParams& q, int which, cudaStream_t st) {
+  k_conv<<<(q.B + 127) / 128, 128, 0, st>>>(q, which, q.mg_max_iters);
+  return 1;
 }
 
 int launch_psum(const SolverParams& q, cudaStream_t st) {
@@ -694,11 +714,16 @@ int launch_psum(const SolverParams& q, cudaStream_t st) {
   return 1;
 }
 
-int launch_project(const SolverParams& q, float* ux, float* uy, cudaStream_t st) {
+int launch_project_u(const SolverParams& q, float* ux, float* uy, cudaStream_t st) {
   dim3 blk(32, 8);
   k_project_u<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, ux, uy);
+  return 1;
+}
+
+int launch_shift_p(const SolverParams& q, cudaStream_t st) {
+  dim3 blk(32, 8);
   k_shift_p<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q);
-  return 2;
+  return 1;
 }
 
 int launch_heun(const SolverParams& q, const float* ucx, const float* ucy, const float* ubx, const float* uby,

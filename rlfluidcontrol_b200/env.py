@@ -72,6 +72,9 @@ def load_library():
     L.rlfc_env_get_static.argtypes = [vp, C.c_char_p, C.c_int, fp, ip, ip]
     L.rlfc_geometry_static.argtypes = [C.POINTER(Config), C.c_char_p, C.c_int, fp, ip, ip, ip]
     L.rlfc_env_num_levels.argtypes = [vp]
+    L.rlfc_env_set_profiling.argtypes = [vp, C.c_int]
+    L.rlfc_env_get_profile.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double),
+                                       C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
     L.rlfc_env_stream.argtypes = [vp]
     L.rlfc_env_stream.restype = vp
     L.rlfc_env_launch_count.argtypes = [vp]
@@ -211,6 +214,23 @@ class AFCCylinderBatch:
         self._check(self._L.rlfc_env_get_static(self._h, name.encode(), level, None, C.byref(n), C.byref(m)), "rlfc_env_get_static")
         out = np.empty((n.value, m.value), np.float32)
         self._check(self._L.rlfc_env_get_static(self._h, name.encode(), level, _fp(out), None, None), "rlfc_env_get_static")
+        return out
+
+    def set_profiling(self, on=True):
+        self._check(self._L.rlfc_env_set_profiling(self._h, int(on)), "rlfc_env_set_profiling")
+
+    def get_profile(self):
+        """[{name, ms, launches, bytes_per_launch}] accumulated since profiling was switched on."""
+        out, idx = [], 0
+        while True:
+            name = C.create_string_buffer(64)
+            ms, cnt, by = C.c_double(), C.c_longlong(), C.c_double()
+            rc = self._L.rlfc_env_get_profile(self._h, idx, name, 64, C.byref(ms), C.byref(cnt), C.byref(by))
+            if rc == 1:
+                break
+            self._check(rc, "rlfc_env_get_profile")
+            out.append(dict(name=name.value.decode(), ms=ms.value, launches=cnt.value, bytes_per_launch=by.value))
+            idx += 1
         return out
 
     @property
