@@ -338,6 +338,26 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     TRY(upload_static(E, H.ly, H.n, H.m, L.P, &L.ly));
     TRY(upload_static(E, H.inv, H.n, H.m, L.P, &L.inv));
     TRY(upload_static(E, H.diag, H.n, H.m, L.P, &L.diag));
+    {  // pre-skewed coefficient tables for the strip smoother (layout: solver.h SkewLevel)
+      const int ni = H.n - 2, mj = H.m - 2;
+      const int ns = (mj + 31) / 32, Tsk = 16 /*kSkewPad*/ + ni + 64 /*kSkewTail*/;
+      if (ns > 8) return bail(fail(RLFC_EGRID, "grids wider than 256 cells are not supported by the strip smoother yet"));
+      std::vector<float4> A((size_t)ns * Tsk * 32, make_float4(0.f, 0.f, 0.f, 0.f));
+      std::vector<float> ninv((size_t)ns * Tsk * 32, 0.f);
+      for (int k = 0; k < ns; k++)
+        for (int tp = 0; tp < Tsk; tp++)
+          for (int l = 0; l < 32; l++) {
+            const int tau = tp - 16, i = tau - l + 1, j = 32 * k + l + 1;
+            if (i < 1 || i > ni || j > mj) continue;
+            const size_t c = (size_t)i * H.m + j, o = ((size_t)k * Tsk + tp) * 32 + l;
+            A[o] = make_float4(H.lx[c], H.lx[c + H.m], H.ly[c], H.ly[c + 1]);
+            ninv[o] = -H.inv[c];
+          }
+      L.sk.nstrips = ns; L.sk.Tsk = Tsk;
+      TRY(upload_vec(E, A, &L.sk.A));
+      TRY(upload_vec(E, ninv, &L.sk.ninv));
+      if (l >= 1) sp.coarse_strips = std::max(sp.coarse_strips, ns);
+    }
     TRY(E->dmalloc(&L.r, L.stride * B));
     TRY(E->dmalloc(&L.x, L.stride * B));
     TRY(E->dmalloc(&L.d, L.stride * B));

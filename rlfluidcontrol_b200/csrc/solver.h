@@ -16,7 +16,18 @@ namespace rlfc {
 
 constexpr int kMaxLevels = 16;
 
+// Pre-skewed static coefficient tables of one level for the strip smoother (smooth_strip.cuh):
+// entry [(k*Tsk + tau + kSkewPad)*32 + lane] belongs to cell (i = tau - lane + 1, j = 32k + lane + 1).
+struct SkewLevel {
+  const float4* A;          // (lx[i][j], lx[i+1][j], ly[i][j], ly[i][j+1])
+  const float* ninv;        // -inv[i][j]
+  int nstrips, Tsk;
+};
+
+#define IDX(i, j) ((i) * P + (j))
+
 struct DevLevel {
+  SkewLevel sk;
   int n, m, P;              // dims incl. ghosts, pitch
   size_t stride;            // per-env stride (floats) of r/x/d at this level
   const float *lx, *ly, *inv, *diag;   // static, pitched
@@ -57,6 +68,7 @@ struct SolverParams {
   float inv_cells;          // (float)((n-2)*(m-2))
   float mg_tol;
   int   nlevels;
+  int   coarse_strips;      // max strip count over levels >= 1 (warps of k_mg_coarse)
   int   resolution, substeps, mg_max_iters;
   float init_time, episode_time;
   DevLevel lev[kMaxLevels];

@@ -22,11 +22,10 @@
 //   k_heun        u = (u + us) * 0.5                                     BDIM.pde:95-96
 //   k_force       pressForce + probes + time + draw() accumulation       Body.pde:296-303, SaveScalar.pde:61-72, clientCFD.pde:39-47
 #include "solver.h"
+#include "smooth_strip.cuh"
 
 namespace rlfc {
 namespace {
-
-#define IDX(i, j) ((i) * P + (j))
 
 __device__ __forceinline__ float pmin(float a, float b) { return (a < b) ? a : b; }   // PApplet.min
 __device__ __forceinline__ float pmax(float a, float b) { return (a > b) ? a : b; }   // PApplet.max
@@ -217,25 +216,16 @@ k_residual(const __grid_constant__ SolverParams q, const float* __restrict__ ux_
 }
 
 // ------------------------------------------------------------------------------------------------
-// level 0, down: smooth(0) -> d = r*inv, d.setBC, x += d, r -= A d; then restrict r (MG.pde:68-70)
-// one thread per coarse cell = 2x2 fine block
+// down pass of one level, one thread per coarse cell = 2x2 fine block (MG.pde:68-70):
+//   smooth(0): d = r*inv, d.setBC (ghost = clamped interior), x += d, r -= A d;  then restrict r.
+// `rin` is read with its 4x4 neighbourhood, so the new residual goes to a different buffer `rout`.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_mg_down0(const __grid_constant__ SolverParams q, const float* __restrict__ rin_all, float* __restrict__ rout_all) {
-  const int e = blockIdx.z;
-  if (!q.sc.active[e]) return;
-  const DevLevel& L0 = q.lev[0];
-  const DevLevel& L1 = q.lev[1];
-  const int P = L0.P, n = L0.n, m = L0.m;
-  const int J = blockIdx.x * blockDim.x + threadIdx.x + 1;   // coarse interior indices
-  const int I = blockIdx.y * blockDim.y + threadIdx.y + 1;
-  if (I > L1.n - 2 || J > L1.m - 2) return;
-  const size_t eo = (size_t)e * L0.stride;
-  const float* rin = rin_all + eo;
-  float* rout = rout_all + eo;
-  float* x = L0.x + eo;
+template <bool LEVEL0>
+__device__ __forceinline__ void down_block(const DevLevel& L, const DevLevel& C, const float* __restrict__ rin,
+                                           float* __restrict__ rout, float* __restrict__ x, float* __restrict__ rc,
+                                           int I, int J) {
+  const int P = L.P, n = L.n, m = L.m;
   const int i0 = (I - 1) * 2 + 1, j0 = (J - 1) * 2 + 1;
-  // d on the 4x4 neighbourhood (corners unused), ghost = clamped interior (d.setBC, btype 0)
   float d[4][4];
 #pragma unroll
   for (int a = 0; a < 4; a++)
@@ -243,7 +233,7 @@ k_mg_down0(const __grid_constant__ SolverParams q, const float* __restrict__ rin
     for (int b = 0; b < 4; b++) {
       if ((a == 0 || a == 3) && (b == 0 || b == 3)) { d[a][b] = 0.f; continue; }
       int ci = min(max(i0 - 1 + a, 1), n - 2), cj = min(max(j0 - 1 + b, 1), m - 2);
-      d[a][b] = rin[IDX(ci, cj)] * L0.inv[IDX(ci, cj)];
+      d[a][b] = rin[IDX(ci, cj)] * L.inv[IDX(ci, cj)];
     }
   float rn[2][2];
 #pragma unroll
@@ -252,139 +242,90 @@ k_mg_down0(const __grid_constant__ SolverParams q, const float* __restrict__ rin
     for (int b = 0; b < 2; b++) {
       const int i = i0 + a, j = j0 + b, k = IDX(i, j);
       const float dc = d[a + 1][b + 1];
-      float Ad = dc * L0.diag[k] + d[a][b + 1] * L0.lx[k] + d[a + 2][b + 1] * L0.lx[k + P] + d[a + 1][b] * L0.ly[k] +
-                 d[a + 1][b + 2] * L0.ly[k + 1];
+      float Ad = dc * L.diag[k] + d[a][b + 1] * L.lx[k] + d[a + 2][b + 1] * L.lx[k + P] + d[a + 1][b] * L.ly[k] +
+                 d[a + 1][b + 2] * L.ly[k + 1];
       rn[a][b] = rin[k] - Ad;
       rout[k] = rn[a][b];
-      x[k] += dc;
-      // ghosts of x receive the clamped d (x.plusEq(d) runs over all cells, MG.pde:95)
-      const int di = (i == 1) ? -1 : (i == n - 2 ? 1 : 0), dj = (j == 1) ? -1 : (j == m - 2 ? 1 : 0);
-      if (di) x[IDX(i + di, j)] += dc;
-      if (dj) x[IDX(i, j + dj)] += dc;
-      if (di && dj) x[IDX(i + di, j + dj)] += dc;
+      if (LEVEL0) {
+        x[k] += dc;
+        // ghosts of x receive the clamped d (x.plusEq(d) runs over all cells, MG.pde:95); p's ghosts are live data
+        const int di = (i == 1) ? -1 : (i == n - 2 ? 1 : 0), dj = (j == 1) ? -1 : (j == m - 2 ? 1 : 0);
+        if (di) x[IDX(i + di, j)] += dc;
+        if (dj) x[IDX(i, j + dj)] += dc;
+        if (di && dj) x[IDX(i + di, j + dj)] += dc;
+      } else {
+        x[k] = 0.f + dc;   // coarse x starts at 0 (MG.pde:56); its ghosts are never read (prolongate's setBC overwrites them)
+      }
     }
-  // MG.restrict(Field) MG.pde:128-133
-  L1.r[(size_t)e * L1.stride + I * L1.P + J] = rn[0][0] + rn[0][1] + rn[1][0] + rn[1][1];
+  // MG.restrict(Field) MG.pde:128-133 (its setBC only fills ghosts, which no later operation reads with a non-zero weight)
+  rc[I * C.P + J] = rn[0][0] + rn[0][1] + rn[1][0] + rn[1][1];
+}
+
+__global__ void __launch_bounds__(256)
+k_mg_down0(const __grid_constant__ SolverParams q, const float* __restrict__ rin_all, float* __restrict__ rout_all) {
+  const int e = blockIdx.z;
+  if (!q.sc.active[e]) return;
+  const DevLevel& L0 = q.lev[0];
+  const DevLevel& L1 = q.lev[1];
+  const int J = blockIdx.x * blockDim.x + threadIdx.x + 1;   // coarse interior indices
+  const int I = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (I > L1.n - 2 || J > L1.m - 2) return;
+  const size_t eo = (size_t)e * L0.stride;
+  down_block<true>(L0, L1, rin_all + eo, rout_all + eo, L0.x + eo, L1.r + (size_t)e * L1.stride, I, J);
 }
 
 // ------------------------------------------------------------------------------------------------
-// CTA-wide building blocks for one level held in (L2-resident) global scratch
+// levels >= 1: the rest of the V-cycle, one CTA per environment (MG.pde:68-77).  Per level the residual
+// ping-pongs between the level's `r` and `d` arrays: down writes the smoothed residual to `d`, the
+// up pass updates it in place and the strip smoother consumes it, adding its result straight into x.
+// Ghost cells of the coarse r and x are never materialised: every reference read of them is either
+// overwritten by a setBC before use or multiplied by a boundary coefficient that is 0 on coarse levels.
 // ------------------------------------------------------------------------------------------------
-__device__ void cta_bc0(float* a, int n, int m, int P) {   // Field.setBC, btype 0
-  for (int j = threadIdx.x; j < m; j += blockDim.x) { a[IDX(0, j)] = a[IDX(1, j)]; a[IDX(n - 1, j)] = a[IDX(n - 2, j)]; }
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) { a[IDX(i, 0)] = a[IDX(i, 1)]; a[IDX(i, m - 1)] = a[IDX(i, m - 2)]; }
-  __syncthreads();
-}
-
-// d = r.times(A.inv) over all cells (MG.pde:80)
-__device__ void cta_dinit(float* d, const float* r, const float* __restrict__ inv, int n, int m, int P) {
-  for (int c = threadIdx.x; c < n * m; c += blockDim.x) {
-    int i = c / m, j = c - i * m;
-    d[IDX(i, j)] = r[IDX(i, j)] * inv[IDX(i, j)];
-  }
-  __syncthreads();
-}
-
-// MG.increment MG.pde:94-97 (x over all cells, r over the interior; A d is 0 on ghosts)
-__device__ void cta_increment(const DevLevel& L, float* x, float* r, const float* d, bool x_zero, bool update_r) {
-  const int n = L.n, m = L.m, P = L.P;
-  for (int c = threadIdx.x; c < n * m; c += blockDim.x) {
-    int i = c / m, j = c - i * m, k = IDX(i, j);
-    x[k] = (x_zero ? 0.f : x[k]) + d[k];
-    if (update_r && i >= 1 && j >= 1 && i <= n - 2 && j <= m - 2) r[k] -= apply_A(d, L.lx, L.ly, L.diag, P, k);
-  }
-  __syncthreads();
-}
-
-// itmx in-place lexicographic Gauss-Seidel sweeps (MG.pde:81-89) as anti-diagonal wavefronts: cells
-// with equal i+j are independent; sweep s trails sweep s-1 by two diagonals, so all four sweeps run
-// concurrently and every cell sees exactly the operands the serial i-outer/j-inner loop gives it.
-__device__ void cta_gs(const DevLevel& L, float* d, const float* r, int sweeps) {
-  const int n = L.n, m = L.m, P = L.P;
-  const int ni = n - 2, mj = m - 2, W = min(ni, mj), nd = ni + mj - 1;
-  const float* __restrict__ lx = L.lx;
-  const float* __restrict__ ly = L.ly;
-  const float* __restrict__ inv = L.inv;
-  const int steps = nd + 2 * (sweeps - 1);
-  for (int step = 0; step < steps; step++) {
-    for (int c = threadIdx.x; c < sweeps * W; c += blockDim.x) {
-      const int s = c / W, a = c - s * W;
-      const int qd = step - 2 * s;
-      if (qd < 0 || qd >= nd) continue;
-      const int ii = max(0, qd - (mj - 1)) + a;
-      if (ii > min(ni - 1, qd)) continue;
-      const int i = ii + 1, j = qd - ii + 1, k = IDX(i, j);
-      d[k] = -(d[k - P] * lx[k] + d[k + P] * lx[k + P] + d[k - 1] * ly[k] + d[k + 1] * ly[k + 1] - r[k]) * inv[k];
-    }
-    __syncthreads();
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// levels >= 1: the rest of the V-cycle, one CTA per environment (MG.pde:68-77)
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(128)
 k_mg_coarse(const __grid_constant__ SolverParams q) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  StripShared* sh = reinterpret_cast<StripShared*>(smem_raw);
+  StripMail* mail = reinterpret_cast<StripMail*>(smem_raw + sizeof(StripShared) * q.coarse_strips);
   const int e = blockIdx.x;
   if (!q.sc.active[e]) return;
   const int last = q.nlevels - 1;
-  // ---- down ----
-  for (int l = 1; l <= last; l++) {
+  // ---- down: smooth(0) + restrict ----
+  for (int l = 1; l < last; l++) {
     const DevLevel& L = q.lev[l];
-    float* r = L.r + (size_t)e * L.stride;
-    float* x = L.x + (size_t)e * L.stride;
-    float* d = L.d + (size_t)e * L.stride;
-    cta_bc0(r, L.n, L.m, L.P);                     // restrict(Field) ends with b.setBC() (MG.pde:135)
-    if (l == last) break;
-    // smooth(0): d = r*inv; d.setBC(); increment (x starts at 0, MG.pde:56)
-    cta_dinit(d, r, L.inv, L.n, L.m, L.P);
-    cta_bc0(d, L.n, L.m, L.P);
-    cta_increment(L, x, r, d, true, true);
-    // restrict r -> next level interior (MG.pde:124-134)
     const DevLevel& C = q.lev[l + 1];
-    float* rc = C.r + (size_t)e * C.stride;
-    const int P = L.P;
     const int nci = C.n - 2, ncj = C.m - 2;
-    for (int c = threadIdx.x; c < nci * ncj; c += blockDim.x) {
-      int I = c / ncj + 1, J = c % ncj + 1;
-      int ii = (I - 1) * 2 + 1, jj = (J - 1) * 2 + 1;
-      rc[I * C.P + J] = r[IDX(ii, jj)] + r[IDX(ii, jj + 1)] + r[IDX(ii + 1, jj)] + r[IDX(ii + 1, jj + 1)];
-    }
+    const size_t eo = (size_t)e * L.stride;
+    for (int c = threadIdx.x; c < nci * ncj; c += blockDim.x)
+      down_block<false>(L, C, L.r + eo, L.d + eo, L.x + eo, C.r + (size_t)e * C.stride, c / ncj + 1, c % ncj + 1);
     __syncthreads();
   }
-  // ---- coarsest level: smooth(its) only (MG.pde:72-73) ----
+  // ---- coarsest level: smooth(its) only (MG.pde:72-73), x = 0 + d ----
   {
     const DevLevel& L = q.lev[last];
-    float* r = L.r + (size_t)e * L.stride;
-    float* x = L.x + (size_t)e * L.stride;
-    float* d = L.d + (size_t)e * L.stride;
-    cta_dinit(d, r, L.inv, L.n, L.m, L.P);
-    cta_gs(L, d, r, 4);
-    cta_bc0(d, L.n, L.m, L.P);
-    cta_increment(L, x, r, d, true, false);
+    strip_smooth<1>(L, L.r + (size_t)e * L.stride, L.x + (size_t)e * L.stride, sh, mail);
   }
-  // ---- up: prolongate + increment, then smooth(its) (MG.pde:73-76) ----
+  // ---- up: d = prolongate(coarse.x), x += d, r -= A d, then smooth(its): x += GS(r)  (MG.pde:73-76) ----
   for (int l = last - 1; l >= 1; l--) {
     const DevLevel& L = q.lev[l];
     const DevLevel& C = q.lev[l + 1];
-    float* r = L.r + (size_t)e * L.stride;
-    float* x = L.x + (size_t)e * L.stride;
-    float* d = L.d + (size_t)e * L.stride;
+    const size_t eo = (size_t)e * L.stride;
+    float* r = L.d + eo;            // smoothed residual left by the down pass
+    float* x = L.x + eo;
     const float* xc = C.x + (size_t)e * C.stride;
-    const int n = L.n, m = L.m, P = L.P;
-    // d = prolongate(coarse.x) incl. its setBC: ghost = adjacent interior (MG.pde:139-152)
-    for (int c = threadIdx.x; c < n * m; c += blockDim.x) {
-      int i = c / m, j = c - i * m;
-      int ci = min(max(i, 1), n - 2), cj = min(max(j, 1), m - 2);
-      d[IDX(i, j)] = xc[((ci - 1) / 2 + 1) * C.P + ((cj - 1) / 2 + 1)];
+    const int n = L.n, m = L.m, P = L.P, ni = n - 2, mj = m - 2;
+    auto dval = [&](int a, int b) {   // prolongation incl. its setBC: ghost = adjacent interior (MG.pde:139-152)
+      int ci = min(max(a, 1), n - 2), cj = min(max(b, 1), m - 2);
+      return xc[((ci - 1) / 2 + 1) * C.P + ((cj - 1) / 2 + 1)];
+    };
+    for (int c = threadIdx.x; c < ni * mj; c += blockDim.x) {
+      const int i = c / mj + 1, j = c % mj + 1, k = IDX(i, j);
+      const float dc = dval(i, j);
+      x[k] += dc;
+      r[k] -= dc * L.diag[k] + dval(i - 1, j) * L.lx[k] + dval(i + 1, j) * L.lx[k + P] + dval(i, j - 1) * L.ly[k] +
+              dval(i, j + 1) * L.ly[k + 1];
     }
     __syncthreads();
-    cta_increment(L, x, r, d, false, true);
-    cta_dinit(d, r, L.inv, n, m, P);
-    cta_gs(L, d, r, 4);
-    cta_bc0(d, n, m, P);
-    cta_increment(L, x, r, d, false, false);       // the residual update is dead on coarse levels
+    strip_smooth<2>(L, r, x, sh, mail);
   }
 }
 
@@ -417,16 +358,17 @@ k_mg_up0(const __grid_constant__ SolverParams q, float* __restrict__ r_all) {
   }
 }
 
-// level 0 smooth(4), part 1: d = r*inv, then the four Gauss-Seidel sweeps; one CTA per env
-__global__ void __launch_bounds__(1024)
+// level 0 smooth(4), part 1: d = r*inv, then the four Gauss-Seidel sweeps; one CTA (one warp per
+// 32-column strip) per env, see smooth_strip.cuh
+__global__ void __launch_bounds__(256)
 k_gs0(const __grid_constant__ SolverParams q, const float* r_all) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const DevLevel& L = q.lev[0];
+  StripShared* sh = reinterpret_cast<StripShared*>(smem_raw);
+  StripMail* mail = reinterpret_cast<StripMail*>(smem_raw + sizeof(StripShared) * L.sk.nstrips);
   const int e = blockIdx.x;
   if (!q.sc.active[e]) return;
-  const DevLevel& L = q.lev[0];
-  const float* r = r_all + (size_t)e * L.stride;
-  float* d = L.d + (size_t)e * L.stride;
-  cta_dinit(d, r, L.inv, L.n, L.m, L.P);
-  cta_gs(L, d, r, 4);
+  strip_smooth<0>(L, r_all + (size_t)e * L.stride, L.d + (size_t)e * L.stride, sh, mail);
 }
 
 // level 0 smooth(4), part 2: d.setBC (clamped reads), x += d, r -= A d, partial sums of r.r
@@ -485,38 +427,45 @@ __global__ void k_conv(const __grid_constant__ SolverParams q, int which, int it
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32)
 k_psum(const __grid_constant__ SolverParams q) {
+  constexpr int G = 8;                                   // 32-element chunks per group (one row segment each)
+  __shared__ __align__(16) float buf[2][G * 32];
   const int e = blockIdx.x, lane = threadIdx.x;
-  const int P = q.P, n = q.n, m = q.m;
+  const int P = q.P, ni = q.n - 2, len = q.m - 2;
+  const int cpr = (len + 31) / 32;                       // chunks per row; row tails are padded with +0.f (s + 0.f == s)
   const float* p = q.lev[0].x + (size_t)e * q.stride;
-  const int len = m - 2, cpr = (len + 31) / 32, total = (n - 2) * cpr;   // chunks of 32 along a row
-  constexpr int G = 8;                                                  // chunks per prefetch group
-  auto load = [&](int g) -> float {
-    if (g >= total) return 0.f;
-    const int i = 1 + g / cpr, j = (g % cpr) * 32 + lane;
-    return (j < len) ? p[IDX(i, 1 + j)] : 0.f;
-  };
-  float cur[G], nxt[G];
-#pragma unroll
-  for (int u = 0; u < G; u++) cur[u] = load(u);
-  float s = 0.f;
-  for (int g0 = 0; g0 < total; g0 += G) {
-#pragma unroll
-    for (int u = 0; u < G; u++) nxt[u] = load(g0 + G + u);              // in flight during the add chain
+  // group iterator: `cnt` consecutive chunks of row gi starting at chunk gc
+  int gi = 1, gc = 0;
+  const float* rowp = p + IDX(1, 1) + lane;
+  float nxt[G];
+  int ncnt;
+  auto fetch = [&]() {
+    ncnt = (gi <= ni) ? min(G, cpr - gc) : 0;
 #pragma unroll
     for (int u = 0; u < G; u++) {
-      const int g = g0 + u;
-      if (g < total) {
-        const int cnt = min(32, len - (g % cpr) * 32);
-        if (cnt == 32) {
+      const int j = (gc + u) * 32 + lane;
+      nxt[u] = (u < ncnt && j < len) ? rowp[(gc + u) * 32] : 0.f;
+    }
+    gc += ncnt;
+    if (gc >= cpr) { gc = 0; gi++; rowp += P; }
+  };
+  fetch();
+  float s = 0.f;
+  int pb = 0;
+  while (ncnt > 0) {
+    const int cnt = ncnt;
 #pragma unroll
-          for (int l = 0; l < 32; l++) s += __shfl_sync(0xffffffffu, cur[u], l);
-        } else {
-          for (int l = 0; l < cnt; l++) s += __shfl_sync(0xffffffffu, cur[u], l);
-        }
+    for (int u = 0; u < G; u++) buf[pb][u * 32 + lane] = nxt[u];
+    __syncwarp();
+    fetch();                                             // next group's loads are in flight during the chain
+    const float4* b4 = reinterpret_cast<const float4*>(buf[pb]);
+    for (int c = 0; c < cnt; c++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {                      // every lane replays the same serial chain
+        const float4 v = b4[c * 8 + k];
+        s += v.x; s += v.y; s += v.z; s += v.w;
       }
     }
-#pragma unroll
-    for (int u = 0; u < G; u++) cur[u] = nxt[u];
+    pb ^= 1;
   }
   if (lane == 0) q.sc.psum[e] = s;
 }
@@ -680,8 +629,16 @@ int launch_mg_down0(const SolverParams& q, const float* r_in, float* r_out, cuda
   return 1;
 }
 
+static size_t strip_smem(int nstrips) { return sizeof(StripShared) * nstrips + sizeof(StripMail) * (nstrips + 2); }
+
 int launch_mg_coarse(const SolverParams& q, cudaStream_t st) {
-  k_mg_coarse<<<q.B, 1024, 0, st>>>(q);
+  const size_t smem = strip_smem(q.coarse_strips);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(k_mg_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  k_mg_coarse<<<q.B, max(128, 32 * q.coarse_strips), smem, st>>>(q);
   return 1;
 }
 
@@ -692,9 +649,14 @@ int launch_mg_up0(const SolverParams& q, float* r, cudaStream_t st) {
 }
 
 int launch_gs0(const SolverParams& q, const float* r, cudaStream_t st) {
-  const int W = min(q.n - 2, q.m - 2);
-  int threads = min(1024, ((4 * W + 31) / 32) * 32);
-  k_gs0<<<q.B, threads, 0, st>>>(q, r);
+  const int ns = q.lev[0].sk.nstrips;
+  const size_t smem = strip_smem(ns);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(k_gs0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  k_gs0<<<q.B, 32 * ns, smem, st>>>(q, r);
   return 1;
 }
 
