@@ -106,6 +106,7 @@ struct StripState {
   unsigned o_pf, o_w;              // ring offsets of the row being prefetched / written out
   unsigned a_in, a_out;            // shared addresses of this lane's column in the two rings
   unsigned a_cf, a_cn;             // shared addresses of this lane's column in the coefficient landing ring
+  const float* px;                 // XMODE 2: x row tau - 1 (this lane's column), prefetched into the out ring
   unsigned a_mh, a_ml, a_hi, a_lo; // mailboxes: previous strip's hi, next strip's lo, own hi, own lo (parity 0)
 };
 
@@ -114,7 +115,8 @@ struct StripState {
 // XMODE selects what the write-out does with a finished row of d:
 //   0: d_out = d                      (level 0: the increment runs as a separate kernel)
 //   1: x = 0 + d                      (coarsest level: x starts at 0, MG.pde:56,95)
-//   2: x = x + d                      (x.plusEq(d), MG.pde:95)
+//   2: x = x + d                      (x.plusEq(d), MG.pde:95); x rows are prefetched into the out ring and the sum is
+//                                     formed by stage 4, so the write-out never waits on a global load
 template <int PH, int XMODE>
 __device__ __forceinline__ void strip_step(StripState& s, int tau, int lane, unsigned ni_eff, int lag, int P) {
   constexpr unsigned par = PH & 1, rd = (par ^ 1) * 16, wr = par * 16;
@@ -135,6 +137,12 @@ __device__ __forceinline__ void strip_step(StripState& s, int tau, int lane, uns
   {
     const unsigned cslot = (unsigned)(tau + kLook + kPrefetch) & (kCoefRing - 1);
     cp_async4_if((unsigned)(tau + kPrefetch) < ni_eff, s.a_in + s.o_pf, s.pr);
+    if (XMODE == 2) {
+      // x of row tau-1 lands in the out-ring slot that stage 4 will fill for that row (slot (row + 8) mod kRing is
+      // the slot of r row tau+7); lane 0 reaches the row at step row + 7 = tau + kPrefetch, the group's deadline
+      cp_async4_if((unsigned)(tau - 2) < ni_eff, s.a_out + s.o_pf, s.px);
+      s.px += P;
+    }
     cp_async16(s.a_cf + cslot * 512u, s.pa);
     cp_async4(s.a_cn + cslot * 128u, s.pn);
     cp_async_commit();
@@ -163,7 +171,8 @@ __device__ __forceinline__ void strip_step(StripState& s, int tau, int lane, uns
     const float rv = s.qr[(PH - 2 * g + kQueue) % kQueue];
     res[g] = (s.prev[g] * c.x + s.prev[g - 1] * c.y + up[g] * c.z + dn[g - 1] * c.w - rv) * ninv;
   }
-  sts32(s.a_out + s.o_row, res[4]);             // row tau - lane - 7 lives in slot (row + 8) & 63
+  if (XMODE == 2) sts32(s.a_out + s.o_row, lds32(s.a_out + s.o_row) + res[4]);   // x.plusEq(d): x + d
+  else sts32(s.a_out + s.o_row, res[4]);        // row tau - lane - 7 lives in slot (row + 8) mod kRing
   s.o_row = ring_next(s.o_row);
 #pragma unroll
   for (int g = 0; g <= 4; g++) s.prev[g] = res[g];
@@ -175,11 +184,7 @@ __device__ __forceinline__ void strip_step(StripState& s, int tau, int lane, uns
     const int w = tau - lag;
     const float v = lds32(s.a_out + s.o_w);
     s.o_w = ring_next(s.o_w);
-    if ((unsigned)(w - 1) < ni_eff) {
-      if (XMODE == 0) *s.pd = v;
-      else if (XMODE == 1) *s.pd = 0.f + v;
-      else *s.pd = *s.pd + v;
-    }
+    if ((unsigned)(w - 1) < ni_eff) *s.pd = (XMODE == 1) ? 0.f + v : v;
     s.pd += P;
   }
 }
@@ -221,6 +226,7 @@ __device__ __forceinline__ void strip_smooth(const DevLevel& L, const float* __r
     s.o_row = ring_slot(-kWarm - lane + 1);
     s.o_pf = ring_slot(-kWarm + 1 + kPrefetch);
     s.o_w = ring_slot(-kWarm - lag + 8);
+    s.px = d + (ptrdiff_t)(-kWarm - 1) * P + jj;
     s.a_cf = smem_addr(&sh.cf[0][lane]);
     s.a_cn = smem_addr(&sh.cn[0][lane]);
     s.a_in = smem_addr(&sh.in[0][lane]);

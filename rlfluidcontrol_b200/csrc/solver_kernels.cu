@@ -34,64 +34,134 @@ __device__ __forceinline__ float med3(float a, float b, float c) {              
 }
 
 // ------------------------------------------------------------------------------------------------
-// AdvDif
+// AdvDif (VectorField.pde:170-222)
+//
+// The reference evaluates, per cell and component, four limited QUICK face values `bho` (west, east,
+// south, north) and forms  adv = (uo*bho_w - ue*bho_e) + (vs*bho_s - vn*bho_n).  The east face of cell
+// (i,j) is the west face of cell (i+1,j) with the same face velocity and -- for uf != 0 -- the same
+// upwind triple (bc, bd, bu) and the same boundary test, so the product uf*bho is identical; for
+// uf == 0 both products are +-0.  Likewise north(i,j) = south(i,j+1).  Each face flux is therefore
+// computed once:
+//   FXx(i,j) = uo*bho(x,i,j,-1,0,uo)   uo = .5(x[i-1][j] + x[i][j])      (x-faces of the x-component)
+//   FXy(i,j) = vs*bho(x,i,j,0,-1,vs)   vs = .5(y[i][j]   + y[i-1][j])
+//   FYx(i,j) = uo*bho(y,i,j,-1,0,uo)   uo = .5(x[i][j-1] + x[i][j])      (y-component)
+//   FYy(i,j) = vs*bho(y,i,j,0,-1,vs)   vs = .5(y[i][j-1] + y[i][j])
+//   adv_x = (FXx(i,j) - FXx(i+1,j)) + (FXy(i,j) - FXy(i,j+1)),  adv_y likewise.
+// A warp owns 32 consecutive columns j (28 outputs + 2 halo columns each side, coalesced rows) and
+// marches down a chunk of rows with a 4-row register window per component; the i-direction fluxes
+// are carried in registers from one row to the next, the j-direction operands and fluxes come from
+// neighbouring lanes by shuffle.  PApplet.min/max are realised as FMNMX: they differ from the
+// ternaries only in the sign of a zero result, which no later operation can turn into a value change.
 // ------------------------------------------------------------------------------------------------
-// VectorField.bho VectorField.pde:202-219, direction (D1,D2) resolved at compile time
-template <int D1, int D2>
-__device__ __forceinline__ float bho(const float* __restrict__ b, int P, int n, int m, int i, int j, float uf) {
+constexpr int kAdvCols = 28;      // output columns per warp
+constexpr int kAdvRows = 48;      // rows per chunk
+
+__device__ __forceinline__ float med3f(float a, float b, float c) {                   // VectorField.pde:221
+  return fmaxf(fminf(a, b), fminf(fmaxf(a, b), c));
+}
+
+// limited QUICK value on the face between cells L and H = L+1 along one direction (VectorField.bho in its
+// d = -1 form for cell H): bLL, bL | bH, bHH are the four values along the direction, uf the face velocity,
+// `plain_pos` / `plain_neg` say whether the upwind cell (L if uf > 0, else H) fails the bounds test
+// `i>n-2 || i<2 || j>m-2 || j<2` (VectorField.pde:212), in which case the plain average is returned.
+__device__ __forceinline__ float face_value(float uf, float bLL, float bL, float bH, float bHH, bool plain_pos,
+                                            bool plain_neg) {
   const float CF = 1.f / 6.f, S = 10.f;
-  float bf = 0.5f * (b[IDX(i + D1, j + D2)] + b[IDX(i, j)]);
-  int d1 = D1, d2 = D2;
-  if (D1 != 0 && D1 * uf < 0) { i += D1; d1 = -D1; }
-  if (D2 != 0 && D2 * uf < 0) { j += D2; d2 = -D2; }
-  if (i > n - 2 || i < 2 || j > m - 2 || j < 2) return bf;
-  float bc = b[IDX(i, j)];
-  float bd = b[IDX(i + d1, j + d2)];
-  float bu = b[IDX(i - d1, j - d2)];
-  bf -= CF * (bd - 2 * bc + bu);
-  float b1 = bu + S * (bc - bu);
-  return med3(bf, bc, med3(bc, bd, b1));
+  float bf = 0.5f * (bL + bH);
+  const bool pos = uf > 0;
+  const float bc = pos ? bL : bH, bd = pos ? bH : bL, bu = pos ? bLL : bHH;
+  const float q = bf - CF * (bd - 2 * bc + bu);
+  const float b1 = bu + S * (bc - bu);
+  const float lim = med3f(q, bc, med3f(bc, bd, b1));
+  return (pos ? plain_pos : plain_neg) ? bf : lim;
 }
 
-// VectorField.diffusion VectorField.pde:198-200
-__device__ __forceinline__ float diffusion(const float* __restrict__ b, int P, int i, int j) {
-  return b[IDX(i + 1, j)] + b[IDX(i, j + 1)] - 4 * b[IDX(i, j)] + b[IDX(i - 1, j)] + b[IDX(i, j - 1)];
-}
-
-__global__ void __launch_bounds__(256)
+template <bool PREDICTOR>
+__global__ void __launch_bounds__(128)
 k_advdif(const float* __restrict__ srcx, const float* __restrict__ srcy, const float* __restrict__ u0x,
          const float* __restrict__ u0y, float* __restrict__ dstx, float* __restrict__ dsty, int n, int m, int P,
          size_t stride, float dt, float nu) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = blockIdx.y * blockDim.y + threadIdx.y;
-  if (i >= n || j >= m) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ni = n - 2, mj = m - 2;
+  const int jw0 = 1 + blockIdx.x * kAdvCols;                         // first output column of this warp
+  const int ia = 1 + (blockIdx.y * 4 + warp) * kAdvRows;             // first row of this chunk
+  if (ia > ni) return;
+  const int ib = min(ia + kAdvRows - 1, ni);
   const size_t eo = (size_t)blockIdx.z * stride;
-  const float* x = srcx + eo;
-  const float* y = srcy + eo;
-  const int k = IDX(i, j);
-  if (i == 0 || j == 0 || i == n - 1 || j == m - 1) {   // ghosts of F keep u's values (VectorField.pde:171)
-    dstx[eo + k] = x[k];
-    dsty[eo + k] = y[k];
-    return;
+  const float* __restrict__ x = srcx + eo;
+  const float* __restrict__ y = srcy + eo;
+  const int j = jw0 - 2 + lane;                                      // this lane's column (may be outside the array)
+  const int jl = min(max(j, 0), m - 1);                              // clamped for loads
+  const bool last_cw = jw0 + kAdvCols > mj;                          // this warp also owns ghost column m-1
+  const bool out_lane = lane >= 2 && lane < 2 + kAdvCols && j >= 1 && j <= mj;
+  const bool ghost_lane = (j == 0 && jw0 == 1) || (j == m - 1 && last_cw);
+  // bounds test of bho along j for this column's south face (upwind column j-1 if v > 0, else j), and the
+  // column part of the test for the x-direction faces
+  const bool jplain_pos = (j - 1 < 2) || (j - 1 > m - 2), jplain_neg = (j < 2) || (j > m - 2);
+  const bool jbad = jplain_neg;
+  auto ldx = [&](int i) { return x[IDX(min(max(i, 0), n - 1), jl)]; };
+  auto ldy = [&](int i) { return y[IDX(min(max(i, 0), n - 1), jl)]; };
+  // register window: rows i-2 .. i+1 (a = i-2, b = i-1, c = i, d = i+1), e = i+2 arrives during the step
+  float xa = ldx(ia - 2), xb = ldx(ia - 1), xc = ldx(ia), xd = ldx(ia + 1);
+  float ya = ldy(ia - 2), yb = ldy(ia - 1), yc = ldy(ia), yd = ldy(ia + 1);
+  if (ia == 1 && (out_lane || ghost_lane)) {                          // ghost row 0 of F keeps u's values
+    dstx[eo + IDX(0, j)] = xb;
+    dsty[eo + IDX(0, j)] = yb;
   }
-  // x component (btype 1) VectorField.pde:183-188,195
-  float uo = 0.5f * (x[IDX(i - 1, j)] + x[k]);
-  float ue = 0.5f * (x[IDX(i + 1, j)] + x[k]);
-  float vs = 0.5f * (y[k] + y[IDX(i - 1, j)]);
-  float vn = 0.5f * (y[IDX(i, j + 1)] + y[IDX(i - 1, j + 1)]);
-  float advx = ((uo * bho<-1, 0>(x, P, n, m, i, j, uo) - ue * bho<1, 0>(x, P, n, m, i, j, ue)) +
-                (vs * bho<0, -1>(x, P, n, m, i, j, vs) - vn * bho<0, 1>(x, P, n, m, i, j, vn)));
-  float rx = (advx + nu * diffusion(x, P, i, j)) * dt + u0x[eo + k];
-  // y component (btype 2) VectorField.pde:189-195
-  uo = 0.5f * (x[IDX(i, j - 1)] + x[k]);
-  ue = 0.5f * (x[IDX(i + 1, j - 1)] + x[IDX(i + 1, j)]);
-  vs = 0.5f * (y[IDX(i, j - 1)] + y[k]);
-  vn = 0.5f * (y[k] + y[IDX(i, j + 1)]);
-  float advy = ((uo * bho<-1, 0>(y, P, n, m, i, j, uo) - ue * bho<1, 0>(y, P, n, m, i, j, ue)) +
-                (vs * bho<0, -1>(y, P, n, m, i, j, vs) - vn * bho<0, 1>(y, P, n, m, i, j, vn)));
-  float ry = (advy + nu * diffusion(y, P, i, j)) * dt + u0y[eo + k];
-  dstx[eo + k] = rx;
-  dsty[eo + k] = ry;
+  // west fluxes of the first row: faces between rows ia-1 and ia
+  float fxw, fyw;
+  {
+    const bool ip = (ia - 1 < 2) || (ia - 1 > n - 2) || jbad, in_ = (ia < 2) || (ia > n - 2) || jbad;
+    const float uox = 0.5f * (xb + xc);
+    fxw = uox * face_value(uox, xa, xb, xc, xd, ip, in_);
+    const float xcm1 = __shfl_up_sync(0xffffffffu, xc, 1);
+    const float uoy = 0.5f * (xcm1 + xc);
+    fyw = uoy * face_value(uoy, ya, yb, yc, yd, ip, in_);
+  }
+  for (int i = ia; i <= ib; i++) {
+    const float xe = ldx(i + 2), ye = ldy(i + 2);
+    float u0xv, u0yv;
+    if (PREDICTOR) { u0xv = xc; u0yv = yc; }
+    else { u0xv = u0x[eo + IDX(i, jl)]; u0yv = u0y[eo + IDX(i, jl)]; }
+    // neighbours along j of rows i (c) and i+1 (d), i-1 (b)
+    const float xcm2 = __shfl_up_sync(0xffffffffu, xc, 2), xcm1 = __shfl_up_sync(0xffffffffu, xc, 1);
+    const float xcp1 = __shfl_down_sync(0xffffffffu, xc, 1);
+    const float ycm2 = __shfl_up_sync(0xffffffffu, yc, 2), ycm1 = __shfl_up_sync(0xffffffffu, yc, 1);
+    const float ycp1 = __shfl_down_sync(0xffffffffu, yc, 1);
+    const float xdm1 = __shfl_up_sync(0xffffffffu, xd, 1);
+    // east faces (between rows i and i+1) = west faces of row i+1
+    const bool ip = (i < 2) || (i > n - 2) || jbad, in_ = (i + 1 < 2) || (i + 1 > n - 2) || jbad;
+    const float uex = 0.5f * (xc + xd);
+    const float fxe = uex * face_value(uex, xb, xc, xd, xe, ip, in_);
+    const float uey = 0.5f * (xdm1 + xd);
+    const float fye = uey * face_value(uey, yb, yc, yd, ye, ip, in_);
+    // south faces of this column (between columns j-1 and j) on row i
+    const bool ibad = (i < 2) || (i > n - 2);
+    const float vsx = 0.5f * (yc + yb);
+    const float fxs = vsx * face_value(vsx, xcm2, xcm1, xc, xcp1, jplain_pos || ibad, jplain_neg || ibad);
+    const float vsy = 0.5f * (ycm1 + yc);
+    const float fys = vsy * face_value(vsy, ycm2, ycm1, yc, ycp1, jplain_pos || ibad, jplain_neg || ibad);
+    // north faces = south faces of column j+1
+    const float fxn = __shfl_down_sync(0xffffffffu, fxs, 1), fyn = __shfl_down_sync(0xffffffffu, fys, 1);
+    const float advx = (fxw - fxe) + (fxs - fxn);
+    const float advy = (fyw - fye) + (fys - fyn);
+    const float difx = xd + xcp1 - 4 * xc + xb + xcm1;                 // VectorField.pde:198-200
+    const float dify = yd + ycp1 - 4 * yc + yb + ycm1;
+    if (out_lane) {
+      dstx[eo + IDX(i, j)] = (advx + nu * difx) * dt + u0xv;
+      dsty[eo + IDX(i, j)] = (advy + nu * dify) * dt + u0yv;
+    } else if (ghost_lane) {                                           // ghost columns of F keep u's values
+      dstx[eo + IDX(i, j)] = xc;
+      dsty[eo + IDX(i, j)] = yc;
+    }
+    fxw = fxe; fyw = fye;
+    xa = xb; xb = xc; xc = xd; xd = xe;
+    ya = yb; yb = yc; yc = yd; yd = ye;
+  }
+  if (ib == ni && (out_lane || ghost_lane)) {                          // ghost row n-1
+    dstx[eo + IDX(n - 1, j)] = xc;
+    dsty[eo + IDX(n - 1, j)] = yc;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -281,7 +351,43 @@ k_mg_down0(const __grid_constant__ SolverParams q, const float* __restrict__ rin
 // Ghost cells of the coarse r and x are never materialised: every reference read of them is either
 // overwritten by a setBC before use or multiplied by a boundary coefficient that is 0 on coarse levels.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+// up pass of one coarse level for one env: d = prolongate(coarse.x) incl. its setBC (ghost = adjacent interior,
+// MG.pde:139-152), x += d, r -= A d (MG.pde:75-76,94-97).  Warps own rows, lanes own columns; four rows are in
+// flight per warp so the L2 round trips overlap.
+__device__ __forceinline__ void coarse_up_pass(const DevLevel& L, const DevLevel& C, float* __restrict__ r,
+                                               float* __restrict__ x, const float* __restrict__ xc) {
+  const int n = L.n, m = L.m, P = L.P, ni = n - 2, mj = m - 2, CP = C.P;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* __restrict__ lx = L.lx;
+  const float* __restrict__ ly = L.ly;
+  const float* __restrict__ diag = L.diag;
+  constexpr int U = 4;
+  for (int j = 1 + lane; j <= mj; j += 32) {
+    const int cj = (j - 1) / 2 + 1, cjm = (max(j - 1, 1) - 1) / 2 + 1, cjp = (min(j + 1, mj) - 1) / 2 + 1;
+    for (int i0 = 1 + warp; i0 <= ni; i0 += nw * U) {
+      float dc[U], dw[U], de[U], ds[U], dn[U], xo[U], ro[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int i = min(i0 + u * nw, ni);
+        const int ci = (i - 1) / 2 + 1, cim = (max(i - 1, 1) - 1) / 2 + 1, cip = (min(i + 1, ni) - 1) / 2 + 1;
+        dc[u] = xc[ci * CP + cj]; dw[u] = xc[cim * CP + cj]; de[u] = xc[cip * CP + cj];
+        ds[u] = xc[ci * CP + cjm]; dn[u] = xc[ci * CP + cjp];
+        xo[u] = x[IDX(i, j)]; ro[u] = r[IDX(i, j)];
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int i = i0 + u * nw;
+        if (i <= ni) {
+          const int k = IDX(i, j);
+          x[k] = xo[u] + dc[u];
+          r[k] = ro[u] - (dc[u] * diag[k] + dw[u] * lx[k] + de[u] * lx[k + P] + ds[u] * ly[k] + dn[u] * ly[k + 1]);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 2)
 k_mg_coarse(const __grid_constant__ SolverParams q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StripShared* sh = reinterpret_cast<StripShared*>(smem_raw);
@@ -289,14 +395,17 @@ k_mg_coarse(const __grid_constant__ SolverParams q) {
   const int e = blockIdx.x;
   if (!q.sc.active[e]) return;
   const int last = q.nlevels - 1;
-  // ---- down: smooth(0) + restrict ----
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // ---- down: smooth(0) + restrict; warps own coarse rows, lanes own coarse columns ----
   for (int l = 1; l < last; l++) {
     const DevLevel& L = q.lev[l];
     const DevLevel& C = q.lev[l + 1];
     const int nci = C.n - 2, ncj = C.m - 2;
     const size_t eo = (size_t)e * L.stride;
-    for (int c = threadIdx.x; c < nci * ncj; c += blockDim.x)
-      down_block<false>(L, C, L.r + eo, L.d + eo, L.x + eo, C.r + (size_t)e * C.stride, c / ncj + 1, c % ncj + 1);
+    for (int J = 1 + lane; J <= ncj; J += 32)
+#pragma unroll 2
+      for (int I = 1 + warp; I <= nci; I += nw)
+        down_block<false>(L, C, L.r + eo, L.d + eo, L.x + eo, C.r + (size_t)e * C.stride, I, J);
     __syncthreads();
   }
   // ---- coarsest level: smooth(its) only (MG.pde:72-73), x = 0 + d ----
@@ -304,26 +413,14 @@ k_mg_coarse(const __grid_constant__ SolverParams q) {
     const DevLevel& L = q.lev[last];
     strip_smooth<1>(L, L.r + (size_t)e * L.stride, L.x + (size_t)e * L.stride, sh, mail);
   }
-  // ---- up: d = prolongate(coarse.x), x += d, r -= A d, then smooth(its): x += GS(r)  (MG.pde:73-76) ----
+  // ---- up: prolongate + increment, then smooth(its): x += GS(r)  (MG.pde:73-76) ----
   for (int l = last - 1; l >= 1; l--) {
     const DevLevel& L = q.lev[l];
     const DevLevel& C = q.lev[l + 1];
     const size_t eo = (size_t)e * L.stride;
     float* r = L.d + eo;            // smoothed residual left by the down pass
     float* x = L.x + eo;
-    const float* xc = C.x + (size_t)e * C.stride;
-    const int n = L.n, m = L.m, P = L.P, ni = n - 2, mj = m - 2;
-    auto dval = [&](int a, int b) {   // prolongation incl. its setBC: ghost = adjacent interior (MG.pde:139-152)
-      int ci = min(max(a, 1), n - 2), cj = min(max(b, 1), m - 2);
-      return xc[((ci - 1) / 2 + 1) * C.P + ((cj - 1) / 2 + 1)];
-    };
-    for (int c = threadIdx.x; c < ni * mj; c += blockDim.x) {
-      const int i = c / mj + 1, j = c % mj + 1, k = IDX(i, j);
-      const float dc = dval(i, j);
-      x[k] += dc;
-      r[k] -= dc * L.diag[k] + dval(i - 1, j) * L.lx[k] + dval(i + 1, j) * L.lx[k + P] + dval(i, j - 1) * L.ly[k] +
-              dval(i, j + 1) * L.ly[k + 1];
-    }
+    coarse_up_pass(L, C, r, x, C.x + (size_t)e * C.stride);
     __syncthreads();
     strip_smooth<2>(L, r, x, sh, mail);
   }
@@ -600,8 +697,12 @@ inline dim3 grid2d(int m, int n, int B, dim3 blk) { return dim3((m + blk.x - 1) 
 // ================================================================================================
 int launch_advdif(const SolverParams& q, const float* srcx, const float* srcy, const float* u0x, const float* u0y,
                   float* dstx, float* dsty, cudaStream_t st) {
-  dim3 blk(32, 8);
-  k_advdif<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(srcx, srcy, u0x, u0y, dstx, dsty, q.n, q.m, q.P, q.stride, q.dt, q.nu);
+  const int ni = q.n - 2, mj = q.m - 2;
+  dim3 grid((mj + kAdvCols - 1) / kAdvCols, ((ni + kAdvRows - 1) / kAdvRows + 3) / 4, q.B);
+  if (srcx == u0x && srcy == u0y)
+    k_advdif<true><<<grid, 128, 0, st>>>(srcx, srcy, u0x, u0y, dstx, dsty, q.n, q.m, q.P, q.stride, q.dt, q.nu);
+  else
+    k_advdif<false><<<grid, 128, 0, st>>>(srcx, srcy, u0x, u0y, dstx, dsty, q.n, q.m, q.P, q.stride, q.dt, q.nu);
   return 1;
 }
 
@@ -638,7 +739,7 @@ int launch_mg_coarse(const SolverParams& q, cudaStream_t st) {
     cudaFuncSetAttribute(k_mg_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  k_mg_coarse<<<q.B, max(128, 32 * q.coarse_strips), smem, st>>>(q);
+  k_mg_coarse<<<q.B, max(256, 32 * q.coarse_strips), smem, st>>>(q);
   return 1;
 }
 
