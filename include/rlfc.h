@@ -68,6 +68,7 @@ typedef struct {
   const char *init_bdim_path; /* NULL = uniform flow u=(1,0), p=0; else a .bdim text
                                  checkpoint (BDIM.write format) or a .bdimb binary one */
   void *stream;         /* cudaStream_t to run on; NULL = the library creates its own */
+  int   n_groups;       /* env groups advanced concurrently on separate streams; 0 = auto    */
 } rlfc_config;
 
 void rlfc_default_config(rlfc_config *cfg);

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -55,6 +56,22 @@ struct rlfc_env {
   int *h_done = nullptr, *h_any = nullptr;
   long long launches = 0;
   long long mg_iter_launch_rounds = 0;
+  // Environment groups: the batch is split into contiguous groups, each advanced by its own stream (and its own
+  // CUDA graphs), so the latency-bound per-env kernels of one group overlap the bandwidth-bound kernels of another.
+  struct Group {
+    int e0 = 0, B = 0;
+    SolverParams sp{};                       // view of the batch arrays restricted to [e0, e0 + B)
+    float *uAx = nullptr, *uAy = nullptr, *uBx = nullptr, *uBy = nullptr, *uCx = nullptr, *uCy = nullptr;
+    cudaStream_t st = nullptr;               // group 0 runs on the handle's stream
+    cudaEvent_t done = nullptr;
+    cudaGraphExec_t step_graph[2] = {nullptr, nullptr};   // [accumulate]
+    long long graph_launches[2] = {0, 0};    // kernel nodes of one replay outside / inside the MG loops
+  };
+  std::vector<Group> groups;
+  Group whole;                               // the entire batch on the handle's stream (eager / profiled path)
+  cudaStream_t aux_stream = nullptr;         // used to capture the bodies of the conditional nodes
+  cudaEvent_t fork_ev = nullptr;
+  bool use_graph = true;
   // optional per-kernel CUDA-event timing (rlfc_env_set_profiling)
   bool profiling = false;
   struct ProfRec { int id; cudaEvent_t e0, e1; };
@@ -156,21 +173,24 @@ int broadcast_field(rlfc_env* E, float* batch, const float* one, const int* ids,
 // ---- one MG-projected half step on velocity buffer U (BDIM.updateUP tail + VectorField.project) ----
 // The floats-per-interior-cell figures are each kernel's ALGORITHMIC traffic per env (SURVEY 8d
 // convention: per-env arrays only, one read per input and one write per output).
-int project(rlfc_env* E, float* Ux, float* Uy, int which) {
-  SolverParams& sp = E->sp;
-  cudaStream_t st = E->stream;
-  float* r_in = sp.lev[0].r;
-  float* r_out = sp.lev[0].r2;
-  E->run("k_residual", 4, [&] { return launch_residual(sp, Ux, Uy, r_in, which, st); });
+// Level-0 residual flow of one MG iteration: down0 reads r and writes the smoothed residual to the `d`
+// buffer, up0 updates it in place, smooth0 consumes it and writes the new residual back to r.
+using Group = rlfc_env::Group;
+
+// eager path: every kernel individually launched (optionally event-timed); the data-dependent loop exit
+// (MG.pde:34) costs one 4-byte readback per iteration
+int project_eager(rlfc_env* E, Group& G, float* Ux, float* Uy, int which) {
+  SolverParams& sp = G.sp;
+  cudaStream_t st = G.st;
+  float* r = sp.lev[0].r;
+  float* rs = sp.lev[0].d;
+  E->run("k_residual", 4, [&] { return launch_residual(sp, Ux, Uy, r, which, st); });
   for (int it = 0; it < sp.mg_max_iters; it++) {
-    E->run("k_mg_down0", 4.25, [&] { return launch_mg_down0(sp, r_in, r_out, st); });
+    CU(cudaMemsetAsync(sp.sc.any_active, 0, sizeof(int), st));
+    E->run("k_mg_down0", 4.25, [&] { return launch_mg_down0(sp, r, rs, st); });
     E->run("k_mg_coarse", 0.5, [&] { return launch_mg_coarse(sp, st); });
-    E->run("k_mg_up0", 4.25, [&] { return launch_mg_up0(sp, r_out, st); });
-    E->run("k_gs0", 2, [&] { return launch_gs0(sp, r_out, st); });
-    E->run("k_inc0", 5, [&] { return launch_inc0(sp, r_out, st); });
-    E->run("k_conv", 0, [&] { return launch_conv(sp, which, st); });
-    std::swap(r_in, r_out);
-    // data-dependent loop exit (MG.pde:34): one 4-byte readback per iteration
+    E->run("k_mg_up0", 4.25, [&] { return launch_mg_up0(sp, rs, st); });
+    E->run("k_smooth0", 4, [&] { return launch_smooth0(sp, rs, r, which, st); });
     CU(cudaMemcpyAsync(E->h_any, sp.sc.any_active, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     E->mg_iter_launch_rounds++;
@@ -183,21 +203,122 @@ int project(rlfc_env* E, float* Ux, float* Uy, int which) {
   return RLFC_OK;
 }
 
-// AFCCylinder.update2 for the whole batch
-int solver_step(rlfc_env* E, int accumulate) {
-  SolverParams& sp = E->sp;
-  cudaStream_t st = E->stream;
+// AFCCylinder.update2 for one group, eager
+int solver_step_eager(rlfc_env* E, Group& G, int accumulate) {
+  SolverParams& sp = G.sp;
+  cudaStream_t st = G.st;
   int rc;
   // predictor BDIM.update(): u0 = u (buffer A), F = AdvDif(u) -> B, updateUP
-  E->run("k_advdif", 5, [&] { return launch_advdif(sp, E->uAx, E->uAy, E->uAx, E->uAy, E->uBx, E->uBy, st); });
-  E->run("k_band_bc", 0, [&] { return launch_band_bc(sp, E->uBx, E->uBy, st); });
-  if ((rc = project(E, E->uBx, E->uBy, 0))) return rc;
+  E->run("k_advdif", 5, [&] { return launch_advdif(sp, G.uAx, G.uAy, G.uAx, G.uAy, G.uBx, G.uBy, st); });
+  E->run("k_band_bc", 0, [&] { return launch_band_bc(sp, G.uBx, G.uBy, st); });
+  if ((rc = project_eager(E, G, G.uBx, G.uBy, 0))) return rc;
   // corrector BDIM.update2(): us = u (B), F = AdvDif(u; + u0) -> C, updateUP, u = (u + us)/2 -> A
-  E->run("k_advdif", 5, [&] { return launch_advdif(sp, E->uBx, E->uBy, E->uAx, E->uAy, E->uCx, E->uCy, st); });
-  E->run("k_band_bc", 0, [&] { return launch_band_bc(sp, E->uCx, E->uCy, st); });
-  if ((rc = project(E, E->uCx, E->uCy, 1))) return rc;
-  E->run("k_heun", 6, [&] { return launch_heun(sp, E->uCx, E->uCy, E->uBx, E->uBy, E->uAx, E->uAy, st); });
+  E->run("k_advdif", 5, [&] { return launch_advdif(sp, G.uBx, G.uBy, G.uAx, G.uAy, G.uCx, G.uCy, st); });
+  E->run("k_band_bc", 0, [&] { return launch_band_bc(sp, G.uCx, G.uCy, st); });
+  if ((rc = project_eager(E, G, G.uCx, G.uCy, 1))) return rc;
+  E->run("k_heun", 6, [&] { return launch_heun(sp, G.uCx, G.uCy, G.uBx, G.uBy, G.uAx, G.uAy, st); });
   E->run("k_force", 0, [&] { return launch_force(sp, accumulate, st); });
+  CU(cudaGetLastError());
+  return RLFC_OK;
+}
+
+// graph path: one CUDA graph per group = one solver step; each MGsolver loop is a WHILE conditional node whose
+// body is one iteration and whose condition is written on the device (k_loopcond), so no host round trip remains
+int capture_half_step(rlfc_env* E, Group& G, cudaStream_t st, const float* sx, const float* sy, const float* u0x,
+                      const float* u0y, float* dx, float* dy, int which, long long* n_outer, long long* n_body) {
+  SolverParams& sp = G.sp;
+  float* r = sp.lev[0].r;
+  float* rs = sp.lev[0].d;
+  *n_outer += launch_advdif(sp, sx, sy, u0x, u0y, dx, dy, st);
+  *n_outer += launch_band_bc(sp, dx, dy, st);
+  *n_outer += launch_residual(sp, dx, dy, r, which, st);
+  // ---- WHILE node ----
+  cudaStreamCaptureStatus status;
+  cudaGraph_t graph;
+  const cudaGraphNode_t* deps;
+  size_t ndeps;
+  CU(cudaStreamGetCaptureInfo(st, &status, nullptr, &graph, &deps, &ndeps));
+  cudaGraphConditionalHandle handle;
+  CU(cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault));   // do-while: first pass always
+  cudaGraphNodeParams np{};
+  np.type = cudaGraphNodeTypeConditional;
+  np.conditional.handle = handle;
+  np.conditional.type = cudaGraphCondTypeWhile;
+  np.conditional.size = 1;
+  cudaGraphNode_t cond;
+  CU(cudaGraphAddNode(&cond, graph, deps, ndeps, &np));
+  cudaGraph_t body = np.conditional.phGraph_out[0];
+  CU(cudaStreamBeginCaptureToGraph(E->aux_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+  *n_body += launch_mg_down0(sp, r, rs, E->aux_stream);
+  *n_body += launch_mg_coarse(sp, E->aux_stream);
+  *n_body += launch_mg_up0(sp, rs, E->aux_stream);
+  *n_body += launch_smooth0(sp, rs, r, which, E->aux_stream);
+  *n_body += launch_loopcond(sp, (unsigned long long)handle, E->aux_stream);
+  CU(cudaStreamEndCapture(E->aux_stream, nullptr));
+  CU(cudaStreamUpdateCaptureDependencies(st, &cond, 1, cudaStreamSetCaptureDependencies));
+  // ---- projection tail ----
+  *n_outer += launch_psum(sp, st);
+  *n_outer += launch_project_u(sp, dx, dy, st);
+  *n_outer += launch_shift_p(sp, st);
+  *n_outer += launch_bc(sp, dx, dy, st);
+  return RLFC_OK;
+}
+
+int build_step_graph(rlfc_env* E, Group& G, int accumulate) {
+  cudaStream_t st = G.st;
+  long long n_outer = 0, n_body = 0;
+  CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  int rc = capture_half_step(E, G, st, G.uAx, G.uAy, G.uAx, G.uAy, G.uBx, G.uBy, 0, &n_outer, &n_body);
+  if (!rc) rc = capture_half_step(E, G, st, G.uBx, G.uBy, G.uAx, G.uAy, G.uCx, G.uCy, 1, &n_outer, &n_body);
+  if (!rc) {
+    n_outer += launch_heun(G.sp, G.uCx, G.uCy, G.uBx, G.uBy, G.uAx, G.uAy, st);
+    n_outer += launch_force(G.sp, accumulate, st);
+  }
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (ce != cudaSuccess) return fail(RLFC_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+  ce = cudaGraphInstantiate(&G.step_graph[accumulate], graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) return fail(RLFC_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+  G.graph_launches[0] = n_outer;
+  G.graph_launches[1] = n_body;   // per MG iteration pair (predictor + corrector) with one iteration each
+  return RLFC_OK;
+}
+
+// fork the group streams off the handle's stream / join them back
+int fork_groups(rlfc_env* E) {
+  if (E->groups.size() <= 1) return RLFC_OK;
+  CU(cudaEventRecord(E->fork_ev, E->stream));
+  for (size_t g = 1; g < E->groups.size(); g++) CU(cudaStreamWaitEvent(E->groups[g].st, E->fork_ev, 0));
+  return RLFC_OK;
+}
+int join_groups(rlfc_env* E) {
+  for (size_t g = 1; g < E->groups.size(); g++) {
+    CU(cudaEventRecord(E->groups[g].done, E->groups[g].st));
+    CU(cudaStreamWaitEvent(E->stream, E->groups[g].done, 0));
+  }
+  return RLFC_OK;
+}
+
+// `nsteps` solver steps (AFCCylinder.update2) for the whole batch
+int solver_steps(rlfc_env* E, int nsteps, int accumulate) {
+  int rc;
+  const bool graph = E->use_graph && !E->profiling;
+  if (!graph) {
+    for (int s = 0; s < nsteps; s++)
+      if ((rc = solver_step_eager(E, E->whole, accumulate))) return rc;
+    return RLFC_OK;
+  }
+  if ((rc = fork_groups(E))) return rc;
+  for (auto& G : E->groups) {
+    if (graph && !G.step_graph[accumulate] && (rc = build_step_graph(E, G, accumulate))) return rc;
+    for (int s = 0; s < nsteps; s++) {
+      CU(cudaGraphLaunch(G.step_graph[accumulate], G.st));
+      E->launches += G.graph_launches[0] + G.graph_launches[1];   // lower bound: one MG iteration per solve
+    }
+  }
+  if ((rc = join_groups(E))) return rc;
   CU(cudaGetLastError());
   return RLFC_OK;
 }
@@ -238,7 +359,7 @@ void rlfc_default_config(rlfc_config* c) {
   c->dR = .125f; c->gR = .2f; c->theta = 3.1415927f / 3; c->t_step = .0075f;   // clientCFD.pde:9,95-96
   c->action_scale = 5.f;                                                       // clientCFD.pde:53-54
   c->substeps = 16; c->init_time = 1.f; c->episode_time = 50.f;                // clientCFD.pde:5-6,12
-  c->n_envs = 1; c->device = -1; c->exact = 1; c->mg_max_iters = 20;
+  c->n_envs = 1; c->device = -1; c->exact = 1; c->mg_max_iters = 20; c->n_groups = 0;
   c->init_bdim_path = nullptr; c->stream = nullptr;
 }
 
@@ -251,6 +372,14 @@ void rlfc_env_destroy(rlfc_env* E) {
   if (E->stream) cudaStreamSynchronize(E->stream);
   E->prof_collect();
   for (cudaEvent_t ev : E->event_pool) cudaEventDestroy(ev);
+  for (size_t g = 0; g < E->groups.size(); g++) {
+    auto& G = E->groups[g];
+    for (int a = 0; a < 2; a++) if (G.step_graph[a]) cudaGraphExecDestroy(G.step_graph[a]);
+    if (G.done) cudaEventDestroy(G.done);
+    if (g > 0 && G.st) { cudaStreamSynchronize(G.st); cudaStreamDestroy(G.st); }
+  }
+  if (E->aux_stream) cudaStreamDestroy(E->aux_stream);
+  if (E->fork_ev) cudaEventDestroy(E->fork_ev);
   for (void* p : E->allocs) cudaFree(p);
   for (void* p : {(void*)E->h_actions, (void*)E->h_obs, (void*)E->h_reward, (void*)E->h_force, (void*)E->h_probes,
                   (void*)E->h_done, (void*)E->h_any})
@@ -343,7 +472,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
       const int ns = (mj + 31) / 32, Tsk = 16 /*kSkewPad*/ + ni + 64 /*kSkewTail*/;
       if (ns > 8) return bail(fail(RLFC_EGRID, "grids wider than 256 cells are not supported by the strip smoother yet"));
       std::vector<float4> A((size_t)ns * Tsk * 32, make_float4(0.f, 0.f, 0.f, 0.f));
-      std::vector<float> ninv((size_t)ns * Tsk * 32, 0.f);
+      std::vector<float2> nd((size_t)ns * Tsk * 32, make_float2(0.f, 0.f));
       for (int k = 0; k < ns; k++)
         for (int tp = 0; tp < Tsk; tp++)
           for (int l = 0; l < 32; l++) {
@@ -351,18 +480,17 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
             if (i < 1 || i > ni || j > mj) continue;
             const size_t c = (size_t)i * H.m + j, o = ((size_t)k * Tsk + tp) * 32 + l;
             A[o] = make_float4(H.lx[c], H.lx[c + H.m], H.ly[c], H.ly[c + 1]);
-            ninv[o] = -H.inv[c];
+            nd[o] = make_float2(-H.inv[c], H.diag[c]);
           }
       L.sk.nstrips = ns; L.sk.Tsk = Tsk;
       TRY(upload_vec(E, A, &L.sk.A));
-      TRY(upload_vec(E, ninv, &L.sk.ninv));
+      TRY(upload_vec(E, nd, &L.sk.nd));
       if (l >= 1) sp.coarse_strips = std::max(sp.coarse_strips, ns);
     }
     TRY(E->dmalloc(&L.r, L.stride * B));
     TRY(E->dmalloc(&L.x, L.stride * B));
     TRY(E->dmalloc(&L.d, L.stride * B));
     L.r2 = nullptr;
-    if (l == 0) TRY(E->dmalloc(&L.r2, L.stride * B));
   }
   // body band: faces where the BDIM blend is not the identity (del != 1, del1 != 0, or a control
   // cylinder's velocity kernel is non-zero)
@@ -398,13 +526,19 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   TRY(E->dmalloc(&E->uCx, S)); TRY(E->dmalloc(&E->uCy, S));
   TRY(E->dmalloc(&E->init_ux, sp.stride)); TRY(E->dmalloc(&E->init_uy, sp.stride)); TRY(E->dmalloc(&E->init_p, sp.stride));
   // per-env scalars
-  sp.rr_blocks = ((sp.m + 31) / 32) * ((sp.n + 7) / 8);
+  sp.rr_blocks = 0;
+  int n_groups = cfg->n_groups;
+  if (const char* ev = std::getenv("RLFC_GROUPS")) n_groups = std::atoi(ev);
+  if (n_groups <= 0) n_groups = B >= 64 ? 2 : 1;
+  n_groups = std::min(n_groups, B);
+  if (const char* ev = std::getenv("RLFC_NO_GRAPH")) E->use_graph = std::atoi(ev) == 0;
   TRY(E->dmalloc(&sp.sc.xi, 2 * B)); TRY(E->dmalloc(&sp.sc.t, B)); TRY(E->dmalloc(&sp.sc.force, 2 * B));
   TRY(E->dmalloc(&sp.sc.probes, (size_t)B * RLFC_NUM_PROBES));
   TRY(E->dmalloc(&sp.sc.callLearn, B)); TRY(E->dmalloc(&sp.sc.Cd, B)); TRY(E->dmalloc(&sp.sc.Cl, B));
   TRY(E->dmalloc(&sp.sc.obs, 2 * B)); TRY(E->dmalloc(&sp.sc.active, B)); TRY(E->dmalloc(&sp.sc.iters, 2 * B));
-  TRY(E->dmalloc(&sp.sc.rr_part, (size_t)B * sp.rr_blocks)); TRY(E->dmalloc(&sp.sc.psum, B));
-  TRY(E->dmalloc(&sp.sc.any_active, 1));
+  sp.sc.rr_part = nullptr;
+  TRY(E->dmalloc(&sp.sc.psum, B));
+  TRY(E->dmalloc(&sp.sc.any_active, n_groups));
   TRY(E->dmalloc(&E->d_actions, 2 * B)); TRY(E->dmalloc(&E->d_obs, 2 * B)); TRY(E->dmalloc(&E->d_reward, B));
   TRY(E->dmalloc(&E->d_done, B));
 #undef TRY
@@ -414,6 +548,37 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
       !hostalloc((void**)&E->h_probes, (size_t)B * RLFC_NUM_PROBES * sizeof(float)) ||
       !hostalloc((void**)&E->h_done, B * sizeof(int)) || !hostalloc((void**)&E->h_any, sizeof(int)))
     return bail(fail(RLFC_ENOMEM, "cudaMallocHost failed"));
+
+  // environment groups (contiguous), streams, events
+  if ((rc = configure_kernels(sp))) return bail(fail(RLFC_ECUDA, "kernel attribute configuration failed"));
+  E->groups.resize(n_groups);
+  for (int g = 0; g < n_groups; g++) {
+    rlfc_env::Group& G = E->groups[g];
+    const int e0 = (int)((long long)B * g / n_groups), e1 = (int)((long long)B * (g + 1) / n_groups);
+    G.e0 = e0; G.B = e1 - e0;
+    G.sp = sp;
+    SolverParams& v = G.sp;
+    v.B = G.B;
+    for (int l = 0; l < v.nlevels; l++) {
+      const size_t o = (size_t)e0 * v.lev[l].stride;
+      v.lev[l].r += o; v.lev[l].x += o; v.lev[l].d += o;
+    }
+    v.band_tmp += (size_t)e0 * (v.nband_x + v.nband_y);
+    v.sc.xi += 2 * e0; v.sc.t += e0; v.sc.force += 2 * e0; v.sc.probes += (size_t)e0 * RLFC_NUM_PROBES;
+    v.sc.callLearn += e0; v.sc.Cd += e0; v.sc.Cl += e0; v.sc.obs += 2 * e0; v.sc.active += e0; v.sc.iters += 2 * e0;
+    v.sc.psum += e0; v.sc.any_active += g;
+    const size_t o = (size_t)e0 * sp.stride;
+    G.uAx = E->uAx + o; G.uAy = E->uAy + o; G.uBx = E->uBx + o; G.uBy = E->uBy + o; G.uCx = E->uCx + o; G.uCy = E->uCy + o;
+    if (g == 0) G.st = E->stream;
+    else if (cudaStreamCreateWithFlags(&G.st, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(RLFC_ECUDA, "cudaStreamCreate failed"));
+    if (cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming) != cudaSuccess) return bail(fail(RLFC_ECUDA, "cudaEventCreate failed"));
+  }
+  E->whole.e0 = 0; E->whole.B = B; E->whole.sp = sp; E->whole.st = E->stream;
+  E->whole.uAx = E->uAx; E->whole.uAy = E->uAy; E->whole.uBx = E->uBx; E->whole.uBy = E->uBy;
+  E->whole.uCx = E->uCx; E->whole.uCy = E->uCy;
+  if (cudaStreamCreateWithFlags(&E->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&E->fork_ev, cudaEventDisableTiming) != cudaSuccess)
+    return bail(fail(RLFC_ECUDA, "stream/event creation failed"));
 
   if ((rc = load_initial_state(E))) return bail(rc);
   if ((rc = rlfc_env_reset(E, nullptr, B, 1))) return bail(rc);
@@ -456,10 +621,8 @@ int rlfc_env_step_device(rlfc_env* E, const float* d_actions, float* d_obs, floa
   CU(cudaSetDevice(E->device));
   SolverParams& sp = E->sp;
   E->launches += launch_set_actions(sp, d_actions, E->stream);
-  for (int s = 0; s < sp.substeps; s++) {
-    int rc = solver_step(E, 1);
-    if (rc) return rc;
-  }
+  int rc = solver_steps(E, sp.substeps, 1);
+  if (rc) return rc;
   E->launches += launch_emit_obs(sp, d_actions, d_obs, d_reward, d_done, E->stream);
   CU(cudaGetLastError());
   return RLFC_OK;
@@ -493,7 +656,7 @@ int rlfc_env_substep(rlfc_env* E, const float* actions, float* force, float* pro
     CU(cudaMemcpyAsync(E->d_actions, E->h_actions, 2 * B * sizeof(float), cudaMemcpyHostToDevice, E->stream));
     E->launches += launch_set_actions(sp, E->d_actions, E->stream);
   }
-  int rc = solver_step(E, 0);
+  int rc = solver_steps(E, 1, 0);
   if (rc) return rc;
   if (force) CU(cudaMemcpyAsync(E->h_force, sp.sc.force, 2 * B * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
   if (probes)

@@ -20,7 +20,7 @@ constexpr int kMaxLevels = 16;
 // entry [(k*Tsk + tau + kSkewPad)*32 + lane] belongs to cell (i = tau - lane + 1, j = 32k + lane + 1).
 struct SkewLevel {
   const float4* A;          // (lx[i][j], lx[i+1][j], ly[i][j], ly[i][j+1])
-  const float* ninv;        // -inv[i][j]
+  const float2* nd;         // (-inv[i][j], diag[i][j])
   int nstrips, Tsk;
 };
 
@@ -84,19 +84,22 @@ struct SolverParams {
   EnvScalars sc;
 };
 
+// opt-in shared-memory attributes of the strip kernels; call once per handle before the first launch / capture
+int configure_kernels(const SolverParams& P);
+
 // ---- launch wrappers (solver_kernels.cu).  All enqueue on `st`; return number of launches. ----
 int launch_advdif(const SolverParams& P, const float* srcx, const float* srcy, const float* u0x, const float* u0y,
                   float* dstx, float* dsty, cudaStream_t st);
 int launch_band_bc(const SolverParams& P, float* ux, float* uy, cudaStream_t st);
 int launch_residual(const SolverParams& P, const float* ux, const float* uy, float* r, int which, cudaStream_t st);
-// one MG iteration (V-cycle + smooth(4)) on active envs = down0, coarse, up0, gs0, inc0, conv;
+// one MG iteration (V-cycle + smooth(4)) on active envs = down0, coarse, up0, smooth0;
 // r_in/r_out are the level-0 ping-pong residual buffers
 int launch_mg_down0(const SolverParams& P, const float* r_in, float* r_out, cudaStream_t st);
 int launch_mg_coarse(const SolverParams& P, cudaStream_t st);
 int launch_mg_up0(const SolverParams& P, float* r, cudaStream_t st);
-int launch_gs0(const SolverParams& P, const float* r, cudaStream_t st);
-int launch_inc0(const SolverParams& P, float* r, cudaStream_t st);
-int launch_conv(const SolverParams& P, int which, cudaStream_t st);
+int launch_smooth0(const SolverParams& P, const float* r_in, float* r_out, int which, cudaStream_t st);
+// last node of the MG iteration body inside a CUDA-graph WHILE node: cond = any env still active
+int launch_loopcond(const SolverParams& P, unsigned long long cond_handle, cudaStream_t st);
 int launch_psum(const SolverParams& P, cudaStream_t st);
 int launch_project_u(const SolverParams& P, float* ux, float* uy, cudaStream_t st);
 int launch_shift_p(const SolverParams& P, cudaStream_t st);

@@ -12,9 +12,7 @@
 //   k_mg_down0    level-0 smooth(0) + increment + residual restriction  MG.pde:68-70,79-97,124-137
 //   k_mg_coarse   levels >= 1 of the V-cycle in one CTA per env          MG.pde:68-97,124-152
 //   k_mg_up0      level-0 prolongation + increment                       MG.pde:75-76,139-152
-//   k_gs0         level-0 smooth(4): lexicographic Gauss-Seidel wavefronts MG.pde:79-89
-//   k_inc0        level-0 d.setBC + increment + partial r.r              MG.pde:90-97, Field.pde:302-310
-//   k_conv        r.r < tol test, per-env iteration bookkeeping          MG.pde:30-38
+//   k_smooth0     level-0 smooth(4) + increment + r.r + loop test (strip sweep) MG.pde:30-38,79-97, Field.pde:302-310
 //   k_psum        serial float interior sum of p                        Field.pde:311-318
 //   k_project_u   gradient of the mean-shifted p, velocity correction   VectorField.pde:136-139
 //   k_shift_p     p += -sum(p)/N on all cells                            VectorField.pde:136
@@ -455,66 +453,43 @@ k_mg_up0(const __grid_constant__ SolverParams q, float* __restrict__ r_all) {
   }
 }
 
-// level 0 smooth(4), part 1: d = r*inv, then the four Gauss-Seidel sweeps; one CTA (one warp per
-// 32-column strip) per env, see smooth_strip.cuh
+// level 0 smooth(4) complete (MG.pde:79-97) + the MGsolver loop test (MG.pde:32-35), one CTA per env with one
+// warp per 32-column strip (smooth_strip.cuh, XMODE 3): d = r*inv, four lexicographic Gauss-Seidel sweeps,
+// d.setBC, x += d (p, ghosts included), r -= A d, r.r accumulated in double, then iter++ and the
+// `r.r < tol` / `iter == itmx` decision for this environment.
 __global__ void __launch_bounds__(256)
-k_gs0(const __grid_constant__ SolverParams q, const float* r_all) {
+k_smooth0(const __grid_constant__ SolverParams q, const float* r_in_all, float* r_out_all, int which) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const DevLevel& L = q.lev[0];
+  const int ns = L.sk.nstrips, n = L.n, m = L.m, P = L.P, ni = n - 2, mj = m - 2;
   StripShared* sh = reinterpret_cast<StripShared*>(smem_raw);
-  StripMail* mail = reinterpret_cast<StripMail*>(smem_raw + sizeof(StripShared) * L.sk.nstrips);
+  StripMail* mail = reinterpret_cast<StripMail*>(smem_raw + sizeof(StripShared) * ns);
+  float* gbuf = reinterpret_cast<float*>(smem_raw + sizeof(StripShared) * ns + sizeof(StripMail) * (ns + 2));
+  __shared__ double wsum[32];
   const int e = blockIdx.x;
   if (!q.sc.active[e]) return;
-  strip_smooth<0>(L, r_all + (size_t)e * L.stride, L.d + (size_t)e * L.stride, sh, mail);
-}
-
-// level 0 smooth(4), part 2: d.setBC (clamped reads), x += d, r -= A d, partial sums of r.r
-__global__ void __launch_bounds__(256)
-k_inc0(const __grid_constant__ SolverParams q, float* __restrict__ r_all) {
-  const int e = blockIdx.z;
-  if (!q.sc.active[e]) return;
-  const DevLevel& L0 = q.lev[0];
-  const int P = L0.P, n = L0.n, m = L0.m;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = blockIdx.y * blockDim.y + threadIdx.y;
-  const size_t eo = (size_t)e * L0.stride;
-  const float* d = L0.d + eo;
-  double rr = 0.0;
-  if (i < n && j < m) {
-    auto dval = [&](int a, int b) { return d[IDX(min(max(a, 1), n - 2), min(max(b, 1), m - 2))]; };
-    const int k = IDX(i, j);
-    const float dc = dval(i, j);
-    L0.x[eo + k] += dc;
-    if (i >= 1 && j >= 1 && i <= n - 2 && j <= m - 2) {
-      float Ad = dc * L0.diag[k] + dval(i - 1, j) * L0.lx[k] + dval(i + 1, j) * L0.lx[k + P] +
-                 dval(i, j - 1) * L0.ly[k] + dval(i, j + 1) * L0.ly[k + 1];
-      float rn = r_all[eo + k] - Ad;
-      r_all[eo + k] = rn;
-      float prod = rn * rn;                       // float product, double accumulation (Field.pde:304-307)
-      rr = (double)prod;
-    }
+  float* p = L.x + (size_t)e * L.stride;
+  double rr = strip_smooth<3>(L, r_in_all + (size_t)e * L.stride, p, sh, mail, gbuf, r_out_all + (size_t)e * L.stride);
+  // ghost cells of x: x.plusEq(d) runs over all cells and d.setBC copied the adjacent interior value (MG.pde:90,95)
+  const float *gtop = gbuf, *gbot = gbuf + mj, *gleft = gbuf + 2 * mj, *gright = gbuf + 2 * mj + ni;
+  for (int c = threadIdx.x; c < mj; c += blockDim.x) { p[IDX(0, c + 1)] += gtop[c]; p[IDX(n - 1, c + 1)] += gbot[c]; }
+  for (int c = threadIdx.x; c < ni; c += blockDim.x) { p[IDX(c + 1, 0)] += gleft[c]; p[IDX(c + 1, m - 1)] += gright[c]; }
+  if (threadIdx.x == 0) {
+    p[IDX(0, 0)] += gtop[0]; p[IDX(0, m - 1)] += gtop[mj - 1];
+    p[IDX(n - 1, 0)] += gbot[0]; p[IDX(n - 1, m - 1)] += gbot[mj - 1];
   }
-  // deterministic block reduction
-  __shared__ double sred[256];
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  sred[tid] = rr;
+  // r.r: fixed-order reduction (lanes by shuffle tree, then warps in order)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rr += __shfl_down_sync(0xffffffffu, rr, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = rr;
   __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (tid < s) sred[tid] += sred[tid + s];
-    __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += wsum[w];
+    const int it = ++q.sc.iters[2 * e + which];
+    if ((float)s < q.mg_tol || it >= q.mg_max_iters) q.sc.active[e] = 0;
+    else atomicExch(q.sc.any_active, 1);
   }
-  if (tid == 0) q.sc.rr_part[(size_t)e * q.rr_blocks + blockIdx.y * gridDim.x + blockIdx.x] = sred[0];
-}
-
-// MGsolver loop test (MG.pde:32-35): iter++, stop when r.r < tol or iter reaches itmx
-__global__ void k_conv(const __grid_constant__ SolverParams q, int which, int itmx) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= q.B || !q.sc.active[e]) return;
-  double s = 0;
-  for (int b = 0; b < q.rr_blocks; b++) s += q.sc.rr_part[(size_t)e * q.rr_blocks + b];
-  const int it = ++q.sc.iters[2 * e + which];
-  if ((float)s < q.mg_tol || it >= itmx) q.sc.active[e] = 0;
-  else atomicExch(q.sc.any_active, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -688,6 +663,15 @@ __global__ void k_emit_obs(const __grid_constant__ SolverParams q, const float* 
   if (done) done[e] = q.sc.t[e] >= q.episode_time ? 1 : 0;
 }
 
+// end of one MGsolver iteration inside a CUDA-graph WHILE node: continue while any env is still active
+__global__ void k_loopcond(cudaGraphConditionalHandle h, int* any_active) {
+  if (threadIdx.x == 0) {
+    const unsigned v = *any_active ? 1u : 0u;
+    *any_active = 0;
+    cudaGraphSetConditional(h, v);
+  }
+}
+
 inline dim3 grid2d(int m, int n, int B, dim3 blk) { return dim3((m + blk.x - 1) / blk.x, (n + blk.y - 1) / blk.y, B); }
 
 }  // namespace
@@ -722,8 +706,12 @@ int launch_residual(const SolverParams& q, const float* ux, const float* uy, flo
   return 1;
 }
 
+int launch_loopcond(const SolverParams& q, unsigned long long handle, cudaStream_t st) {
+  k_loopcond<<<1, 32, 0, st>>>((cudaGraphConditionalHandle)handle, q.sc.any_active);
+  return 1;
+}
+
 int launch_mg_down0(const SolverParams& q, const float* r_in, float* r_out, cudaStream_t st) {
-  cudaMemsetAsync(q.sc.any_active, 0, sizeof(int), st);
   dim3 blk(32, 8);
   const DevLevel& L1 = q.lev[1];
   k_mg_down0<<<grid2d(L1.m - 2, L1.n - 2, q.B, blk), blk, 0, st>>>(q, r_in, r_out);
@@ -732,13 +720,19 @@ int launch_mg_down0(const SolverParams& q, const float* r_in, float* r_out, cuda
 
 static size_t strip_smem(int nstrips) { return sizeof(StripShared) * nstrips + sizeof(StripMail) * (nstrips + 2); }
 
+static size_t smooth0_smem(const SolverParams& q) {
+  return strip_smem(q.lev[0].sk.nstrips) + sizeof(float) * (2 * (q.n - 2) + 2 * (q.m - 2));
+}
+
+// opt-in shared-memory sizes; called once per handle, outside any stream capture
+int configure_kernels(const SolverParams& q) {
+  cudaError_t e1 = cudaFuncSetAttribute(k_mg_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)strip_smem(q.coarse_strips));
+  cudaError_t e2 = cudaFuncSetAttribute(k_smooth0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smooth0_smem(q));
+  return (e1 == cudaSuccess && e2 == cudaSuccess) ? 0 : -1;
+}
+
 int launch_mg_coarse(const SolverParams& q, cudaStream_t st) {
   const size_t smem = strip_smem(q.coarse_strips);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(k_mg_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
   k_mg_coarse<<<q.B, max(256, 32 * q.coarse_strips), smem, st>>>(q);
   return 1;
 }
@@ -749,26 +743,10 @@ int launch_mg_up0(const SolverParams& q, float* r, cudaStream_t st) {
   return 1;
 }
 
-int launch_gs0(const SolverParams& q, const float* r, cudaStream_t st) {
+int launch_smooth0(const SolverParams& q, const float* r_in, float* r_out, int which, cudaStream_t st) {
   const int ns = q.lev[0].sk.nstrips;
-  const size_t smem = strip_smem(ns);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(k_gs0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
-  k_gs0<<<q.B, 32 * ns, smem, st>>>(q, r);
-  return 1;
-}
-
-int launch_inc0(const SolverParams& q, float* r, cudaStream_t st) {
-  dim3 blk(32, 8);
-  k_inc0<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, r);
-  return 1;
-}
-
-int launch_conv(const SolverParams& q, int which, cudaStream_t st) {
-  k_conv<<<(q.B + 127) / 128, 128, 0, st>>>(q, which, q.mg_max_iters);
+  const size_t smem = smooth0_smem(q);
+  k_smooth0<<<q.B, 32 * ns, smem, st>>>(q, r_in, r_out, which);
   return 1;
 }
 
