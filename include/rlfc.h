@@ -136,6 +136,10 @@ long long rlfc_env_launch_count(const rlfc_env *env);
    counts of the last step; used by bench.py for the roofline line. */
 double rlfc_env_model_bytes_per_solver_step(const rlfc_env *env);
 
+/* java.lang.Float.toString(v) (what String.valueOf(float) / ""+float give in the reference: checkpoint lines,
+   SaveScalar traces, the "<Cl>_<Cd>" RPC payload, clientCFD.pde:119).  Returns the length. */
+int  rlfc_format_float_java(float v, char *buf, int cap);
+
 const char *rlfc_last_error(void);
 const char *rlfc_version(void);
 

@@ -424,6 +424,8 @@ std::string java_float(float v) {
 }
 }  // namespace
 
+std::string format_float_java(float v) { return java_float(v); }
+
 int write_bdim_text(const std::string& path, int n, int m, float t, float dt, const float* ux, const float* uy,
                     const float* p, std::string& err) {
   FILE* f = std::fopen(path.c_str(), "w");

@@ -55,6 +55,8 @@ int build_geometry(const rlfc_config& cfg, Geometry& g, std::string& err);
 // Checkpoint IO (BDIM.write / BDIM.resume text format BDIM.pde:226-251, and the .bdimb binary form).
 int read_checkpoint(const std::string& path, int n, int m, float& t, float& dt,
                     std::vector<float>& ux, std::vector<float>& uy, std::vector<float>& p, std::string& err);
+// java.lang.Float.toString(v): the text form the reference writes into checkpoints, traces and RPC payloads
+std::string format_float_java(float v);
 int write_bdim_text(const std::string& path, int n, int m, float t, float dt,
                     const float* ux, const float* uy, const float* p, std::string& err);
 

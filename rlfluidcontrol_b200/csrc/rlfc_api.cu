@@ -815,6 +815,14 @@ int rlfc_env_get_profile(rlfc_env* E, int idx, char* name, int name_cap, double*
   return RLFC_OK;
 }
 
+int rlfc_format_float_java(float v, char* buf, int cap) {
+  if (!buf || cap <= 0) return RLFC_EINVAL;
+  const std::string s = format_float_java(v);
+  std::strncpy(buf, s.c_str(), cap - 1);
+  buf[cap - 1] = 0;
+  return (int)s.size();
+}
+
 void* rlfc_env_stream(rlfc_env* E) { return E ? (void*)E->stream : nullptr; }
 long long rlfc_env_launch_count(const rlfc_env* E) { return E ? E->launches : 0; }
 

@@ -1,0 +1,37 @@
+"""Multi-GPU sharding of batched environments: environments are independent, so global env ids are
+split contiguously over ranks (one process per GPU) and the only exchange is the gather of the per-step
+observations (2 floats per env) for a policy that wants the whole batch."""
+from __future__ import annotations
+
+
+def shard_range(n_envs_total: int, rank: int, world: int) -> tuple[int, int]:
+    """[e0, e1) of the global env ids owned by `rank` (contiguous, sizes differ by at most one)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    e0 = n_envs_total * rank // world
+    e1 = n_envs_total * (rank + 1) // world
+    return e0, e1
+
+
+def gather_observations(obs, world: int, group=None):
+    """All-gather the (B_local, 2) observation tensors of every rank into (B_total, 2) (equal shard sizes).
+    Works with the gloo backend on CPU tensors and the nccl backend on CUDA tensors."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return obs
+    out = torch.empty((world * obs.shape[0],) + tuple(obs.shape[1:]), dtype=obs.dtype, device=obs.device)
+    dist.all_gather_into_tensor(out, obs.contiguous(), group=group)
+    return out
+
+
+def max_over_ranks(value: float, world: int, device="cpu") -> float:
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
