@@ -46,7 +46,7 @@ def workload_config(envs_per_gpu, n_gpus):
                     "synthetic per-env actions a=clip(0.8 sin(2 pi k/25 + 2 pi e/256)+0.1 N(0,1)) (env 0: config-1 sequence)",
         "envs_per_gpu": envs_per_gpu, "n_envs_total": envs_per_gpu * n_gpus, "substeps": 16,
         "mode": "exact (bit-identical to the oracle)", "l2": "per-GPU state >> 126 MB L2 (inputs larger than L2)",
-        "parallelism": f"env-sharded x{n_gpus}, no collective",
+        "parallelism": f"env-sharded x{n_gpus}, no data-path collective (observations all-gathered once per env-step)",
     }
 
 
@@ -274,8 +274,12 @@ def run_b200(args):
     done_dev = torch.empty(B, dtype=torch.int32, device="cuda")
     torch.cuda.synchronize()
 
+    obs_all = torch.empty((B * world, 2), dtype=torch.float32, device="cuda") if world > 1 else None
+
     def dev_step(k):
         env.step_device(acts_dev[k].data_ptr(), obs_dev.data_ptr(), rew_dev.data_ptr(), done_dev.data_ptr())
+        if world > 1:   # the one exchange of the env-sharded path: every rank sees the whole batch's observations
+            dist.all_gather_into_tensor(obs_all, obs_dev)
 
     step_idx = 0
     with torch.cuda.stream(stream):

@@ -65,8 +65,11 @@ def test_execution_modes_are_equivalent(rlfc, mode, monkeypatch):
 
     def run(init):
         with rlfc.AFCCylinderBatch(B, init_state=init) as env:
-            fs = [env.update2(acts if k == 0 else None).copy() for k in range(3)]
-            return fs, env.get_fields(B - 1), env.mg_iters().copy()
+            fs, its = [], []
+            for k in range(3):
+                fs.append(env.update2(acts if k == 0 else None).copy())
+                its.append(env.mg_iters().copy())
+            return fs, env.get_fields(B - 1), np.stack(its)
 
     base = {init: run(init) for init in ("default", None)}
     if mode == "eager":
