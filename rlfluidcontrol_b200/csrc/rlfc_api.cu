@@ -59,7 +59,7 @@ struct rlfc_env {
   // Environment groups: the batch is split into contiguous groups, each advanced by its own stream (and its own
   // CUDA graphs), so the latency-bound per-env kernels of one group overlap the bandwidth-bound kernels of another.
   struct Group {
-    int e0 = 0, B = 0;
+    int e0 = 0, B = 0, index = 0;
     SolverParams sp{};                       // view of the batch arrays restricted to [e0, e0 + B)
     float *uAx = nullptr, *uAy = nullptr, *uBx = nullptr, *uBy = nullptr, *uCx = nullptr, *uCy = nullptr;
     cudaStream_t st = nullptr;               // group 0 runs on the handle's stream
@@ -72,9 +72,13 @@ struct rlfc_env {
   cudaStream_t aux_stream = nullptr;         // used to capture the bodies of the conditional nodes
   cudaEvent_t fork_ev = nullptr;
   bool use_graph = true;
+  bool eager_groups = false;
+  int fixed_iters = 0;                       // experiment: > 0 = that many unconditional MG iterations per solve, no WHILE node
   // optional per-kernel CUDA-event timing (rlfc_env_set_profiling)
   bool profiling = false;
-  struct ProfRec { int id; cudaEvent_t e0, e1; };
+  struct ProfRec { int id; cudaEvent_t e0, e1; int group; };
+  cudaEvent_t trace_base = nullptr;          // RLFC_TRACE=<csv path>: per-launch (group, kernel, start, end) timeline
+  std::string trace_path;
   std::vector<ProfRec> prof_recs;
   std::vector<cudaEvent_t> event_pool;
   struct ProfAgg { std::string name; double ms = 0; long long count = 0; double floats_per_cell = 0; };
@@ -91,17 +95,30 @@ struct rlfc_env {
   }
   // run one kernel launch, optionally bracketed by events on the handle's stream
   template <typename F>
-  void run(const char* name, double floats_per_cell, F&& launch) {
+  void run(const char* name, double floats_per_cell, F&& launch, cudaStream_t st = nullptr, int group = 0) {
     if (!profiling) { launches += launch(); return; }
-    ProfRec r{prof_id(name, floats_per_cell), get_event(), get_event()};
-    cudaEventRecord(r.e0, stream);
+    if (!st) st = stream;
+    ProfRec r{prof_id(name, floats_per_cell), get_event(), get_event(), group};
+    cudaEventRecord(r.e0, st);
     launches += launch();
-    cudaEventRecord(r.e1, stream);
+    cudaEventRecord(r.e1, st);
     prof_recs.push_back(r);
   }
   void prof_collect() {
     if (prof_recs.empty()) return;
     cudaStreamSynchronize(stream);
+    for (auto& G : groups) if (G.st) cudaStreamSynchronize(G.st);
+    if (!trace_path.empty() && trace_base) {
+      if (FILE* f = std::fopen(trace_path.c_str(), "a")) {
+        for (auto& r : prof_recs) {
+          float a = 0, b = 0;
+          cudaEventElapsedTime(&a, trace_base, r.e0);
+          cudaEventElapsedTime(&b, trace_base, r.e1);
+          std::fprintf(f, "%d,%s,%.4f,%.4f\n", r.group, prof[r.id].name.c_str(), a, b);
+        }
+        std::fclose(f);
+      }
+    }
     for (auto& r : prof_recs) {
       float ms = 0;
       cudaEventElapsedTime(&ms, r.e0, r.e1);
@@ -182,24 +199,26 @@ using Group = rlfc_env::Group;
 int project_eager(rlfc_env* E, Group& G, float* Ux, float* Uy, int which) {
   SolverParams& sp = G.sp;
   cudaStream_t st = G.st;
+  const int gi = G.index;
   float* r = sp.lev[0].r;
   float* rs = sp.lev[0].d;
-  E->run("k_residual", 4, [&] { return launch_residual(sp, Ux, Uy, r, which, st); });
-  for (int it = 0; it < sp.mg_max_iters; it++) {
+  E->run("k_residual", 4, [&] { return launch_residual(sp, Ux, Uy, r, which, st); }, st, gi);
+  for (int it = 0; it < (E->fixed_iters > 0 ? E->fixed_iters : sp.mg_max_iters); it++) {
     CU(cudaMemsetAsync(sp.sc.any_active, 0, sizeof(int), st));
-    E->run("k_mg_down0", 4.25, [&] { return launch_mg_down0(sp, r, rs, st); });
-    E->run("k_mg_coarse", 0.5, [&] { return launch_mg_coarse(sp, st); });
-    E->run("k_mg_up0", 4.25, [&] { return launch_mg_up0(sp, rs, st); });
-    E->run("k_smooth0", 4, [&] { return launch_smooth0(sp, rs, r, which, st); });
+    E->run("k_mg_down0", 4.25, [&] { return launch_mg_down0(sp, r, rs, st); }, st, gi);
+    E->run("k_mg_coarse", 0.5, [&] { return launch_mg_coarse(sp, st); }, st, gi);
+    E->run("k_mg_up0", 4.25, [&] { return launch_mg_up0(sp, rs, st); }, st, gi);
+    E->run("k_smooth0", 4, [&] { return launch_smooth0(sp, rs, r, which, st); }, st, gi);
+    E->mg_iter_launch_rounds++;
+    if (E->fixed_iters > 0) continue;
     CU(cudaMemcpyAsync(E->h_any, sp.sc.any_active, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    E->mg_iter_launch_rounds++;
     if (!*E->h_any) break;
   }
-  E->run("k_psum", 1, [&] { return launch_psum(sp, st); });
-  E->run("k_project_u", 5, [&] { return launch_project_u(sp, Ux, Uy, st); });
-  E->run("k_shift_p", 2, [&] { return launch_shift_p(sp, st); });
-  E->run("k_bc", 0, [&] { return launch_bc(sp, Ux, Uy, st); });
+  E->run("k_psum", 1, [&] { return launch_psum(sp, st); }, st, gi);
+  E->run("k_project_u", 5, [&] { return launch_project_u(sp, Ux, Uy, st); }, st, gi);
+  E->run("k_shift_p", 2, [&] { return launch_shift_p(sp, st); }, st, gi);
+  E->run("k_bc", 0, [&] { return launch_bc(sp, Ux, Uy, st); }, st, gi);
   return RLFC_OK;
 }
 
@@ -207,17 +226,18 @@ int project_eager(rlfc_env* E, Group& G, float* Ux, float* Uy, int which) {
 int solver_step_eager(rlfc_env* E, Group& G, int accumulate) {
   SolverParams& sp = G.sp;
   cudaStream_t st = G.st;
+  const int gi = G.index;
   int rc;
   // predictor BDIM.update(): u0 = u (buffer A), F = AdvDif(u) -> B, updateUP
-  E->run("k_advdif", 5, [&] { return launch_advdif(sp, G.uAx, G.uAy, G.uAx, G.uAy, G.uBx, G.uBy, st); });
-  E->run("k_band_bc", 0, [&] { return launch_band_bc(sp, G.uBx, G.uBy, st); });
+  E->run("k_advdif", 5, [&] { return launch_advdif(sp, G.uAx, G.uAy, G.uAx, G.uAy, G.uBx, G.uBy, st); }, st, gi);
+  E->run("k_band_bc", 0, [&] { return launch_band_bc(sp, G.uBx, G.uBy, st); }, st, gi);
   if ((rc = project_eager(E, G, G.uBx, G.uBy, 0))) return rc;
   // corrector BDIM.update2(): us = u (B), F = AdvDif(u; + u0) -> C, updateUP, u = (u + us)/2 -> A
-  E->run("k_advdif", 5, [&] { return launch_advdif(sp, G.uBx, G.uBy, G.uAx, G.uAy, G.uCx, G.uCy, st); });
-  E->run("k_band_bc", 0, [&] { return launch_band_bc(sp, G.uCx, G.uCy, st); });
+  E->run("k_advdif", 5, [&] { return launch_advdif(sp, G.uBx, G.uBy, G.uAx, G.uAy, G.uCx, G.uCy, st); }, st, gi);
+  E->run("k_band_bc", 0, [&] { return launch_band_bc(sp, G.uCx, G.uCy, st); }, st, gi);
   if ((rc = project_eager(E, G, G.uCx, G.uCy, 1))) return rc;
-  E->run("k_heun", 6, [&] { return launch_heun(sp, G.uCx, G.uCy, G.uBx, G.uBy, G.uAx, G.uAy, st); });
-  E->run("k_force", 0, [&] { return launch_force(sp, accumulate, st); });
+  E->run("k_heun", 6, [&] { return launch_heun(sp, G.uCx, G.uCy, G.uBx, G.uBy, G.uAx, G.uAy, st); }, st, gi);
+  E->run("k_force", 0, [&] { return launch_force(sp, accumulate, st); }, st, gi);
   CU(cudaGetLastError());
   return RLFC_OK;
 }
@@ -232,6 +252,19 @@ int capture_half_step(rlfc_env* E, Group& G, cudaStream_t st, const float* sx, c
   *n_outer += launch_advdif(sp, sx, sy, u0x, u0y, dx, dy, st);
   *n_outer += launch_band_bc(sp, dx, dy, st);
   *n_outer += launch_residual(sp, dx, dy, r, which, st);
+  if (E->fixed_iters > 0) {
+    for (int it = 0; it < E->fixed_iters; it++) {
+      *n_body += launch_mg_down0(sp, r, rs, st);
+      *n_body += launch_mg_coarse(sp, st);
+      *n_body += launch_mg_up0(sp, rs, st);
+      *n_body += launch_smooth0(sp, rs, r, which, st);
+    }
+    *n_outer += launch_psum(sp, st);
+    *n_outer += launch_project_u(sp, dx, dy, st);
+    *n_outer += launch_shift_p(sp, st);
+    *n_outer += launch_bc(sp, dx, dy, st);
+    return RLFC_OK;
+  }
   // ---- WHILE node ----
   cudaStreamCaptureStatus status;
   cudaGraph_t graph;
@@ -305,10 +338,18 @@ int join_groups(rlfc_env* E) {
 int solver_steps(rlfc_env* E, int nsteps, int accumulate) {
   int rc;
   const bool graph = E->use_graph && !E->profiling;
-  if (!graph) {
+  if (!graph && !(E->fixed_iters > 0 && E->eager_groups)) {
     for (int s = 0; s < nsteps; s++)
       if ((rc = solver_step_eager(E, E->whole, accumulate))) return rc;
     return RLFC_OK;
+  }
+  if (!graph) {   // experiment: eager launches on the group streams, fixed MG iteration count (no host sync)
+    if (E->profiling && !E->trace_base) { cudaEventCreate(&E->trace_base); cudaEventRecord(E->trace_base, E->stream); }
+    if ((rc = fork_groups(E))) return rc;
+    for (int s = 0; s < nsteps; s++)
+      for (auto& G : E->groups)
+        if ((rc = solver_step_eager(E, G, accumulate))) return rc;
+    return join_groups(E);
   }
   if ((rc = fork_groups(E))) return rc;
   for (auto& G : E->groups) {
@@ -439,6 +480,8 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   sp.action_scale = cfg->action_scale;
   sp.inv_cells = (float)((g.n - 2) * (g.m - 2));
   sp.mg_tol = g.mg_tol;
+  sp.use_rows = 1;
+  if (const char* ev = std::getenv("RLFC_SMOOTHER")) sp.use_rows = std::string(ev) != "strip";
   sp.nlevels = (int)g.levels.size();
   sp.resolution = cfg->resolution; sp.substeps = cfg->substeps; sp.mg_max_iters = cfg->mg_max_iters;
   sp.init_time = cfg->init_time; sp.episode_time = cfg->episode_time;
@@ -487,6 +530,35 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
       TRY(upload_vec(E, nd, &L.sk.nd));
       if (l >= 1) sp.coarse_strips = std::max(sp.coarse_strips, ns);
     }
+    {  // pre-skewed coefficient table for the row-pipelined smoother (layout: solver.h RowTab)
+      const int ni = H.n - 2, mj = H.m - 2;
+      const int C = (mj + 31) / 32, K = (4 * C + 1 + 3) / 4, nl = (mj + C - 1) / C;
+      const int front = 10 /*kTabFront*/, entries = front + ni + nl + 10 /*kStageLag*/ + 5 /*kPF*/ + 6;
+      if (C > 8) return bail(fail(RLFC_EGRID, "grids wider than 256 cells are not supported by the smoother yet"));
+      std::vector<float4> T((size_t)entries * K * 32, make_float4(0.f, 0.f, 0.f, 0.f));
+      std::vector<float> f(4 * K);
+      for (int e = 0; e < entries; e++)
+        for (int ln = 0; ln < 32; ln++) {
+          const int row = (e - front) - ln, j0 = C * ln + 1;
+          std::fill(f.begin(), f.end(), 0.f);
+          for (int c = 0; c < C; c++) {
+            const int j = j0 + c;
+            if (row >= 1 && row <= ni + 1 && j <= mj) f[2 * C + 1 + c] = H.lx[(size_t)row * H.m + j];
+            if (row >= 1 && row <= ni && j <= mj) {
+              f[C + 1 + c] = -H.inv[(size_t)row * H.m + j];
+              f[3 * C + 1 + c] = H.diag[(size_t)row * H.m + j];
+            }
+          }
+          for (int c = 0; c <= C; c++) {
+            const int j = j0 + c;
+            if (row >= 1 && row <= ni && j <= mj + 1) f[c] = H.ly[(size_t)row * H.m + j];
+          }
+          for (int k = 0; k < K; k++)
+            T[((size_t)e * K + k) * 32 + ln] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+        }
+      L.rt.C = C; L.rt.K = K; L.rt.entries = entries;
+      TRY(upload_vec(E, T, &L.rt.T));
+    }
     TRY(E->dmalloc(&L.r, L.stride * B));
     TRY(E->dmalloc(&L.x, L.stride * B));
     TRY(E->dmalloc(&L.d, L.stride * B));
@@ -532,6 +604,9 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   if (n_groups <= 0) n_groups = B >= 64 ? 2 : 1;
   n_groups = std::min(n_groups, B);
   if (const char* ev = std::getenv("RLFC_NO_GRAPH")) E->use_graph = std::atoi(ev) == 0;
+  if (const char* ev = std::getenv("RLFC_FIXED_ITERS")) E->fixed_iters = std::atoi(ev);
+  if (const char* ev = std::getenv("RLFC_EAGER_GROUPS")) E->eager_groups = std::atoi(ev) != 0;
+  if (const char* ev = std::getenv("RLFC_TRACE")) E->trace_path = ev;
   TRY(E->dmalloc(&sp.sc.xi, 2 * B)); TRY(E->dmalloc(&sp.sc.t, B)); TRY(E->dmalloc(&sp.sc.force, 2 * B));
   TRY(E->dmalloc(&sp.sc.probes, (size_t)B * RLFC_NUM_PROBES));
   TRY(E->dmalloc(&sp.sc.callLearn, B)); TRY(E->dmalloc(&sp.sc.Cd, B)); TRY(E->dmalloc(&sp.sc.Cl, B));
@@ -555,7 +630,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   for (int g = 0; g < n_groups; g++) {
     rlfc_env::Group& G = E->groups[g];
     const int e0 = (int)((long long)B * g / n_groups), e1 = (int)((long long)B * (g + 1) / n_groups);
-    G.e0 = e0; G.B = e1 - e0;
+    G.e0 = e0; G.B = e1 - e0; G.index = g;
     G.sp = sp;
     SolverParams& v = G.sp;
     v.B = G.B;

@@ -1,0 +1,350 @@
+// smooth_rows.cuh -- exact lexicographic Gauss-Seidel smoothing (MG.smooth, MG.pde:79-97) as a
+// row pipeline with one warp per sweep.
+//
+// The serial reference updates d[i][j] in place with i outer, j inner, so cell (i,j) sees NEW values at
+// (i-1,j), (i,j-1) and OLD values (previous sweep) at (i+1,j), (i,j+1).  Mapping, per level and environment
+// (one CTA of kRowsWarps warps; tools/rows_schedule_model.py is a numpy model of exactly this schedule):
+//   * lane L owns the C = ceil(mj/32) consecutive columns j0 = C*L+1 .. C*L+C and walks down the rows, one
+//     row per step; lanes are skewed by one step, so within a step the lane's C cells form the only serial
+//     chain (C dependent updates) and (i,j0-1) was finished by lane L-1 one step earlier;
+//   * stage g of lane L works on row  i = t - L - 2g  at global step t:  stage 0 forms d = r*inv, stages
+//     1..4 are the four sweeps (each two rows behind the previous one: exactly the distance at which it
+//     finds the previous sweep's values at (i+1,j), (i,j+1)), the increment stage (row t - L - 10) applies
+//     d.setBC, x += d and, on level 0, r -= A d;
+//   * every stage runs in its OWN warp, so a step costs one sweep of one row (C*9 flops per lane) instead
+//     of five:  warps 0..3 = sweeps 1..4,  warp 4 = residual increment (level 0),  warp 5 = stage 0 +
+//     cp.async loader,  warp 6 = x increment,  warp 7 = coalesced write-out (+ r.r).  Stages hand rows to
+//     each other through small shared-memory buffers indexed by step ([lane][C] blocks, read and written
+//     with vector accesses), with one __syncthreads per step;
+//   * static coefficients come from a host-built, pre-skewed table: entry tau holds, for lane L, the
+//     coefficients of row tau - L ([cy(C+1) | -inv(C) | cx(C) | diag(C)] as float4 vectors, lane-contiguous),
+//     so all lanes of a stage read the same ring slot; entries land in a 16-slot shared-memory ring by
+//     cp.async kPF steps ahead.  Entries are zero for every (row, column) that is not an interior cell, so
+//     such a stage evaluates to +-0 by itself; out-of-domain operands are ghosts of d whose products with
+//     the boundary coefficients are +-0 on every level (level 0: r_ghost = 0; coarse: boundary coefficients
+//     = 0, MG.pde:120);
+//   * r (and x) rows are staged in kRowRing-deep shared-memory rings with coalesced 16-byte cp.async row
+//     copies (plain rows); stage 0 picks this lane's columns of row t - L out of it and republishes them in a
+//     step-indexed ring for the sweeps; the increment stages write x+d and the new residual back into the
+//     plain rings, and once all lanes are past a row it is written out as a coalesced row.
+// Arithmetic per update keeps the reference order:
+//     d = -(dW*lxW + dE*lxE + dS*lyS + dN*lyN - r) * inv      (the minus sign is folded into ninv = -inv,
+//                                                               which is exact: (-a)*b == a*(-b) bitwise)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "solver.h"
+
+namespace rlfc {
+
+constexpr int kRowsWarps = 8;
+constexpr int kRowsThreads = 32 * kRowsWarps;
+constexpr int kPF = 5;             // cp.async groups (steps) in flight
+constexpr int kCoefSlots = 16;     // coefficient-entry ring: entries t-10 .. t+kPF live at step t
+constexpr int kRSlots = 16;        // step-indexed ring of this lane's r values (stage 0 -> sweeps, increment)
+constexpr int kRowRing = 48;       // plain r / x row rings: rows t+kPF .. t-32-10 live at step t
+constexpr int kStageLag = 10;      // rows between stage 0 and the residual increment stage
+constexpr int kTabFront = 10;      // table entry index = tau + kTabFront (entries tau <= 0 are zero)
+constexpr int kSLanes = 33;        // stage buffers carry a zero 33rd lane (right-hand domain edge)
+
+__host__ __device__ constexpr int rows_K(int C) { return (4 * C + 1 + 3) / 4; }   // float4 vectors per lane-entry
+__host__ __device__ constexpr int rows_CP(int C) { return (C + 1) & ~1; }          // lane block of the stage buffers (even)
+__host__ __device__ inline int rows_table_entries(int ni, int nl) { return kTabFront + ni + nl + kStageLag + kPF + 6; }
+
+// dynamic shared memory of one rows_smooth call (bytes): [coef ring | r ring | x ring | R ring | stage buffers]
+__host__ __device__ inline size_t rows_smem_bytes(int C, int P) {
+  return (size_t)kCoefSlots * rows_K(C) * 32 * 16 + 2 * (size_t)kRowRing * P * 4 +
+         (size_t)(kRSlots * 32 + 5 * 2 * kSLanes) * rows_CP(C) * 4 + 16;
+}
+
+namespace rows_detail {
+
+__device__ __forceinline__ void cp16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// floats [A, B) of a lane-entry (float4 vectors, lane-contiguous: vector k of lane l sits at ent[k*32 + l])
+template <int A, int B>
+__device__ __forceinline__ void ld_entry(const float4* ent, float (&out)[B - A]) {
+  constexpr int k0 = A / 4, k1 = (B + 3) / 4;
+#pragma unroll
+  for (int k = k0; k < k1; k++) {
+    const float4 v = ent[k * 32];
+    const float tmp[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int f = 4 * k + q;
+      if (f >= A && f < B) out[f - A] = tmp[q];
+    }
+  }
+}
+
+// a lane block of C floats (padded to CP = even) as float2 vector accesses
+template <int C>
+__device__ __forceinline__ void ld_block(const float* p, float (&out)[C]) {
+#pragma unroll
+  for (int k = 0; k < C / 2; k++) {
+    const float2 v = reinterpret_cast<const float2*>(p)[k];
+    out[2 * k] = v.x; out[2 * k + 1] = v.y;
+  }
+  if (C & 1) out[C - 1] = p[C - 1];
+}
+template <int C>
+__device__ __forceinline__ void st_block(float* p, const float (&in)[C]) {
+#pragma unroll
+  for (int k = 0; k < C / 2; k++) reinterpret_cast<float2*>(p)[k] = make_float2(in[2 * k], in[2 * k + 1]);
+  if (C & 1) p[C - 1] = in[C - 1];
+}
+
+__device__ __forceinline__ int ring_inc(int s) { return (s + 1 == kRowRing) ? 0 : s + 1; }
+__host__ __device__ constexpr int ring_mod(int row) { return ((row % kRowRing) + kRowRing) % kRowRing; }
+
+}  // namespace rows_detail
+
+// XMODE selects what the increment stages do with a finished row of d:
+//   1: x = 0 + d                      (coarsest level: x starts at 0, MG.pde:56,95)
+//   2: x = x + d                      (x.plusEq(d), MG.pde:95)
+//   3: level-0 smooth(4) complete (MG.pde:90-97): d.setBC (clamped neighbours), x += d, r -= A d written to
+//      r_out, r.r accumulated, and the boundary values of d kept in gbuf (top row, bottom row, left column,
+//      right column: 2*mj + 2*ni floats) for the ghost cells of x
+// Called by ALL kRowsThreads threads of the CTA.  r, x (and r_out) are this environment's row-major pitched
+// arrays of the level.  Returns this thread's share of r.r (XMODE 3; non-zero only in the write-out warp).
+template <int C, int XMODE>
+__device__ __forceinline__ double rows_smooth(const DevLevel& L, const float* __restrict__ r, float* __restrict__ x,
+                                              float* __restrict__ r_out, unsigned char* smem_raw, float* gbuf) {
+  using namespace rows_detail;
+  constexpr int K = rows_K(C), CP = rows_CP(C);
+  // float offsets inside a lane-entry
+  constexpr int F_CY = 0, F_NINV = C + 1, F_CX = 2 * C + 1, F_DIAG = 3 * C + 1;
+  constexpr int ES = K * 32;                       // float4s per entry
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ni = L.n - 2, mj = L.m - 2, P = L.P;
+  const int nl = (mj + C - 1) / C;                 // lanes that own at least one column
+  const int lag = nl + kStageLag;                  // row w is complete after step w + nl - 1 + kStageLag
+  const int t_end = (ni + lag + 1) & ~1;           // last step (even count; the last write-out is at step ni + lag)
+  float4* coef = reinterpret_cast<float4*>(smem_raw);
+  float* rring = reinterpret_cast<float*>(smem_raw + (size_t)kCoefSlots * ES * 16);
+  float* xring = rring + (size_t)kRowRing * P;
+  float* R = xring + (size_t)kRowRing * P;         // [kRSlots][32][CP]
+  float* S = R + (size_t)kRSlots * 32 * CP;        // [stage 0..4][parity][kSLanes][CP]
+  const float4* __restrict__ tab = L.rt.T;
+  const int j0 = C * lane + 1;                     // first column of this lane
+
+  // zero the coefficient ring (entries tau <= 0), the R ring and the stage buffers (incl. the 33rd lane)
+  for (int k = threadIdx.x; k < kCoefSlots * ES; k += kRowsThreads) coef[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = threadIdx.x; k < (kRSlots * 32 + 5 * 2 * kSLanes) * CP; k += kRowsThreads) R[k] = 0.f;
+  __syncthreads();
+
+  // loader (warp 5): row q of r (and x) and table entry q
+  const int nch = P / 4;
+  auto issue = [&](int q) {
+    if (q >= 1 && q <= ni) {
+      const int slot = ring_mod(q);
+      for (int ch = lane; ch < nch; ch += 32) {
+        cp16(rring + (size_t)slot * P + 4 * ch, r + (size_t)q * P + 4 * ch);
+        if (XMODE != 1) cp16(xring + (size_t)slot * P + 4 * ch, x + (size_t)q * P + 4 * ch);
+      }
+    }
+    const float4* src = tab + ((size_t)(q + kTabFront) * ES) + lane;
+    float4* dst = coef + ((size_t)(q & (kCoefSlots - 1)) * ES) + lane;
+#pragma unroll
+    for (int k = 0; k < K; k++) cp16(dst + k * 32, src + k * 32);
+  };
+  if (warp == 5) {
+    for (int q = 1; q <= kPF; q++) { issue(q); cp_commit(); }
+    cp_wait<kPF - 1>();
+  }
+  __syncthreads();
+
+  double rr = 0.0;
+  if (warp < 4) {
+    // ------------------------------------------------------------------ sweep g = warp + 1, row t - L - 2g
+    const int g = warp + 1;
+    float prev[C], Ep[C], cxW[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) { prev[c] = 0.f; Ep[c] = 0.f; cxW[c] = 0.f; }
+    const float* Sin = S + ((size_t)(g - 1) * 2 * kSLanes + lane) * CP;
+    float* Sout = S + ((size_t)g * 2 * kSLanes + lane) * CP;
+    const float* Rl = R + (size_t)lane * CP;
+    const float4* cl = coef + lane;
+    int e0 = (1 - 2 * g) & (kCoefSlots - 1);       // slot of entry t - 2g at t = 1 (same index for the R ring)
+    auto step = [&](auto par_c) {
+      constexpr int par = decltype(par_c)::value;
+      const int e1 = (e0 + 1) & (kCoefSlots - 1);
+      float cxE[C], cyn[2 * C + 1], E[C], rv[C];   // cyn = [cy(C+1) | ninv(C)]
+      float Sl = __shfl_up_sync(0xffffffffu, prev[C - 1], 1);
+      ld_entry<F_CY, F_CX>(cl + e0 * ES, cyn);
+      ld_entry<F_CX, F_DIAG>(cl + e1 * ES, cxE);
+      const float* Sp = Sin + (par ^ 1) * kSLanes * CP;
+      ld_block<C>(Sp, E);
+      const float Nx = Sp[CP];                      // column 0 of lane L+1 (lane 32 = zero pad)
+      ld_block<C>(Rl + e0 * 32 * CP, rv);
+      Sl = (lane == 0) ? 0.f : Sl;
+      float res[C];
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        const float Sop = (c == 0) ? Sl : res[c == 0 ? 0 : c - 1];
+        const float Nop = (c == C - 1) ? Nx : Ep[c == C - 1 ? c : c + 1];
+        res[c] = (prev[c] * cxW[c] + E[c] * cxE[c] + Sop * cyn[c] + Nop * cyn[c + 1] - rv[c]) * cyn[C + 1 + c];
+      }
+      st_block<C>(Sout + par * kSLanes * CP, res);
+#pragma unroll
+      for (int c = 0; c < C; c++) { prev[c] = res[c]; Ep[c] = E[c]; cxW[c] = cxE[c]; }
+      e0 = e1;
+      __syncthreads();
+    };
+    for (int t = 1; t <= t_end; t += 2) {
+      step(std::integral_constant<int, 1>{});
+      step(std::integral_constant<int, 0>{});
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ residual increment, row i5 = t - L - 10
+    if (XMODE == 3) {
+      float dC[C], dW[C], dEp[C], cxW[C];
+#pragma unroll
+      for (int c = 0; c < C; c++) { dC[c] = 0.f; dW[c] = 0.f; dEp[c] = 0.f; cxW[c] = 0.f; }
+      int i5 = 1 - lane - kStageLag;
+      int slot = ring_mod(i5);
+      const float* Sin = S + ((size_t)4 * 2 * kSLanes + lane) * CP;
+      const float* Rl = R + (size_t)lane * CP;
+      const float4* cl = coef + lane;
+      int e0 = (1 - kStageLag) & (kCoefSlots - 1);
+      // which of this lane's columns are the first / last column of the level
+      const int cfirst = (lane == 0) ? 0 : -1;
+      const int clast = (lane == nl - 1) ? (mj - 1) - C * lane : -1;
+      auto step = [&](auto par_c) {
+        constexpr int par = decltype(par_c)::value;
+        const int e1 = (e0 + 1) & (kCoefSlots - 1);
+        const float* Sp = Sin + (par ^ 1) * kSLanes * CP;
+        float dE[C], cxE[C], cy[C + 1], dg[C], rv[C];
+        ld_block<C>(Sp, dE);
+        const float Nx = Sp[CP];
+#pragma unroll
+        for (int c = 0; c < C; c++) { dW[c] = dC[c]; dC[c] = dEp[c]; dEp[c] = dE[c]; }
+        float Sl = __shfl_up_sync(0xffffffffu, dW[C - 1], 1);
+        ld_entry<F_CY, F_NINV>(cl + e0 * ES, cy);
+        ld_entry<F_DIAG, 4 * C + 1>(cl + e0 * ES, dg);
+        ld_entry<F_CX, F_DIAG>(cl + e1 * ES, cxE);
+        ld_block<C>(Rl + e0 * 32 * CP, rv);
+        const bool rowok = (unsigned)(i5 - 1) < (unsigned)ni;
+        const bool top = i5 == 1, bot = i5 == ni;
+        float* rrow = rring + (size_t)slot * P + j0;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          const float d0 = dC[c];
+          const float w_ = top ? d0 : dW[c];
+          const float e_ = bot ? d0 : dE[c];
+          const float s_ = (c == cfirst) ? d0 : ((c == 0) ? Sl : dC[c == 0 ? 0 : c - 1]);
+          const float n_ = (c == clast) ? d0 : ((c == C - 1) ? Nx : dC[c == C - 1 ? c : c + 1]);
+          const float Ad = d0 * dg[c] + w_ * cxW[c] + e_ * cxE[c] + s_ * cy[c] + n_ * cy[c + 1];   // PoissonMatrix.pde:56-61
+          if (rowok && C * lane + c < mj) rrow[c] = rv[c] - Ad;
+          cxW[c] = cxE[c];
+        }
+        e0 = e1;
+        i5++;
+        slot = ring_inc(slot);
+        __syncthreads();
+      };
+      for (int t = 1; t <= t_end; t += 2) {
+        step(std::integral_constant<int, 1>{});
+        step(std::integral_constant<int, 0>{});
+      }
+    } else {
+      for (int t = 1; t <= t_end; t++) __syncthreads();
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ stage 0 (row t - L) + loader
+    int i0 = 1 - lane;
+    int slot0 = ring_mod(i0);
+    float* Sout = S + (size_t)lane * CP;
+    float* Rl = R + (size_t)lane * CP;
+    const float4* cl = coef + lane;
+    for (int t = 1; t <= t_end; t++) {
+      const int par = t & 1, e0 = t & (kCoefSlots - 1);
+      float ninv[C], rv[C], d0[C];
+      ld_entry<F_NINV, F_CX>(cl + e0 * ES, ninv);
+      const bool rowok = (unsigned)(i0 - 1) < (unsigned)ni;
+      const float* rrow = rring + (size_t)slot0 * P + j0;
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        rv[c] = (rowok && C * lane + c < mj) ? rrow[c] : 0.f;
+        d0[c] = rv[c] * (-ninv[c]);                 // MG.pde:80
+      }
+      st_block<C>(Sout + par * kSLanes * CP, d0);
+      st_block<C>(Rl + e0 * 32 * CP, rv);
+      issue(t + kPF);
+      cp_commit();
+      cp_wait<kPF - 1>();
+      i0++;
+      slot0 = ring_inc(slot0);
+      __syncthreads();
+    }
+    cp_wait<0>();
+  } else if (warp == 6) {
+    // ------------------------------------------------------------------ x increment: row t - L - 9 (sweep 4's last row)
+    int i6 = 1 - lane - 9;
+    int slot = ring_mod(i6);
+    const float* Sin = S + ((size_t)4 * 2 * kSLanes + lane) * CP;
+    float* gtop = gbuf;
+    float* gbot = gbuf + mj;
+    float* gleft = gbuf + 2 * mj;
+    float* gright = gbuf + 2 * mj + ni;
+    for (int t = 1; t <= t_end; t++) {
+      const int par = t & 1;
+      float d[C];
+      ld_block<C>(Sin + (par ^ 1) * kSLanes * CP, d);
+      const bool rowok = (unsigned)(i6 - 1) < (unsigned)ni;
+      float* xrow = xring + (size_t)slot * P + j0;
+      if (rowok) {
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          const int j = j0 + c;
+          if (j <= mj) {
+            xrow[c] = (XMODE == 1) ? 0.f + d[c] : xrow[c] + d[c];
+            if (XMODE == 3) {
+              // boundary values of d feed the ghost cells of x after the sweep (x.plusEq(d) runs over all cells)
+              if (i6 == 1) gtop[j - 1] = d[c];
+              if (i6 == ni) gbot[j - 1] = d[c];
+              if (j == 1) gleft[i6 - 1] = d[c];
+              if (j == mj) gright[i6 - 1] = d[c];
+            }
+          }
+        }
+      }
+      i6++;
+      slot = ring_inc(slot);
+      __syncthreads();
+    }
+  } else {
+    // ------------------------------------------------------------------ write-out of row t - lag (+ r.r)
+    for (int t = 1; t <= t_end; t++) {
+      const int w = t - lag;                        // every lane's increment stage passed row w at step t - 1
+      if (w >= 1 && w <= ni) {
+        const int ws = ring_mod(w);
+        const float* xs = xring + (size_t)ws * P;
+        const float* rs = rring + (size_t)ws * P;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          const int j = 1 + lane + 32 * c;
+          if (j <= mj) {
+            x[(size_t)w * P + j] = xs[j];
+            if (XMODE == 3) {
+              const float rN = rs[j];
+              r_out[(size_t)w * P + j] = rN;
+              const float prod = rN * rN;            // float product, double accumulation (Field.pde:304-307)
+              rr += (double)prod;
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  return rr;
+}
+
+}  // namespace rlfc

@@ -24,10 +24,21 @@ struct SkewLevel {
   int nstrips, Tsk;
 };
 
+// Pre-skewed static coefficient table of one level for the row-pipelined smoother (smooth_rows.cuh):
+// entry tau (stored at index tau + kTabFront) holds, for lane l, the coefficients of row tau - l of the
+// lane's C columns j0 = C*l+1 .. C*l+C as the float stream [ly[row][j0+c] (C+1) | -inv[row][j0+c] (C) |
+// lx[row][j0+c] (C) | diag[row][j0+c] (C)], packed into K = ceil((4C+1)/4) float4 vectors that are
+// lane-contiguous: vector k of lane l of entry e sits at T[(e*K + k)*32 + l].
+struct RowTab {
+  const float4* T;
+  int C, K, entries;
+};
+
 #define IDX(i, j) ((i) * P + (j))
 
 struct DevLevel {
   SkewLevel sk;
+  RowTab rt;
   int n, m, P;              // dims incl. ghosts, pitch
   size_t stride;            // per-env stride (floats) of r/x/d at this level
   const float *lx, *ly, *inv, *diag;   // static, pitched
@@ -69,6 +80,7 @@ struct SolverParams {
   float mg_tol;
   int   nlevels;
   int   coarse_strips;      // max strip count over levels >= 1 (warps of k_mg_coarse)
+  int   use_rows;           // 1 = row-pipelined smoother (smooth_rows.cuh), 0 = strip smoother (smooth_strip.cuh)
   int   resolution, substeps, mg_max_iters;
   float init_time, episode_time;
   DevLevel lev[kMaxLevels];

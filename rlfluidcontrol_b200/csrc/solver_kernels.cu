@@ -21,6 +21,7 @@
 //   k_force       pressForce + probes + time + draw() accumulation       Body.pde:296-303, SaveScalar.pde:61-72, clientCFD.pde:39-47
 #include "solver.h"
 #include "smooth_strip.cuh"
+#include "smooth_rows.cuh"
 
 namespace rlfc {
 namespace {
@@ -493,6 +494,87 @@ k_smooth0(const __grid_constant__ SolverParams q, const float* r_in_all, float* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Row-pipelined variants (smooth_rows.cuh): one warp per sweep, C columns per lane.
+// ------------------------------------------------------------------------------------------------
+template <int XMODE>
+__device__ __forceinline__ void rows_dispatch(const DevLevel& L, const float* r, float* x, unsigned char* smem) {
+  switch (L.rt.C) {
+    case 1: rows_smooth<1, XMODE>(L, r, x, nullptr, smem, nullptr); break;
+    case 2: rows_smooth<2, XMODE>(L, r, x, nullptr, smem, nullptr); break;
+    case 3: rows_smooth<3, XMODE>(L, r, x, nullptr, smem, nullptr); break;
+    default: rows_smooth<4, XMODE>(L, r, x, nullptr, smem, nullptr); break;
+  }
+}
+
+__global__ void __launch_bounds__(kRowsThreads, 2)
+k_mg_coarse_rows(const __grid_constant__ SolverParams q) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int e = blockIdx.x;
+  if (!q.sc.active[e]) return;
+  const int last = q.nlevels - 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int l = 1; l < last; l++) {
+    const DevLevel& L = q.lev[l];
+    const DevLevel& C = q.lev[l + 1];
+    const int nci = C.n - 2, ncj = C.m - 2;
+    const size_t eo = (size_t)e * L.stride;
+    for (int J = 1 + lane; J <= ncj; J += 32)
+#pragma unroll 2
+      for (int I = 1 + warp; I <= nci; I += nw)
+        down_block<false>(L, C, L.r + eo, L.d + eo, L.x + eo, C.r + (size_t)e * C.stride, I, J);
+    __syncthreads();
+  }
+  {
+    const DevLevel& L = q.lev[last];
+    rows_dispatch<1>(L, L.r + (size_t)e * L.stride, L.x + (size_t)e * L.stride, smem_raw);
+  }
+  for (int l = last - 1; l >= 1; l--) {
+    const DevLevel& L = q.lev[l];
+    const DevLevel& C = q.lev[l + 1];
+    const size_t eo = (size_t)e * L.stride;
+    float* r = L.d + eo;
+    float* x = L.x + eo;
+    coarse_up_pass(L, C, r, x, C.x + (size_t)e * C.stride);
+    __syncthreads();
+    rows_dispatch<2>(L, r, x, smem_raw);
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kRowsThreads)
+k_smooth0_rows(const __grid_constant__ SolverParams q, const float* r_in_all, float* r_out_all, int which) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const DevLevel& L = q.lev[0];
+  const int n = L.n, m = L.m, P = L.P, ni = n - 2, mj = m - 2;
+  float* gbuf = reinterpret_cast<float*>(smem_raw + rows_smem_bytes(C, P));
+  __shared__ double wsum[32];
+  const int e = blockIdx.x;
+  if (!q.sc.active[e]) return;
+  float* p = L.x + (size_t)e * L.stride;
+  double rr = rows_smooth<C, 3>(L, r_in_all + (size_t)e * L.stride, p, r_out_all + (size_t)e * L.stride, smem_raw, gbuf);
+  // ghost cells of x: x.plusEq(d) runs over all cells and d.setBC copied the adjacent interior value (MG.pde:90,95)
+  const float *gtop = gbuf, *gbot = gbuf + mj, *gleft = gbuf + 2 * mj, *gright = gbuf + 2 * mj + ni;
+  for (int c = threadIdx.x; c < mj; c += blockDim.x) { p[IDX(0, c + 1)] += gtop[c]; p[IDX(n - 1, c + 1)] += gbot[c]; }
+  for (int c = threadIdx.x; c < ni; c += blockDim.x) { p[IDX(c + 1, 0)] += gleft[c]; p[IDX(c + 1, m - 1)] += gright[c]; }
+  if (threadIdx.x == 0) {
+    p[IDX(0, 0)] += gtop[0]; p[IDX(0, m - 1)] += gtop[mj - 1];
+    p[IDX(n - 1, 0)] += gbot[0]; p[IDX(n - 1, m - 1)] += gbot[mj - 1];
+  }
+  // r.r: fixed-order reduction (lanes by shuffle tree, then warps in order)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rr += __shfl_down_sync(0xffffffffu, rr, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = rr;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += wsum[w];
+    const int it = ++q.sc.iters[2 * e + which];
+    if ((float)s < q.mg_tol || it >= q.mg_max_iters) q.sc.active[e] = 0;
+    else atomicExch(q.sc.any_active, 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Field.sum (Field.pde:311-318): a serial float accumulation over the interior in i-major order.
 // One warp per env: lanes load 32 consecutive values (coalesced), every lane then replays the same
 // 32 dependent adds on broadcast values, so the chain is pure FADD latency.
@@ -725,13 +807,43 @@ static size_t smooth0_smem(const SolverParams& q) {
 }
 
 // opt-in shared-memory sizes; called once per handle, outside any stream capture
+static size_t coarse_rows_smem(const SolverParams& q) {
+  size_t s = 0;
+  for (int l = 1; l < q.nlevels; l++) s = max(s, rows_smem_bytes(min(q.lev[l].rt.C, 4), q.lev[l].P));
+  return s;
+}
+static size_t smooth0_rows_smem(const SolverParams& q) {
+  return rows_smem_bytes(q.lev[0].rt.C, q.P) + sizeof(float) * (2 * (q.n - 2) + 2 * (q.m - 2));
+}
+
+template <int C>
+static cudaError_t set_smooth0_rows_attr(const SolverParams& q) {
+  return cudaFuncSetAttribute(k_smooth0_rows<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smooth0_rows_smem(q));
+}
+
 int configure_kernels(const SolverParams& q) {
   cudaError_t e1 = cudaFuncSetAttribute(k_mg_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)strip_smem(q.coarse_strips));
   cudaError_t e2 = cudaFuncSetAttribute(k_smooth0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smooth0_smem(q));
-  return (e1 == cudaSuccess && e2 == cudaSuccess) ? 0 : -1;
+  cudaError_t e3 = cudaFuncSetAttribute(k_mg_coarse_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coarse_rows_smem(q));
+  cudaError_t e4 = cudaSuccess;
+  switch (q.lev[0].rt.C) {
+    case 1: e4 = set_smooth0_rows_attr<1>(q); break;
+    case 2: e4 = set_smooth0_rows_attr<2>(q); break;
+    case 3: e4 = set_smooth0_rows_attr<3>(q); break;
+    case 4: e4 = set_smooth0_rows_attr<4>(q); break;
+    case 5: e4 = set_smooth0_rows_attr<5>(q); break;
+    case 6: e4 = set_smooth0_rows_attr<6>(q); break;
+    case 7: e4 = set_smooth0_rows_attr<7>(q); break;
+    default: e4 = set_smooth0_rows_attr<8>(q); break;
+  }
+  return (e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess && e4 == cudaSuccess) ? 0 : -1;
 }
 
 int launch_mg_coarse(const SolverParams& q, cudaStream_t st) {
+  if (q.use_rows) {
+    k_mg_coarse_rows<<<q.B, kRowsThreads, coarse_rows_smem(q), st>>>(q);
+    return 1;
+  }
   const size_t smem = strip_smem(q.coarse_strips);
   k_mg_coarse<<<q.B, max(256, 32 * q.coarse_strips), smem, st>>>(q);
   return 1;
@@ -744,6 +856,20 @@ int launch_mg_up0(const SolverParams& q, float* r, cudaStream_t st) {
 }
 
 int launch_smooth0(const SolverParams& q, const float* r_in, float* r_out, int which, cudaStream_t st) {
+  if (q.use_rows) {
+    const size_t sm = smooth0_rows_smem(q);
+    switch (q.lev[0].rt.C) {
+      case 1: k_smooth0_rows<1><<<q.B, kRowsThreads, sm, st>>>(q, r_in, r_out, which); break;
+      case 2: k_smooth0_rows<2><<<q.B, kRowsThreads, sm, st>>>(q, r_in, r_out, which); break;
+      case 3: k_smooth0_rows<3><<<q.B, kRowsThreads, sm, st>>>(q, r_in, r_out, which); break;
+      case 4: k_smooth0_rows<4><<<q.B, kRowsThreads, sm, st>>>(q, r_in, r_out, which); break;
+      case 5: k_smooth0_rows<5><<<q.B, kRowsThreads, sm, st>>>(q, r_in, r_out, which); break;
+      case 6: k_smooth0_rows<6><<<q.B, kRowsThreads, sm, st>>>(q, r_in, r_out, which); break;
+      case 7: k_smooth0_rows<7><<<q.B, kRowsThreads, sm, st>>>(q, r_in, r_out, which); break;
+      default: k_smooth0_rows<8><<<q.B, kRowsThreads, sm, st>>>(q, r_in, r_out, which); break;
+    }
+    return 1;
+  }
   const int ns = q.lev[0].sk.nstrips;
   const size_t smem = smooth0_smem(q);
   k_smooth0<<<q.B, 32 * ns, smem, st>>>(q, r_in, r_out, which);

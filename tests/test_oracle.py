@@ -43,7 +43,8 @@ def test_mg_docstring(oracle):
     it, rr, tol = A.solve(x, b, 20.0)
     assert 1 <= it < 20 and rr < tol
     assert abs(tol - 128 * 128 * 1e-8) / tol < 1e-4          # tol = sum over the interior of (1e-4)^2
-    r = b.a - A.times(x).a
+    Ax = A.times(x)                                          # keep the owner alive while .a is read
+    r = b.a - Ax.a
     assert np.abs(r).max() < 1e-3
 
 
