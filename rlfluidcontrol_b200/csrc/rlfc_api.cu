@@ -481,6 +481,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   sp.inv_cells = (float)((g.n - 2) * (g.m - 2));
   sp.mg_tol = g.mg_tol;
   sp.use_rows = 1;
+  if (const char* ev = std::getenv("RLFC_DBG")) sp.dbg = std::atoi(ev);
   if (const char* ev = std::getenv("RLFC_SMOOTHER")) sp.use_rows = std::string(ev) != "strip";
   sp.nlevels = (int)g.levels.size();
   sp.resolution = cfg->resolution; sp.substeps = cfg->substeps; sp.mg_max_iters = cfg->mg_max_iters;
@@ -556,8 +557,15 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
           for (int k = 0; k < K; k++)
             T[((size_t)e * K + k) * 32 + ln] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
         }
-      L.rt.C = C; L.rt.K = K; L.rt.entries = entries;
-      TRY(upload_vec(E, T, &L.rt.T));
+      // the table is shared by every environment and all CTAs walk it in near lockstep, so each 128-byte line is
+      // requested by ~148 SMs at once from the ONE L2 slice that owns it; kTabCopies copies at different addresses
+      // spread that burst over several slices (CTA e reads copy e % kTabCopies)
+      const int copies = 8;
+      std::vector<float4> Trep;
+      Trep.reserve(T.size() * copies);
+      for (int c = 0; c < copies; c++) Trep.insert(Trep.end(), T.begin(), T.end());
+      L.rt.C = C; L.rt.K = K; L.rt.entries = entries; L.rt.copies = copies;
+      TRY(upload_vec(E, Trep, &L.rt.T));
     }
     TRY(E->dmalloc(&L.r, L.stride * B));
     TRY(E->dmalloc(&L.x, L.stride * B));

@@ -13,7 +13,8 @@
 //     d.setBC, x += d and, on level 0, r -= A d;
 //   * every stage runs in its OWN warp, so a step costs one sweep of one row (C*9 flops per lane) instead
 //     of five:  warps 0..3 = sweeps 1..4,  warp 4 = residual increment (level 0),  warp 5 = stage 0 +
-//     cp.async loader,  warp 6 = x increment,  warp 7 = coalesced write-out (+ r.r).  Stages hand rows to
+//     bulk-copy loader,  warp 6 = x increment + coalesced write-out (+ r.r),  warp 7 = the serial Field.sum of
+//     the new x (level 0).  Stages hand rows to
 //     each other through small shared-memory buffers indexed by step ([lane][C] blocks, read and written
 //     with vector accesses), with one __syncthreads per step;
 //   * static coefficients come from a host-built, pre-skewed table: entry tau holds, for lane L, the
@@ -33,14 +34,21 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdint>
+#include <cstdio>
+#include <type_traits>
+
+#ifndef RLFC_NO_SOLVER_H
 #include "solver.h"
+#endif
 
 namespace rlfc {
 
 constexpr int kRowsWarps = 8;
 constexpr int kRowsThreads = 32 * kRowsWarps;
 constexpr int kPF = 5;             // cp.async groups (steps) in flight
-constexpr int kCoefSlots = 16;     // coefficient-entry ring: entries t-10 .. t+kPF live at step t
+constexpr int kCoefShift = 4;
+constexpr int kCoefSlots = 1 << kCoefShift;     // coefficient-entry ring: entries t-10 .. t+kPF live at step t
 constexpr int kRSlots = 16;        // step-indexed ring of this lane's r values (stage 0 -> sweeps, increment)
 constexpr int kRowRing = 48;       // plain r / x row rings: rows t+kPF .. t-32-10 live at step t
 constexpr int kStageLag = 10;      // rows between stage 0 and the residual increment stage
@@ -54,7 +62,7 @@ __host__ __device__ inline int rows_table_entries(int ni, int nl) { return kTabF
 // dynamic shared memory of one rows_smooth call (bytes): [coef ring | r ring | x ring | R ring | stage buffers]
 __host__ __device__ inline size_t rows_smem_bytes(int C, int P) {
   return (size_t)kCoefSlots * rows_K(C) * 32 * 16 + 2 * (size_t)kRowRing * P * 4 +
-         (size_t)(kRSlots * 32 + 5 * 2 * kSLanes) * rows_CP(C) * 4 + 16;
+         (size_t)(kRSlots * 32 + 5 * 2 * kSLanes) * rows_CP(C) * 4 + 16 + kCoefSlots * 8;
 }
 
 namespace rows_detail {
@@ -65,6 +73,47 @@ __device__ __forceinline__ void cp16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// ---- bulk async copies (cp.async.bulk, SASS UBLKCP) completing on a shared-memory mbarrier ----
+__device__ __forceinline__ unsigned sm_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sm_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(unsigned long long* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(sm_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sm_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(ok) : "r"(sm_addr(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+#ifdef RLFC_DEBUG_MBAR
+  long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > (1ll << 28)) {
+      printf("mbar timeout: block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, sm_addr(bar), parity);
+      __trap();
+    }
+  }
+#else
+  while (!mbar_try(bar, parity)) {}
+#endif
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sm_addr(smem)),
+               "l"(gmem), "r"(bytes), "r"(sm_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // floats [A, B) of a lane-entry (float4 vectors, lane-contiguous: vector k of lane l sits at ent[k*32 + l])
 template <int A, int B>
@@ -114,7 +163,8 @@ __host__ __device__ constexpr int ring_mod(int row) { return ((row % kRowRing) +
 // arrays of the level.  Returns this thread's share of r.r (XMODE 3; non-zero only in the write-out warp).
 template <int C, int XMODE>
 __device__ __forceinline__ double rows_smooth(const DevLevel& L, const float* __restrict__ r, float* __restrict__ x,
-                                              float* __restrict__ r_out, unsigned char* smem_raw, float* gbuf) {
+                                              float* __restrict__ r_out, unsigned char* smem_raw, float* gbuf, float* psum_out = nullptr,
+                                              const int dbg = 0) {
   using namespace rows_detail;
   constexpr int K = rows_K(C), CP = rows_CP(C);
   // float offsets inside a lane-entry
@@ -130,7 +180,7 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, const float* __
   float* xring = rring + (size_t)kRowRing * P;
   float* R = xring + (size_t)kRowRing * P;         // [kRSlots][32][CP]
   float* S = R + (size_t)kRSlots * 32 * CP;        // [stage 0..4][parity][kSLanes][CP]
-  const float4* __restrict__ tab = L.rt.T;
+  const float4* __restrict__ tab = L.rt.T + (size_t)(blockIdx.x % (unsigned)L.rt.copies) * ((size_t)L.rt.entries * ES);
   const int j0 = C * lane + 1;                     // first column of this lane
 
   // zero the coefficient ring (entries tau <= 0), the R ring and the stage buffers (incl. the 33rd lane)
@@ -138,27 +188,42 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, const float* __
   for (int k = threadIdx.x; k < (kRSlots * 32 + 5 * 2 * kSLanes) * CP; k += kRowsThreads) R[k] = 0.f;
   __syncthreads();
 
-  // loader (warp 5): row q of r (and x) and table entry q
-  const int nch = P / 4;
+  // loader (one lane of warp 5): row q of r (and x) and table entry q as bulk copies completing on bars[(q-1) & 15]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(
+      (reinterpret_cast<uintptr_t>(S + (size_t)5 * 2 * kSLanes * CP) + 15) & ~(uintptr_t)15);
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < kCoefSlots; k++) mbar_init(bars + k, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const unsigned row_bytes = (unsigned)P * 4u, ent_bytes = (unsigned)ES * 16u;
   auto issue = [&](int q) {
-    if (q >= 1 && q <= ni) {
+    unsigned long long* bar = bars + ((q - 1) & (kCoefSlots - 1));    // q >= 1: use k = (q-1)/16 of this barrier
+    const bool row = q >= 1 && q <= ni;
+    mbar_expect_tx(bar, ent_bytes + (row ? (XMODE != 1 ? 2u : 1u) * row_bytes : 0u));
+    if (row) {
       const int slot = ring_mod(q);
-      for (int ch = lane; ch < nch; ch += 32) {
-        cp16(rring + (size_t)slot * P + 4 * ch, r + (size_t)q * P + 4 * ch);
-        if (XMODE != 1) cp16(xring + (size_t)slot * P + 4 * ch, x + (size_t)q * P + 4 * ch);
-      }
+      bulk_g2s(rring + (size_t)slot * P, r + (size_t)q * P, row_bytes, bar);
+      if (XMODE != 1) bulk_g2s(xring + (size_t)slot * P, x + (size_t)q * P, row_bytes, bar);
     }
-    const float4* src = tab + ((size_t)(q + kTabFront) * ES) + lane;
-    float4* dst = coef + ((size_t)(q & (kCoefSlots - 1)) * ES) + lane;
-#pragma unroll
-    for (int k = 0; k < K; k++) cp16(dst + k * 32, src + k * 32);
+    bulk_g2s(coef + (size_t)(q & (kCoefSlots - 1)) * ES, tab + (size_t)(q + kTabFront) * ES, ent_bytes, bar);
   };
   if (warp == 5) {
-    for (int q = 1; q <= kPF; q++) { issue(q); cp_commit(); }
-    cp_wait<kPF - 1>();
+    if (lane == 0) {
+      fence_proxy_async();
+      for (int q = 1; q <= kPF; q++) issue(q);
+    }
+    mbar_wait(bars + 0, 0);
   }
   __syncthreads();
 
+#ifdef RLFC_ROLE_TIMING
+  long long wait_cycles = 0;
+  const long long role_t0 = clock64();
+#define RLFC_STEP_SYNC() do { long long a_ = clock64(); __syncthreads(); wait_cycles += clock64() - a_; } while (0)
+#else
+#define RLFC_STEP_SYNC() __syncthreads()
+#endif
   double rr = 0.0;
   if (warp < 4) {
     // ------------------------------------------------------------------ sweep g = warp + 1, row t - L - 2g
@@ -171,30 +236,38 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, const float* __
     const float* Rl = R + (size_t)lane * CP;
     const float4* cl = coef + lane;
     int e0 = (1 - 2 * g) & (kCoefSlots - 1);       // slot of entry t - 2g at t = 1 (same index for the R ring)
-    auto step = [&](auto par_c) {
-      constexpr int par = decltype(par_c)::value;
+    // operands that do not depend on the previous step are fetched BEFORE the step's barrier (entries <= t and the
+    // R slots <= t - 1 are complete by then), so only the previous stage's row is loaded on the critical path
+    float cxE[C], cyn[2 * C + 1], rv[C];           // cyn = [cy(C+1) | ninv(C)]
+    auto fetch = [&]() {
       const int e1 = (e0 + 1) & (kCoefSlots - 1);
-      float cxE[C], cyn[2 * C + 1], E[C], rv[C];   // cyn = [cy(C+1) | ninv(C)]
-      float Sl = __shfl_up_sync(0xffffffffu, prev[C - 1], 1);
       ld_entry<F_CY, F_CX>(cl + e0 * ES, cyn);
       ld_entry<F_CX, F_DIAG>(cl + e1 * ES, cxE);
+      ld_block<C>(Rl + e0 * 32 * CP, rv);
+    };
+    fetch();
+    auto step = [&](auto par_c) {
+      constexpr int par = decltype(par_c)::value;
+      if (dbg & 64) { RLFC_STEP_SYNC(); return; }
+      float E[C];
+      float Sl = __shfl_up_sync(0xffffffffu, prev[C - 1], 1);
       const float* Sp = Sin + (par ^ 1) * kSLanes * CP;
       ld_block<C>(Sp, E);
       const float Nx = Sp[CP];                      // column 0 of lane L+1 (lane 32 = zero pad)
-      ld_block<C>(Rl + e0 * 32 * CP, rv);
       Sl = (lane == 0) ? 0.f : Sl;
       float res[C];
 #pragma unroll
       for (int c = 0; c < C; c++) {
-        const float Sop = (c == 0) ? Sl : res[c == 0 ? 0 : c - 1];
+        const float Sop = (c == 0 || (dbg & 32)) ? Sl : res[c == 0 ? 0 : c - 1];
         const float Nop = (c == C - 1) ? Nx : Ep[c == C - 1 ? c : c + 1];
         res[c] = (prev[c] * cxW[c] + E[c] * cxE[c] + Sop * cyn[c] + Nop * cyn[c + 1] - rv[c]) * cyn[C + 1 + c];
       }
-      st_block<C>(Sout + par * kSLanes * CP, res);
+      if (!(dbg & 256)) st_block<C>(Sout + par * kSLanes * CP, res);
 #pragma unroll
       for (int c = 0; c < C; c++) { prev[c] = res[c]; Ep[c] = E[c]; cxW[c] = cxE[c]; }
-      e0 = e1;
-      __syncthreads();
+      e0 = (e0 + 1) & (kCoefSlots - 1);
+      if (!(dbg & 512)) fetch();
+      RLFC_STEP_SYNC();
     };
     for (int t = 1; t <= t_end; t += 2) {
       step(std::integral_constant<int, 1>{});
@@ -217,6 +290,7 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, const float* __
       const int clast = (lane == nl - 1) ? (mj - 1) - C * lane : -1;
       auto step = [&](auto par_c) {
         constexpr int par = decltype(par_c)::value;
+        if (dbg & 1) { RLFC_STEP_SYNC(); return; }
         const int e1 = (e0 + 1) & (kCoefSlots - 1);
         const float* Sp = Sin + (par ^ 1) * kSLanes * CP;
         float dE[C], cxE[C], cy[C + 1], dg[C], rv[C];
@@ -246,14 +320,14 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, const float* __
         e0 = e1;
         i5++;
         slot = ring_inc(slot);
-        __syncthreads();
+        RLFC_STEP_SYNC();
       };
       for (int t = 1; t <= t_end; t += 2) {
         step(std::integral_constant<int, 1>{});
         step(std::integral_constant<int, 0>{});
       }
     } else {
-      for (int t = 1; t <= t_end; t++) __syncthreads();
+      for (int t = 1; t <= t_end; t++) RLFC_STEP_SYNC();
     }
   } else if (warp == 5) {
     // ------------------------------------------------------------------ stage 0 (row t - L) + loader
@@ -264,7 +338,9 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, const float* __
     const float4* cl = coef + lane;
     for (int t = 1; t <= t_end; t++) {
       const int par = t & 1, e0 = t & (kCoefSlots - 1);
+      if (dbg & 16) { RLFC_STEP_SYNC(); continue; }
       float ninv[C], rv[C], d0[C];
+      if (!(dbg & 8)) {
       ld_entry<F_NINV, F_CX>(cl + e0 * ES, ninv);
       const bool rowok = (unsigned)(i0 - 1) < (unsigned)ni;
       const float* rrow = rring + (size_t)slot0 * P + j0;
@@ -275,14 +351,18 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, const float* __
       }
       st_block<C>(Sout + par * kSLanes * CP, d0);
       st_block<C>(Rl + e0 * 32 * CP, rv);
-      issue(t + kPF);
-      cp_commit();
-      cp_wait<kPF - 1>();
+      }
+      if (lane == 0) {
+        if (!(dbg & 128)) fence_proxy_async();
+        issue(t + kPF);
+      }
+      mbar_wait(bars + (t & (kCoefSlots - 1)), ((unsigned)t >> kCoefShift) & 1u);   // entry / row t + 1 has landed
       i0++;
       slot0 = ring_inc(slot0);
-      __syncthreads();
+      RLFC_STEP_SYNC();
     }
-    cp_wait<0>();
+    // drain: every issued copy must have landed before the shared memory is reused
+    if (!(dbg & 16)) for (int q = t_end + 2; q <= t_end + kPF; q++) mbar_wait(bars + ((q - 1) & (kCoefSlots - 1)), ((unsigned)(q - 1) >> kCoefShift) & 1u);
   } else if (warp == 6) {
     // ------------------------------------------------------------------ x increment: row t - L - 9 (sweep 4's last row)
     int i6 = 1 - lane - 9;
@@ -294,55 +374,110 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, const float* __
     float* gright = gbuf + 2 * mj + ni;
     for (int t = 1; t <= t_end; t++) {
       const int par = t & 1;
-      float d[C];
+      if (dbg & 2) { RLFC_STEP_SYNC(); continue; }
+      float d[C], xv[C];
       ld_block<C>(Sin + (par ^ 1) * kSLanes * CP, d);
       const bool rowok = (unsigned)(i6 - 1) < (unsigned)ni;
       float* xrow = xring + (size_t)slot * P + j0;
-      if (rowok) {
+      if (XMODE != 1) {
+#pragma unroll
+        for (int c = 0; c < C; c++) xv[c] = (rowok && C * lane + c < mj) ? xrow[c] : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        const float xn = (XMODE == 1) ? 0.f + d[c] : xv[c] + d[c];
+        if (rowok && C * lane + c < mj) xrow[c] = xn;
+      }
+      if (XMODE == 3 && rowok && (i6 == 1 || i6 == ni || lane == 0 || lane == nl - 1)) {
+        // boundary values of d feed the ghost cells of x after the sweep (x.plusEq(d) runs over all cells)
 #pragma unroll
         for (int c = 0; c < C; c++) {
           const int j = j0 + c;
           if (j <= mj) {
-            xrow[c] = (XMODE == 1) ? 0.f + d[c] : xrow[c] + d[c];
+            if (i6 == 1) gtop[j - 1] = d[c];
+            if (i6 == ni) gbot[j - 1] = d[c];
+            if (j == 1) gleft[i6 - 1] = d[c];
+            if (j == mj) gright[i6 - 1] = d[c];
+          }
+        }
+      }
+      {  // write-out of row t - lag: every lane's increment stages passed it at step t - 1 (+ r.r)
+        const int w = t - lag;
+        if (w >= 1 && w <= ni) {
+          const int ws = ring_mod(w);
+          const float* xs = xring + (size_t)ws * P;
+          const float* rs = rring + (size_t)ws * P;
+          float xo[C], rN[C];
+#pragma unroll
+          for (int c = 0; c < C; c++) {
+            const int j = 1 + lane + 32 * c;
+            xo[c] = (j <= mj) ? xs[j] : 0.f;
+            if (XMODE == 3) rN[c] = (j <= mj) ? rs[j] : 0.f;
+          }
+          float* xg = x + (size_t)w * P + 1 + lane;
+          float* rg = r_out + (size_t)w * P + 1 + lane;
+#pragma unroll
+          for (int c = 0; c < C; c++) {
+            if (1 + lane + 32 * c <= mj) {
+              xg[32 * c] = xo[c];
+              if (XMODE == 3) rg[32 * c] = rN[c];
+            }
             if (XMODE == 3) {
-              // boundary values of d feed the ghost cells of x after the sweep (x.plusEq(d) runs over all cells)
-              if (i6 == 1) gtop[j - 1] = d[c];
-              if (i6 == ni) gbot[j - 1] = d[c];
-              if (j == 1) gleft[i6 - 1] = d[c];
-              if (j == mj) gright[i6 - 1] = d[c];
+              const float prod = rN[c] * rN[c];          // float product, double accumulation (Field.pde:304-307)
+              rr += (double)prod;
             }
           }
         }
       }
       i6++;
       slot = ring_inc(slot);
-      __syncthreads();
+      RLFC_STEP_SYNC();
     }
   } else {
-    // ------------------------------------------------------------------ write-out of row t - lag (+ r.r)
+    // ------------------------------------------------------------------ Field.sum of the new x (level 0 only)
+    // Field.pde:311-318: a serial float accumulation over the interior in i-major order.  Row w is complete in the
+    // ring after step w + lag - 1; one lane-uniform chain of mj dependent adds per step keeps pace with the pipeline,
+    // so the sum is finished together with the smoother instead of costing a kernel of its own.
+    float s = 0.f;
     for (int t = 1; t <= t_end; t++) {
-      const int w = t - lag;                        // every lane's increment stage passed row w at step t - 1
-      if (w >= 1 && w <= ni) {
-        const int ws = ring_mod(w);
-        const float* xs = xring + (size_t)ws * P;
-        const float* rs = rring + (size_t)ws * P;
+      const int w = t - lag;
+      if (XMODE == 3 && w >= 1 && w <= ni && !(dbg & 4)) {
+        const float4* xs4 = reinterpret_cast<const float4*>(xring + (size_t)ring_mod(w) * P);   // columns 0..3, 4..7, ...
+        // the chain runs over columns 1 .. mj (column 0 is the ghost); the row is fetched kSumB vectors at a time, one
+        // batch ahead of the adds, so the chain never waits for shared memory
+        constexpr int kSumB = 8;
+        const int nv = (mj + 4) / 4;                 // vectors that hold columns 0 .. mj
+        float4 cur[kSumB], nxt[kSumB];
 #pragma unroll
-        for (int c = 0; c < C; c++) {
-          const int j = 1 + lane + 32 * c;
-          if (j <= mj) {
-            x[(size_t)w * P + j] = xs[j];
-            if (XMODE == 3) {
-              const float rN = rs[j];
-              r_out[(size_t)w * P + j] = rN;
-              const float prod = rN * rN;            // float product, double accumulation (Field.pde:304-307)
-              rr += (double)prod;
-            }
+        for (int u = 0; u < kSumB; u++) cur[u] = (u < nv) ? xs4[u] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int b = 0; b < nv; b += kSumB) {
+#pragma unroll
+          for (int u = 0; u < kSumB; u++) nxt[u] = (b + kSumB + u < nv) ? xs4[b + kSumB + u] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < kSumB; u++) {
+            const int j = 4 * (b + u);               // column of cur[u].x
+            if (j >= 1 && j <= mj) s += cur[u].x;
+            if (j + 1 <= mj) s += cur[u].y;
+            if (j + 2 <= mj) s += cur[u].z;
+            if (j + 3 <= mj) s += cur[u].w;
           }
+#pragma unroll
+          for (int u = 0; u < kSumB; u++) cur[u] = nxt[u];
         }
       }
-      __syncthreads();
+      RLFC_STEP_SYNC();
     }
+    if (XMODE == 3 && lane == 0 && psum_out) *psum_out = s;
   }
+#ifdef RLFC_ROLE_TIMING
+  if (blockIdx.x == 0 && lane == 0 && XMODE == 3)
+    printf("role warp %d: total %lld cycles, barrier wait %lld (%.1f%%), steps %d\n", warp, clock64() - role_t0, wait_cycles,
+           100.0 * wait_cycles / (double)(clock64() - role_t0), t_end);
+#endif
+#undef RLFC_STEP_SYNC
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int k = 0; k < kCoefSlots; k++) mbar_inval(bars + k);
   __syncthreads();
   return rr;
 }

@@ -31,7 +31,7 @@ struct SkewLevel {
 // lane-contiguous: vector k of lane l of entry e sits at T[(e*K + k)*32 + l].
 struct RowTab {
   const float4* T;
-  int C, K, entries;
+  int C, K, entries, copies;   // `copies` identical tables back to back (L2-slice load spreading)
 };
 
 #define IDX(i, j) ((i) * P + (j))
@@ -80,6 +80,7 @@ struct SolverParams {
   float mg_tol;
   int   nlevels;
   int   coarse_strips;      // max strip count over levels >= 1 (warps of k_mg_coarse)
+  int   dbg;                // experiment switches (RLFC_DBG), 0 in production
   int   use_rows;           // 1 = row-pipelined smoother (smooth_rows.cuh), 0 = strip smoother (smooth_strip.cuh)
   int   resolution, substeps, mg_max_iters;
   float init_time, episode_time;

@@ -551,7 +551,7 @@ k_smooth0_rows(const __grid_constant__ SolverParams q, const float* r_in_all, fl
   const int e = blockIdx.x;
   if (!q.sc.active[e]) return;
   float* p = L.x + (size_t)e * L.stride;
-  double rr = rows_smooth<C, 3>(L, r_in_all + (size_t)e * L.stride, p, r_out_all + (size_t)e * L.stride, smem_raw, gbuf);
+  double rr = rows_smooth<C, 3>(L, r_in_all + (size_t)e * L.stride, p, r_out_all + (size_t)e * L.stride, smem_raw, gbuf, q.sc.psum + e, q.dbg);
   // ghost cells of x: x.plusEq(d) runs over all cells and d.setBC copied the adjacent interior value (MG.pde:90,95)
   const float *gtop = gbuf, *gbot = gbuf + mj, *gleft = gbuf + 2 * mj, *gright = gbuf + 2 * mj + ni;
   for (int c = threadIdx.x; c < mj; c += blockDim.x) { p[IDX(0, c + 1)] += gtop[c]; p[IDX(n - 1, c + 1)] += gbot[c]; }
@@ -877,6 +877,7 @@ int launch_smooth0(const SolverParams& q, const float* r_in, float* r_out, int w
 }
 
 int launch_psum(const SolverParams& q, cudaStream_t st) {
+  if (q.use_rows) return 0;   // the row-pipelined level-0 smoother produces Field.sum itself (smooth_rows.cuh, warp 7)
   k_psum<<<q.B, 32, 0, st>>>(q);
   return 1;
 }
