@@ -48,6 +48,7 @@ struct rlfc_env {
   float *uAx = nullptr, *uAy = nullptr, *uBx = nullptr, *uBy = nullptr, *uCx = nullptr, *uCy = nullptr;
   // initial state in pitched device layout (one env) for fast batched reset
   float *init_ux = nullptr, *init_uy = nullptr, *init_p = nullptr;
+  float* pB = nullptr;                       // second pressure buffer (solver.h: k_resid_down0 / k_project_shift)
   float init_t = 0, init_dt = 0;
   // staging
   float *d_actions = nullptr, *d_obs = nullptr, *d_reward = nullptr;
@@ -60,7 +61,8 @@ struct rlfc_env {
   // CUDA graphs), so the latency-bound per-env kernels of one group overlap the bandwidth-bound kernels of another.
   struct Group {
     int e0 = 0, B = 0, index = 0;
-    SolverParams sp{};                       // view of the batch arrays restricted to [e0, e0 + B)
+    SolverParams sp{};                       // view of the batch arrays restricted to [e0, e0 + B); lev[0].x = pressure buffer A
+    SolverParams spB{};                      // same view with lev[0].x = pressure buffer B (p ping-pongs A -> B -> A per half step)
     float *uAx = nullptr, *uAy = nullptr, *uBx = nullptr, *uBy = nullptr, *uCx = nullptr, *uCy = nullptr;
     cudaStream_t st = nullptr;               // group 0 runs on the handle's stream
     cudaEvent_t done = nullptr;
@@ -73,6 +75,7 @@ struct rlfc_env {
   cudaEvent_t fork_ev = nullptr;
   bool use_graph = true;
   bool eager_groups = false;
+  bool fused = true;                         // RLFC_FUSED=0: unfused residual/down0 and project/shift kernels (A/B experiments)
   int fixed_iters = 0;                       // experiment: > 0 = that many unconditional MG iterations per solve, no WHILE node
   // optional per-kernel CUDA-event timing (rlfc_env_set_profiling)
   bool profiling = false;
@@ -198,26 +201,36 @@ using Group = rlfc_env::Group;
 // (MG.pde:34) costs one 4-byte readback per iteration
 int project_eager(rlfc_env* E, Group& G, float* Ux, float* Uy, int which) {
   SolverParams& sp = G.sp;
+  SolverParams& sb = E->fused ? G.spB : G.sp;
   cudaStream_t st = G.st;
   const int gi = G.index;
   float* r = sp.lev[0].r;
   float* rs = sp.lev[0].d;
-  E->run("k_residual", 4, [&] { return launch_residual(sp, Ux, Uy, r, which, st); }, st, gi);
+  float* pA = sp.lev[0].x;
+  float* pB = sb.lev[0].x;
+  if (!E->fused) E->run("k_residual", 4, [&] { return launch_residual(sp, Ux, Uy, r, which, st); }, st, gi);
   for (int it = 0; it < (E->fixed_iters > 0 ? E->fixed_iters : sp.mg_max_iters); it++) {
     CU(cudaMemsetAsync(sp.sc.any_active, 0, sizeof(int), st));
-    E->run("k_mg_down0", 4.25, [&] { return launch_mg_down0(sp, r, rs, st); }, st, gi);
-    E->run("k_mg_coarse", 0.5, [&] { return launch_mg_coarse(sp, st); }, st, gi);
-    E->run("k_mg_up0", 4.25, [&] { return launch_mg_up0(sp, rs, st); }, st, gi);
-    E->run("k_smooth0", 4, [&] { return launch_smooth0(sp, rs, r, which, st); }, st, gi);
+    if (it == 0 && E->fused)
+      E->run("k_resid_down0", 5.25, [&] { return launch_resid_down0(sp, Ux, Uy, pA, pB, rs, which, st); }, st, gi);
+    else
+      E->run("k_mg_down0", 4.25, [&] { return launch_mg_down0(sb, r, rs, st); }, st, gi);
+    E->run("k_mg_coarse", 0.5, [&] { return launch_mg_coarse(sb, st); }, st, gi);
+    E->run("k_mg_up0", 4.25, [&] { return launch_mg_up0(sb, rs, st); }, st, gi);
+    E->run("k_smooth0", 4, [&] { return launch_smooth0(sb, rs, r, which, st); }, st, gi);
     E->mg_iter_launch_rounds++;
     if (E->fixed_iters > 0) continue;
     CU(cudaMemcpyAsync(E->h_any, sp.sc.any_active, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (!*E->h_any) break;
   }
-  E->run("k_psum", 1, [&] { return launch_psum(sp, st); }, st, gi);
-  E->run("k_project_u", 5, [&] { return launch_project_u(sp, Ux, Uy, st); }, st, gi);
-  E->run("k_shift_p", 2, [&] { return launch_shift_p(sp, st); }, st, gi);
+  if (!sp.fuse_psum) E->run("k_psum", 1, [&] { return launch_psum(sb, st); }, st, gi);
+  if (E->fused) {
+    E->run("k_project_shift", 6, [&] { return launch_project_shift(sp, pB, pA, Ux, Uy, st); }, st, gi);
+  } else {
+    E->run("k_project_u", 5, [&] { return launch_project_u(sp, Ux, Uy, st); }, st, gi);
+    E->run("k_shift_p", 2, [&] { return launch_shift_p(sp, st); }, st, gi);
+  }
   E->run("k_bc", 0, [&] { return launch_bc(sp, Ux, Uy, st); }, st, gi);
   return RLFC_OK;
 }
@@ -247,52 +260,57 @@ int solver_step_eager(rlfc_env* E, Group& G, int accumulate) {
 int capture_half_step(rlfc_env* E, Group& G, cudaStream_t st, const float* sx, const float* sy, const float* u0x,
                       const float* u0y, float* dx, float* dy, int which, long long* n_outer, long long* n_body) {
   SolverParams& sp = G.sp;
+  SolverParams& sb = G.spB;
   float* r = sp.lev[0].r;
   float* rs = sp.lev[0].d;
+  float* pA = sp.lev[0].x;
+  float* pB = sb.lev[0].x;
   *n_outer += launch_advdif(sp, sx, sy, u0x, u0y, dx, dy, st);
   *n_outer += launch_band_bc(sp, dx, dy, st);
-  *n_outer += launch_residual(sp, dx, dy, r, which, st);
-  if (E->fixed_iters > 0) {
-    for (int it = 0; it < E->fixed_iters; it++) {
-      *n_body += launch_mg_down0(sp, r, rs, st);
-      *n_body += launch_mg_coarse(sp, st);
-      *n_body += launch_mg_up0(sp, rs, st);
-      *n_body += launch_smooth0(sp, rs, r, which, st);
+  // first MG iteration (MG.pde:32-35 is a do-while in effect: iter < itmx holds on entry)
+  *n_outer += launch_resid_down0(sp, dx, dy, pA, pB, rs, which, st);
+  *n_outer += launch_mg_coarse(sb, st);
+  *n_outer += launch_mg_up0(sb, rs, st);
+  *n_outer += launch_smooth0(sb, rs, r, which, st);
+  if (E->fixed_iters <= 0) {
+    // ---- WHILE node: further iterations while any environment is still unconverged (rare) ----
+    cudaStreamCaptureStatus status;
+    cudaGraph_t graph;
+    const cudaGraphNode_t* deps;
+    size_t ndeps;
+    CU(cudaStreamGetCaptureInfo(st, &status, nullptr, &graph, &deps, &ndeps));
+    cudaGraphConditionalHandle handle;
+    CU(cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault));
+    // the condition is written by a kernel ahead of the node and again at the end of every body pass
+    *n_outer += launch_loopcond(sb, (unsigned long long)handle, st);
+    CU(cudaStreamGetCaptureInfo(st, &status, nullptr, &graph, &deps, &ndeps));
+    cudaGraphNodeParams np{};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = handle;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t cond;
+    CU(cudaGraphAddNode(&cond, graph, deps, ndeps, &np));
+    cudaGraph_t body = np.conditional.phGraph_out[0];
+    CU(cudaStreamBeginCaptureToGraph(E->aux_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    launch_mg_down0(sb, r, rs, E->aux_stream);
+    launch_mg_coarse(sb, E->aux_stream);
+    launch_mg_up0(sb, rs, E->aux_stream);
+    launch_smooth0(sb, rs, r, which, E->aux_stream);
+    launch_loopcond(sb, (unsigned long long)handle, E->aux_stream);
+    CU(cudaStreamEndCapture(E->aux_stream, nullptr));
+    CU(cudaStreamUpdateCaptureDependencies(st, &cond, 1, cudaStreamSetCaptureDependencies));
+  } else {
+    for (int it = 1; it < E->fixed_iters; it++) {
+      *n_body += launch_mg_down0(sb, r, rs, st);
+      *n_body += launch_mg_coarse(sb, st);
+      *n_body += launch_mg_up0(sb, rs, st);
+      *n_body += launch_smooth0(sb, rs, r, which, st);
     }
-    *n_outer += launch_psum(sp, st);
-    *n_outer += launch_project_u(sp, dx, dy, st);
-    *n_outer += launch_shift_p(sp, st);
-    *n_outer += launch_bc(sp, dx, dy, st);
-    return RLFC_OK;
   }
-  // ---- WHILE node ----
-  cudaStreamCaptureStatus status;
-  cudaGraph_t graph;
-  const cudaGraphNode_t* deps;
-  size_t ndeps;
-  CU(cudaStreamGetCaptureInfo(st, &status, nullptr, &graph, &deps, &ndeps));
-  cudaGraphConditionalHandle handle;
-  CU(cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault));   // do-while: first pass always
-  cudaGraphNodeParams np{};
-  np.type = cudaGraphNodeTypeConditional;
-  np.conditional.handle = handle;
-  np.conditional.type = cudaGraphCondTypeWhile;
-  np.conditional.size = 1;
-  cudaGraphNode_t cond;
-  CU(cudaGraphAddNode(&cond, graph, deps, ndeps, &np));
-  cudaGraph_t body = np.conditional.phGraph_out[0];
-  CU(cudaStreamBeginCaptureToGraph(E->aux_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-  *n_body += launch_mg_down0(sp, r, rs, E->aux_stream);
-  *n_body += launch_mg_coarse(sp, E->aux_stream);
-  *n_body += launch_mg_up0(sp, rs, E->aux_stream);
-  *n_body += launch_smooth0(sp, rs, r, which, E->aux_stream);
-  *n_body += launch_loopcond(sp, (unsigned long long)handle, E->aux_stream);
-  CU(cudaStreamEndCapture(E->aux_stream, nullptr));
-  CU(cudaStreamUpdateCaptureDependencies(st, &cond, 1, cudaStreamSetCaptureDependencies));
   // ---- projection tail ----
-  *n_outer += launch_psum(sp, st);
-  *n_outer += launch_project_u(sp, dx, dy, st);
-  *n_outer += launch_shift_p(sp, st);
+  if (!sp.fuse_psum) *n_outer += launch_psum(sb, st);
+  *n_outer += launch_project_shift(sp, pB, pA, dx, dy, st);
   *n_outer += launch_bc(sp, dx, dy, st);
   return RLFC_OK;
 }
@@ -481,8 +499,11 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   sp.inv_cells = (float)((g.n - 2) * (g.m - 2));
   sp.mg_tol = g.mg_tol;
   sp.use_rows = 1;
+  sp.fuse_psum = 0;
+  if (const char* ev = std::getenv("RLFC_FUSE_PSUM")) sp.fuse_psum = std::atoi(ev) != 0;
   if (const char* ev = std::getenv("RLFC_DBG")) sp.dbg = std::atoi(ev);
   if (const char* ev = std::getenv("RLFC_SMOOTHER")) sp.use_rows = std::string(ev) != "strip";
+  if (!sp.use_rows) sp.fuse_psum = 0;
   sp.nlevels = (int)g.levels.size();
   sp.resolution = cfg->resolution; sp.substeps = cfg->substeps; sp.mg_max_iters = cfg->mg_max_iters;
   sp.init_time = cfg->init_time; sp.episode_time = cfg->episode_time;
@@ -609,12 +630,13 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   sp.rr_blocks = 0;
   int n_groups = cfg->n_groups;
   if (const char* ev = std::getenv("RLFC_GROUPS")) n_groups = std::atoi(ev);
-  if (n_groups <= 0) n_groups = B >= 64 ? 2 : 1;
+  if (n_groups <= 0) n_groups = B >= 128 ? 4 : (B >= 32 ? 2 : 1);
   n_groups = std::min(n_groups, B);
   if (const char* ev = std::getenv("RLFC_NO_GRAPH")) E->use_graph = std::atoi(ev) == 0;
   if (const char* ev = std::getenv("RLFC_FIXED_ITERS")) E->fixed_iters = std::atoi(ev);
   if (const char* ev = std::getenv("RLFC_EAGER_GROUPS")) E->eager_groups = std::atoi(ev) != 0;
   if (const char* ev = std::getenv("RLFC_TRACE")) E->trace_path = ev;
+  if (const char* ev = std::getenv("RLFC_FUSED")) E->fused = std::atoi(ev) != 0;
   TRY(E->dmalloc(&sp.sc.xi, 2 * B)); TRY(E->dmalloc(&sp.sc.t, B)); TRY(E->dmalloc(&sp.sc.force, 2 * B));
   TRY(E->dmalloc(&sp.sc.probes, (size_t)B * RLFC_NUM_PROBES));
   TRY(E->dmalloc(&sp.sc.callLearn, B)); TRY(E->dmalloc(&sp.sc.Cd, B)); TRY(E->dmalloc(&sp.sc.Cl, B));
@@ -624,6 +646,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   TRY(E->dmalloc(&sp.sc.any_active, n_groups));
   TRY(E->dmalloc(&E->d_actions, 2 * B)); TRY(E->dmalloc(&E->d_obs, 2 * B)); TRY(E->dmalloc(&E->d_reward, B));
   TRY(E->dmalloc(&E->d_done, B));
+  TRY(E->dmalloc(&E->pB, S));
 #undef TRY
   auto hostalloc = [&](void** p, size_t bytes) { return cudaMallocHost(p, bytes) == cudaSuccess; };
   if (!hostalloc((void**)&E->h_actions, 2 * B * sizeof(float)) || !hostalloc((void**)&E->h_obs, 2 * B * sizeof(float)) ||
@@ -652,11 +675,14 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     v.sc.psum += e0; v.sc.any_active += g;
     const size_t o = (size_t)e0 * sp.stride;
     G.uAx = E->uAx + o; G.uAy = E->uAy + o; G.uBx = E->uBx + o; G.uBy = E->uBy + o; G.uCx = E->uCx + o; G.uCy = E->uCy + o;
+    G.spB = G.sp;
+    G.spB.lev[0].x = E->pB + (size_t)e0 * sp.stride;
     if (g == 0) G.st = E->stream;
     else if (cudaStreamCreateWithFlags(&G.st, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(RLFC_ECUDA, "cudaStreamCreate failed"));
     if (cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming) != cudaSuccess) return bail(fail(RLFC_ECUDA, "cudaEventCreate failed"));
   }
   E->whole.e0 = 0; E->whole.B = B; E->whole.sp = sp; E->whole.st = E->stream;
+  E->whole.spB = sp; E->whole.spB.lev[0].x = E->pB;
   E->whole.uAx = E->uAx; E->whole.uAy = E->uAy; E->whole.uBx = E->uBx; E->whole.uBy = E->uBy;
   E->whole.uCx = E->uCx; E->whole.uCy = E->uCy;
   if (cudaStreamCreateWithFlags(&E->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||

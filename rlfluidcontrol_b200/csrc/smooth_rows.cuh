@@ -441,7 +441,7 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, const float* __
     float s = 0.f;
     for (int t = 1; t <= t_end; t++) {
       const int w = t - lag;
-      if (XMODE == 3 && w >= 1 && w <= ni && !(dbg & 4)) {
+      if (XMODE == 3 && psum_out && w >= 1 && w <= ni && !(dbg & 4)) {
         const float4* xs4 = reinterpret_cast<const float4*>(xring + (size_t)ring_mod(w) * P);   // columns 0..3, 4..7, ...
         // the chain runs over columns 1 .. mj (column 0 is the ghost); the row is fetched kSumB vectors at a time, one
         // batch ahead of the adds, so the chain never waits for shared memory

@@ -81,6 +81,7 @@ struct SolverParams {
   int   nlevels;
   int   coarse_strips;      // max strip count over levels >= 1 (warps of k_mg_coarse)
   int   dbg;                // experiment switches (RLFC_DBG), 0 in production
+  int   fuse_psum;          // 1 = the level-0 smoother also produces Field.sum(p) (no k_psum launch)
   int   use_rows;           // 1 = row-pipelined smoother (smooth_rows.cuh), 0 = strip smoother (smooth_strip.cuh)
   int   resolution, substeps, mg_max_iters;
   float init_time, episode_time;
@@ -105,6 +106,11 @@ int launch_advdif(const SolverParams& P, const float* srcx, const float* srcy, c
                   float* dstx, float* dsty, cudaStream_t st);
 int launch_band_bc(const SolverParams& P, float* ux, float* uy, cudaStream_t st);
 int launch_residual(const SolverParams& P, const float* ux, const float* uy, float* r, int which, cudaStream_t st);
+// first MG iteration fused: residual + level-0 smooth(0)/increment/restriction; p_in -> p_out (different buffers)
+int launch_resid_down0(const SolverParams& P, const float* ux, const float* uy, const float* p_in, float* p_out, float* r_out,
+                       int which, cudaStream_t st);
+// projection tail fused: p_out = p_in + shift (different buffers), u -= c * grad(p_in + shift)
+int launch_project_shift(const SolverParams& P, const float* p_in, float* p_out, float* ux, float* uy, cudaStream_t st);
 // one MG iteration (V-cycle + smooth(4)) on active envs = down0, coarse, up0, smooth0;
 // r_in/r_out are the level-0 ping-pong residual buffers
 int launch_mg_down0(const SolverParams& P, const float* r_in, float* r_out, cudaStream_t st);

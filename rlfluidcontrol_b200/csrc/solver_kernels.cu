@@ -344,6 +344,75 @@ k_mg_down0(const __grid_constant__ SolverParams q, const float* __restrict__ rin
 }
 
 // ------------------------------------------------------------------------------------------------
+// First MG iteration of a solve, level 0, fused:  r = div(u) - A p  (VectorField.pde:56-65,
+// PoissonMatrix.pde:53-68), then smooth(0) + increment + residual restriction (MG.pde:68-70,79-97,124-137).
+// A CTA owns kRdI x kRdJ coarse cells (= 2*kRdI x 2*kRdJ fine cells); phase 1 forms the residual on that tile
+// plus a one-cell halo (clamped to the interior, exactly the operands d.setBC would provide) in shared memory,
+// phase 2 is down_block on shared-memory operands.  p is read with a distance-2 halo while it is being
+// updated, so the new p goes to the OTHER pressure buffer (p ping-pongs A -> B here and B -> A in
+// k_project_shift); the unsmoothed residual never reaches HBM.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRdI = 8, kRdJ = 32;                       // coarse cells per CTA (one per thread)
+constexpr int kRdTI = 2 * kRdI + 2, kRdTJ = 2 * kRdJ + 2;
+
+__global__ void __launch_bounds__(kRdI * kRdJ)
+k_resid_down0(const __grid_constant__ SolverParams q, const float* __restrict__ ux_all, const float* __restrict__ uy_all,
+              const float* __restrict__ pin_all, float* __restrict__ pout_all, float* __restrict__ rout_all, int which) {
+  __shared__ float s_r[kRdTI][kRdTJ + 1];
+  __shared__ float s_d[kRdTI][kRdTJ + 1];
+  const DevLevel& L = q.lev[0];
+  const DevLevel& C = q.lev[1];
+  const int P = L.P, n = L.n, m = L.m;
+  const int e = blockIdx.z;
+  const int tid = threadIdx.y * kRdJ + threadIdx.x;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) { q.sc.active[e] = 1; q.sc.iters[2 * e + which] = 0; }
+  const size_t eo = (size_t)e * L.stride;
+  const float* __restrict__ ux = ux_all + eo;
+  const float* __restrict__ uy = uy_all + eo;
+  const float* __restrict__ pin = pin_all + eo;
+  const int I0 = blockIdx.y * kRdI + 1, J0 = blockIdx.x * kRdJ + 1;     // first coarse cell of the tile
+  const int i0 = (I0 - 1) * 2 + 1, j0 = (J0 - 1) * 2 + 1;              // first fine cell
+  // ---- phase 1: r and d = r*inv on the tile + halo, at clamped coordinates ----
+  for (int t = tid; t < kRdTI * kRdTJ; t += kRdI * kRdJ) {
+    const int a = t / kRdTJ, b = t - a * kRdTJ;
+    const int i = min(max(i0 - 1 + a, 1), n - 2), j = min(max(j0 - 1 + b, 1), m - 2);
+    const int k = IDX(i, j);
+    const float sdiv = ux[k + P] - ux[k] + uy[k + 1] - uy[k];
+    const float rv = sdiv - apply_A(pin, L.lx, L.ly, L.diag, P, k);
+    s_r[a][b] = rv;
+    s_d[a][b] = rv * L.inv[k];
+  }
+  __syncthreads();
+  // ---- phase 2: smooth(0) increment and restriction for this thread's coarse cell ----
+  const int I = I0 + threadIdx.y, J = J0 + threadIdx.x;
+  if (I > C.n - 2 || J > C.m - 2) return;
+  const int fi = (I - 1) * 2 + 1, fj = (J - 1) * 2 + 1;
+  const int ta = 2 * threadIdx.y + 1, tb = 2 * threadIdx.x + 1;          // tile coordinates of (fi, fj)
+  float* __restrict__ pout = pout_all + eo;
+  float* __restrict__ rout = rout_all + eo;
+  float rn[2][2];
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      const int i = fi + a, j = fj + b, k = IDX(i, j);
+      const float dc = s_d[ta + a][tb + b];
+      const float Ad = dc * L.diag[k] + s_d[ta + a - 1][tb + b] * L.lx[k] + s_d[ta + a + 1][tb + b] * L.lx[k + P] +
+                       s_d[ta + a][tb + b - 1] * L.ly[k] + s_d[ta + a][tb + b + 1] * L.ly[k + 1];
+      rn[a][b] = s_r[ta + a][tb + b] - Ad;
+      rout[k] = rn[a][b];
+      pout[k] = pin[k] + dc;
+      // ghosts of x receive the clamped d (x.plusEq(d) runs over all cells, MG.pde:95)
+      const int di = (i == 1) ? -1 : (i == n - 2 ? 1 : 0), dj = (j == 1) ? -1 : (j == m - 2 ? 1 : 0);
+      if (di) pout[IDX(i + di, j)] = pin[IDX(i + di, j)] + dc;
+      if (dj) pout[IDX(i, j + dj)] = pin[IDX(i, j + dj)] + dc;
+      if (di && dj) pout[IDX(i + di, j + dj)] = pin[IDX(i + di, j + dj)] + dc;
+    }
+  // MG.restrict(Field) MG.pde:128-133
+  C.r[(size_t)e * C.stride + I * C.P + J] = rn[0][0] + rn[0][1] + rn[1][0] + rn[1][1];
+}
+
+// ------------------------------------------------------------------------------------------------
 // levels >= 1: the rest of the V-cycle, one CTA per environment (MG.pde:68-77).  Per level the residual
 // ping-pongs between the level's `r` and `d` arrays: down writes the smoothed residual to `d`, the
 // up pass updates it in place and the strip smoother consumes it, adding its result straight into x.
@@ -551,7 +620,7 @@ k_smooth0_rows(const __grid_constant__ SolverParams q, const float* r_in_all, fl
   const int e = blockIdx.x;
   if (!q.sc.active[e]) return;
   float* p = L.x + (size_t)e * L.stride;
-  double rr = rows_smooth<C, 3>(L, r_in_all + (size_t)e * L.stride, p, r_out_all + (size_t)e * L.stride, smem_raw, gbuf, q.sc.psum + e, q.dbg);
+  double rr = rows_smooth<C, 3>(L, r_in_all + (size_t)e * L.stride, p, r_out_all + (size_t)e * L.stride, smem_raw, gbuf, q.fuse_psum ? q.sc.psum + e : nullptr, q.dbg);
   // ghost cells of x: x.plusEq(d) runs over all cells and d.setBC copied the adjacent interior value (MG.pde:90,95)
   const float *gtop = gbuf, *gbot = gbuf + mj, *gleft = gbuf + 2 * mj, *gright = gbuf + 2 * mj + ni;
   for (int c = threadIdx.x; c < mj; c += blockDim.x) { p[IDX(0, c + 1)] += gtop[c]; p[IDX(n - 1, c + 1)] += gbot[c]; }
@@ -661,6 +730,53 @@ k_shift_p(const __grid_constant__ SolverParams q) {
   float* p = q.lev[0].x + (size_t)e * q.stride;
   const float shift = -1 * q.sc.psum[e] / q.inv_cells;
   p[IDX(i, j)] += shift;
+}
+
+// projection tail fused (VectorField.pde:136-139): p_out = p_in + shift on all cells (p ping-pongs B -> A, so no
+// thread reads a value another thread has already shifted), u += c * (grad(p_in + shift) * -1) on the interior.
+// One thread handles four consecutive columns (aligned float4 accesses; the pitch is a multiple of 8 floats).
+__global__ void __launch_bounds__(256)
+k_project_shift(const __grid_constant__ SolverParams q, const float* __restrict__ pin_all, float* __restrict__ pout_all,
+                float* __restrict__ ux_all, float* __restrict__ uy_all) {
+  const int P = q.P, n = q.n, m = q.m, nv = P >> 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = blockIdx.y;
+  if (idx >= n * nv) return;
+  const int i = idx / nv, j4 = (idx - i * nv) << 2;
+  const size_t eo = (size_t)e * q.stride;
+  const float shift = -1 * q.sc.psum[e] / q.inv_cells;
+  const int k = IDX(i, j4);
+  const float4 pv = *reinterpret_cast<const float4*>(pin_all + eo + k);
+  const float pc[4] = {pv.x + shift, pv.y + shift, pv.z + shift, pv.w + shift};
+  *reinterpret_cast<float4*>(pout_all + eo + k) = make_float4(pc[0], pc[1], pc[2], pc[3]);
+  if (i < 1 || i > n - 2 || j4 > m - 2) return;
+  float4 uxv = *reinterpret_cast<const float4*>(ux_all + eo + k);
+  float4 uyv = *reinterpret_cast<const float4*>(uy_all + eo + k);
+  const float4 cxv = *reinterpret_cast<const float4*>(q.c_x + k);
+  const float4 cyv = *reinterpret_cast<const float4*>(q.c_y + k);
+  float uxa[4] = {uxv.x, uxv.y, uxv.z, uxv.w}, uya[4] = {uyv.x, uyv.y, uyv.z, uyv.w};
+  const float cxa[4] = {cxv.x, cxv.y, cxv.z, cxv.w}, cya[4] = {cyv.x, cyv.y, cyv.z, cyv.w};
+  float pw[4] = {0.f, 0.f, 0.f, 0.f};
+  if (i >= 2) {
+    const float4 w = *reinterpret_cast<const float4*>(pin_all + eo + k - P);
+    pw[0] = w.x + shift; pw[1] = w.y + shift; pw[2] = w.z + shift; pw[3] = w.w + shift;
+  }
+  const float psm = (j4 >= 1) ? pin_all[eo + k - 1] + shift : 0.f;       // column j4 - 1
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const int j = j4 + c;
+    if (j < 1 || j > m - 2) continue;
+    if (i >= 2) {
+      const float dpx = pc[c] - pw[c];
+      uxa[c] += cxa[c] * (dpx * -1);
+    }
+    if (j >= 2) {
+      const float dpy = pc[c] - (c == 0 ? psm : pc[c == 0 ? 0 : c - 1]);
+      uya[c] += cya[c] * (dpy * -1);
+    }
+  }
+  *reinterpret_cast<float4*>(ux_all + eo + k) = make_float4(uxa[0], uxa[1], uxa[2], uxa[3]);
+  *reinterpret_cast<float4*>(uy_all + eo + k) = make_float4(uya[0], uya[1], uya[2], uya[3]);
 }
 
 // BDIM.update2: u.plusEq(us); u.timesEq(0.5) over all cells (BDIM.pde:95-96)
@@ -788,6 +904,22 @@ int launch_residual(const SolverParams& q, const float* ux, const float* uy, flo
   return 1;
 }
 
+int launch_resid_down0(const SolverParams& q, const float* ux, const float* uy, const float* p_in, float* p_out, float* r_out,
+                       int which, cudaStream_t st) {
+  const DevLevel& L1 = q.lev[1];
+  dim3 blk(kRdJ, kRdI);
+  dim3 grid((L1.m - 2 + kRdJ - 1) / kRdJ, (L1.n - 2 + kRdI - 1) / kRdI, q.B);
+  k_resid_down0<<<grid, blk, 0, st>>>(q, ux, uy, p_in, p_out, r_out, which);
+  return 1;
+}
+
+int launch_project_shift(const SolverParams& q, const float* p_in, float* p_out, float* ux, float* uy, cudaStream_t st) {
+  const int items = q.n * (q.P >> 2);
+  dim3 grid((items + 255) / 256, q.B);
+  k_project_shift<<<grid, 256, 0, st>>>(q, p_in, p_out, ux, uy);
+  return 1;
+}
+
 int launch_loopcond(const SolverParams& q, unsigned long long handle, cudaStream_t st) {
   k_loopcond<<<1, 32, 0, st>>>((cudaGraphConditionalHandle)handle, q.sc.any_active);
   return 1;
@@ -877,7 +1009,7 @@ int launch_smooth0(const SolverParams& q, const float* r_in, float* r_out, int w
 }
 
 int launch_psum(const SolverParams& q, cudaStream_t st) {
-  if (q.use_rows) return 0;   // the row-pipelined level-0 smoother produces Field.sum itself (smooth_rows.cuh, warp 7)
+  if (q.fuse_psum) return 0;   // the row-pipelined level-0 smoother produces Field.sum itself (smooth_rows.cuh, warp 7)
   k_psum<<<q.B, 32, 0, st>>>(q);
   return 1;
 }
