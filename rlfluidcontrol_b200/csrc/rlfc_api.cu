@@ -14,6 +14,7 @@
 #include "../../include/rlfc.h"
 #include "geometry.h"
 #include "solver.h"
+#include "smooth_rows.cuh"
 
 using namespace rlfc;
 
@@ -213,8 +214,10 @@ int project_eager(rlfc_env* E, Group& G, float* Ux, float* Uy, int which) {
     CU(cudaMemsetAsync(sp.sc.any_active, 0, sizeof(int), st));
     if (it == 0 && E->fused)
       E->run("k_resid_down0", 5.25, [&] { return launch_resid_down0(sp, Ux, Uy, pA, pB, rs, which, st); }, st, gi);
-    else
+    else {
+      E->run("k_unskew_r", 2, [&] { return launch_unskew_r(sb, r, st); }, st, gi);
       E->run("k_mg_down0", 4.25, [&] { return launch_mg_down0(sb, r, rs, st); }, st, gi);
+    }
     E->run("k_mg_coarse", 0.5, [&] { return launch_mg_coarse(sb, st); }, st, gi);
     E->run("k_mg_up0", 4.25, [&] { return launch_mg_up0(sb, rs, st); }, st, gi);
     E->run("k_smooth0", 4, [&] { return launch_smooth0(sb, rs, r, which, st); }, st, gi);
@@ -293,6 +296,7 @@ int capture_half_step(rlfc_env* E, Group& G, cudaStream_t st, const float* sx, c
     CU(cudaGraphAddNode(&cond, graph, deps, ndeps, &np));
     cudaGraph_t body = np.conditional.phGraph_out[0];
     CU(cudaStreamBeginCaptureToGraph(E->aux_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    launch_unskew_r(sb, r, E->aux_stream);
     launch_mg_down0(sb, r, rs, E->aux_stream);
     launch_mg_coarse(sb, E->aux_stream);
     launch_mg_up0(sb, rs, E->aux_stream);
@@ -302,6 +306,7 @@ int capture_half_step(rlfc_env* E, Group& G, cudaStream_t st, const float* sx, c
     CU(cudaStreamUpdateCaptureDependencies(st, &cond, 1, cudaStreamSetCaptureDependencies));
   } else {
     for (int it = 1; it < E->fixed_iters; it++) {
+      *n_body += launch_unskew_r(sb, r, st);
       *n_body += launch_mg_down0(sb, r, rs, st);
       *n_body += launch_mg_coarse(sb, st);
       *n_body += launch_mg_up0(sb, rs, st);
@@ -554,7 +559,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     }
     {  // pre-skewed coefficient table for the row-pipelined smoother (layout: solver.h RowTab)
       const int ni = H.n - 2, mj = H.m - 2;
-      const int C = (mj + 31) / 32, K = (4 * C + 1 + 3) / 4, nl = (mj + C - 1) / C;
+      const int C = (mj + 31) / 32, K = (3 * C + 1 + 3) / 4, nl = (mj + C - 1) / C;
       const int front = 10 /*kTabFront*/, entries = front + ni + nl + 10 /*kStageLag*/ + 5 /*kPF*/ + 6;
       if (C > 8) return bail(fail(RLFC_EGRID, "grids wider than 256 cells are not supported by the smoother yet"));
       std::vector<float4> T((size_t)entries * K * 32, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -568,7 +573,10 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
             if (row >= 1 && row <= ni + 1 && j <= mj) f[2 * C + 1 + c] = H.lx[(size_t)row * H.m + j];
             if (row >= 1 && row <= ni && j <= mj) {
               f[C + 1 + c] = -H.inv[(size_t)row * H.m + j];
-              f[3 * C + 1 + c] = H.diag[(size_t)row * H.m + j];
+              // the smoother recomputes the diagonal as PoissonMatrix does (PoissonMatrix.pde:46-48); it must agree
+              const size_t k = (size_t)row * H.m + j;
+              if (H.diag[k] != -(H.lx[k] + H.lx[k + H.m] + H.ly[k] + H.ly[k + 1]))
+                return bail(fail(RLFC_EGRID, "PoissonMatrix diagonal is not the plain coefficient sum"));
             }
           }
           for (int c = 0; c <= C; c++) {
@@ -647,6 +655,11 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   TRY(E->dmalloc(&E->d_actions, 2 * B)); TRY(E->dmalloc(&E->d_obs, 2 * B)); TRY(E->dmalloc(&E->d_reward, B));
   TRY(E->dmalloc(&E->d_done, B));
   TRY(E->dmalloc(&E->pB, S));
+  {
+    const int C0 = sp.lev[0].rt.C, mj0 = g.m - 2;
+    sp.rsk_stride = (size_t)round_up((int)rows_skew_floats(C0, g.n - 2, (mj0 + C0 - 1) / C0), 32);
+    TRY(E->dmalloc(&sp.rsk, sp.rsk_stride * B));
+  }
 #undef TRY
   auto hostalloc = [&](void** p, size_t bytes) { return cudaMallocHost(p, bytes) == cudaSuccess; };
   if (!hostalloc((void**)&E->h_actions, 2 * B * sizeof(float)) || !hostalloc((void**)&E->h_obs, 2 * B * sizeof(float)) ||
@@ -670,6 +683,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
       v.lev[l].r += o; v.lev[l].x += o; v.lev[l].d += o;
     }
     v.band_tmp += (size_t)e0 * (v.nband_x + v.nband_y);
+    v.rsk += (size_t)e0 * v.rsk_stride;
     v.sc.xi += 2 * e0; v.sc.t += e0; v.sc.force += 2 * e0; v.sc.probes += (size_t)e0 * RLFC_NUM_PROBES;
     v.sc.callLearn += e0; v.sc.Cd += e0; v.sc.Cl += e0; v.sc.obs += 2 * e0; v.sc.active += e0; v.sc.iters += 2 * e0;
     v.sc.psum += e0; v.sc.any_active += g;

@@ -12,13 +12,13 @@
 //     finds the previous sweep's values at (i+1,j), (i,j+1)), the increment stage (row t - L - 10) applies
 //     d.setBC, x += d and, on level 0, r -= A d;
 //   * every stage runs in its OWN warp, so a step costs one sweep of one row (C*9 flops per lane) instead
-//     of five:  warps 0..3 = sweeps 1..4,  warp 4 = residual increment (level 0),  warp 5 = stage 0 +
-//     bulk-copy loader,  warp 6 = x increment + coalesced write-out (+ r.r),  warp 7 = the serial Field.sum of
+//     of five:  warps 0..3 = sweeps 1..4,  warp 4 = residual increment + r.r (level 0),  warp 5 = stage 0 +
+//     bulk-copy loader,  warp 6 = x increment + coalesced write-out,  warp 7 = the serial Field.sum of
 //     the new x (level 0).  Stages hand rows to
 //     each other through small shared-memory buffers indexed by step ([lane][C] blocks, read and written
 //     with vector accesses), with one __syncthreads per step;
 //   * static coefficients come from a host-built, pre-skewed table: entry tau holds, for lane L, the
-//     coefficients of row tau - L ([cy(C+1) | -inv(C) | cx(C) | diag(C)] as float4 vectors, lane-contiguous),
+//     coefficients of row tau - L ([cy(C+1) | -inv(C) | cx(C)] as float4 vectors, lane-contiguous),
 //     so all lanes of a stage read the same ring slot; entries land in a 16-slot shared-memory ring by
 //     cp.async kPF steps ahead.  Entries are zero for every (row, column) that is not an interior cell, so
 //     such a stage evaluates to +-0 by itself; out-of-domain operands are ghosts of d whose products with
@@ -55,14 +55,20 @@ constexpr int kStageLag = 10;      // rows between stage 0 and the residual incr
 constexpr int kTabFront = 10;      // table entry index = tau + kTabFront (entries tau <= 0 are zero)
 constexpr int kSLanes = 33;        // stage buffers carry a zero 33rd lane (right-hand domain edge)
 
-__host__ __device__ constexpr int rows_K(int C) { return (4 * C + 1 + 3) / 4; }   // float4 vectors per lane-entry
+__host__ __device__ constexpr int rows_K(int C) { return (3 * C + 1 + 3) / 4; }   // float4 vectors per lane-entry
 __host__ __device__ constexpr int rows_CP(int C) { return (C + 1) & ~1; }          // lane block of the stage buffers (even)
 __host__ __device__ inline int rows_table_entries(int ni, int nl) { return kTabFront + ni + nl + kStageLag + kPF + 6; }
 
-// dynamic shared memory of one rows_smooth call (bytes): [coef ring | r ring | x ring | R ring | stage buffers]
-__host__ __device__ inline size_t rows_smem_bytes(int C, int P) {
-  return (size_t)kCoefSlots * rows_K(C) * 32 * 16 + 2 * (size_t)kRowRing * P * 4 +
+// dynamic shared memory of one rows_smooth call (bytes): [coef ring | r ring (plain-r modes) | x ring | R ring |
+// stage buffers | mbarriers]; `skewed_r` = level-0 mode, where r arrives pre-skewed and needs no row ring
+__host__ __device__ inline size_t rows_smem_bytes(int C, int P, bool skewed_r) {
+  return (size_t)kCoefSlots * rows_K(C) * 32 * 16 + (skewed_r ? 1 : 2) * (size_t)kRowRing * P * 4 +
          (size_t)(kRSlots * 32 + 5 * 2 * kSLanes) * rows_CP(C) * 4 + 16 + kCoefSlots * 8;
+}
+// skewed residual array of one environment (level 0): entry tau = i + l holds row i of lane l's columns,
+// [tau][32][CP] floats; entries the smoother touches: 1 .. ni + nl + kStageLag + kPF + 2
+__host__ __device__ inline size_t rows_skew_floats(int C, int ni, int nl) {
+  return (size_t)(ni + nl + kStageLag + kPF + 8) * 32 * rows_CP(C);
 }
 
 namespace rows_detail {
@@ -156,19 +162,22 @@ __host__ __device__ constexpr int ring_mod(int row) { return ((row % kRowRing) +
 // XMODE selects what the increment stages do with a finished row of d:
 //   1: x = 0 + d                      (coarsest level: x starts at 0, MG.pde:56,95)
 //   2: x = x + d                      (x.plusEq(d), MG.pde:95)
-//   3: level-0 smooth(4) complete (MG.pde:90-97): d.setBC (clamped neighbours), x += d, r -= A d written to
-//      r_out, r.r accumulated, and the boundary values of d kept in gbuf (top row, bottom row, left column,
-//      right column: 2*mj + 2*ni floats) for the ghost cells of x
-// Called by ALL kRowsThreads threads of the CTA.  r, x (and r_out) are this environment's row-major pitched
-// arrays of the level.  Returns this thread's share of r.r (XMODE 3; non-zero only in the write-out warp).
+//   3: level-0 smooth(4) complete (MG.pde:90-97): d.setBC (clamped neighbours), x += d, r -= A d, r.r accumulated,
+//      and the boundary values of d kept in gbuf (top row, bottom row, left column, right column: 2*mj + 2*ni
+//      floats) for the ghost cells of x.  In this mode `r` is the environment's SKEWED residual array
+//      (rows_skew_floats; written by k_mg_up0): entry tau is one contiguous block that is bulk-copied straight into
+//      the step-indexed ring, and the new residual is written back in place, skewed, as coalesced stores.
+// Called by ALL kRowsThreads threads of the CTA.  x (and r in modes 1, 2) are this environment's row-major pitched
+// arrays of the level.  Returns this thread's share of r.r (XMODE 3; non-zero only in the residual warp).
 template <int C, int XMODE>
-__device__ __forceinline__ double rows_smooth(const DevLevel& L, const float* __restrict__ r, float* __restrict__ x,
-                                              float* __restrict__ r_out, unsigned char* smem_raw, float* gbuf, float* psum_out = nullptr,
+__device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restrict__ r, float* __restrict__ x,
+                                              unsigned char* smem_raw, float* gbuf, float* psum_out = nullptr,
                                               const int dbg = 0) {
   using namespace rows_detail;
   constexpr int K = rows_K(C), CP = rows_CP(C);
   // float offsets inside a lane-entry
-  constexpr int F_CY = 0, F_NINV = C + 1, F_CX = 2 * C + 1, F_DIAG = 3 * C + 1;
+  constexpr int F_CY = 0, F_NINV = C + 1, F_CX = 2 * C + 1, F_END = 3 * C + 1;
+  constexpr bool SKEW = (XMODE == 3);
   constexpr int ES = K * 32;                       // float4s per entry
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ni = L.n - 2, mj = L.m - 2, P = L.P;
@@ -176,8 +185,8 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, const float* __
   const int lag = nl + kStageLag;                  // row w is complete after step w + nl - 1 + kStageLag
   const int t_end = (ni + lag + 1) & ~1;           // last step (even count; the last write-out is at step ni + lag)
   float4* coef = reinterpret_cast<float4*>(smem_raw);
-  float* rring = reinterpret_cast<float*>(smem_raw + (size_t)kCoefSlots * ES * 16);
-  float* xring = rring + (size_t)kRowRing * P;
+  float* rring = reinterpret_cast<float*>(smem_raw + (size_t)kCoefSlots * ES * 16);   // plain-r modes only
+  float* xring = rring + (SKEW ? 0 : (size_t)kRowRing * P);
   float* R = xring + (size_t)kRowRing * P;         // [kRSlots][32][CP]
   float* S = R + (size_t)kRSlots * 32 * CP;        // [stage 0..4][parity][kSLanes][CP]
   const float4* __restrict__ tab = L.rt.T + (size_t)(blockIdx.x % (unsigned)L.rt.copies) * ((size_t)L.rt.entries * ES);
@@ -196,16 +205,17 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, const float* __
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const unsigned row_bytes = (unsigned)P * 4u, ent_bytes = (unsigned)ES * 16u;
+  const unsigned row_bytes = (unsigned)P * 4u, ent_bytes = (unsigned)ES * 16u, rsk_bytes = 32u * CP * 4u;
   auto issue = [&](int q) {
     unsigned long long* bar = bars + ((q - 1) & (kCoefSlots - 1));    // q >= 1: use k = (q-1)/16 of this barrier
     const bool row = q >= 1 && q <= ni;
-    mbar_expect_tx(bar, ent_bytes + (row ? (XMODE != 1 ? 2u : 1u) * row_bytes : 0u));
+    mbar_expect_tx(bar, ent_bytes + (SKEW ? rsk_bytes : 0u) + (row ? ((XMODE != 1 ? 1u : 0u) + (SKEW ? 0u : 1u)) * row_bytes : 0u));
     if (row) {
       const int slot = ring_mod(q);
-      bulk_g2s(rring + (size_t)slot * P, r + (size_t)q * P, row_bytes, bar);
+      if (!SKEW) bulk_g2s(rring + (size_t)slot * P, r + (size_t)q * P, row_bytes, bar);
       if (XMODE != 1) bulk_g2s(xring + (size_t)slot * P, x + (size_t)q * P, row_bytes, bar);
     }
+    if (SKEW) bulk_g2s(R + (size_t)(q & (kRSlots - 1)) * 32 * CP, r + (size_t)q * 32 * CP, rsk_bytes, bar);
     bulk_g2s(coef + (size_t)(q & (kCoefSlots - 1)) * ES, tab + (size_t)(q + kTabFront) * ES, ent_bytes, bar);
   };
   if (warp == 5) {
@@ -242,7 +252,7 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, const float* __
     auto fetch = [&]() {
       const int e1 = (e0 + 1) & (kCoefSlots - 1);
       ld_entry<F_CY, F_CX>(cl + e0 * ES, cyn);
-      ld_entry<F_CX, F_DIAG>(cl + e1 * ES, cxE);
+      ld_entry<F_CX, F_END>(cl + e1 * ES, cxE);
       ld_block<C>(Rl + e0 * 32 * CP, rv);
     };
     fetch();
@@ -280,11 +290,11 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, const float* __
 #pragma unroll
       for (int c = 0; c < C; c++) { dC[c] = 0.f; dW[c] = 0.f; dEp[c] = 0.f; cxW[c] = 0.f; }
       int i5 = 1 - lane - kStageLag;
-      int slot = ring_mod(i5);
       const float* Sin = S + ((size_t)4 * 2 * kSLanes + lane) * CP;
       const float* Rl = R + (size_t)lane * CP;
       const float4* cl = coef + lane;
       int e0 = (1 - kStageLag) & (kCoefSlots - 1);
+      float* rout = r + ((ptrdiff_t)(1 - kStageLag) * 32 + lane) * CP;   // skewed entry t - 10 of this lane
       // which of this lane's columns are the first / last column of the level
       const int cfirst = (lane == 0) ? 0 : -1;
       const int clast = (lane == nl - 1) ? (mj - 1) - C * lane : -1;
@@ -293,33 +303,36 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, const float* __
         if (dbg & 1) { RLFC_STEP_SYNC(); return; }
         const int e1 = (e0 + 1) & (kCoefSlots - 1);
         const float* Sp = Sin + (par ^ 1) * kSLanes * CP;
-        float dE[C], cxE[C], cy[C + 1], dg[C], rv[C];
+        float dE[C], cxE[C], cy[C + 1], rv[C], rN[C];
         ld_block<C>(Sp, dE);
         const float Nx = Sp[CP];
 #pragma unroll
         for (int c = 0; c < C; c++) { dW[c] = dC[c]; dC[c] = dEp[c]; dEp[c] = dE[c]; }
         float Sl = __shfl_up_sync(0xffffffffu, dW[C - 1], 1);
         ld_entry<F_CY, F_NINV>(cl + e0 * ES, cy);
-        ld_entry<F_DIAG, 4 * C + 1>(cl + e0 * ES, dg);
-        ld_entry<F_CX, F_DIAG>(cl + e1 * ES, cxE);
+        ld_entry<F_CX, F_END>(cl + e1 * ES, cxE);
         ld_block<C>(Rl + e0 * 32 * CP, rv);
         const bool rowok = (unsigned)(i5 - 1) < (unsigned)ni;
         const bool top = i5 == 1, bot = i5 == ni;
-        float* rrow = rring + (size_t)slot * P + j0;
 #pragma unroll
         for (int c = 0; c < C; c++) {
           const float d0 = dC[c];
+          const float dg = -(cxW[c] + cxE[c] + cy[c] + cy[c + 1]);   // diagonal = -sumd, PoissonMatrix.pde:46-48
           const float w_ = top ? d0 : dW[c];
           const float e_ = bot ? d0 : dE[c];
           const float s_ = (c == cfirst) ? d0 : ((c == 0) ? Sl : dC[c == 0 ? 0 : c - 1]);
           const float n_ = (c == clast) ? d0 : ((c == C - 1) ? Nx : dC[c == C - 1 ? c : c + 1]);
-          const float Ad = d0 * dg[c] + w_ * cxW[c] + e_ * cxE[c] + s_ * cy[c] + n_ * cy[c + 1];   // PoissonMatrix.pde:56-61
-          if (rowok && C * lane + c < mj) rrow[c] = rv[c] - Ad;
+          const float Ad = d0 * dg + w_ * cxW[c] + e_ * cxE[c] + s_ * cy[c] + n_ * cy[c + 1];   // PoissonMatrix.pde:56-61
+          const bool ok = rowok && C * lane + c < mj;
+          rN[c] = ok ? rv[c] - Ad : 0.f;
+          const float prod = rN[c] * rN[c];            // float product, double accumulation (Field.pde:304-307)
+          rr += (double)prod;
           cxW[c] = cxE[c];
         }
+        if (rowok) st_block<C>(rout, rN);              // one contiguous 32*CP-float block per warp and step
         e0 = e1;
         i5++;
-        slot = ring_inc(slot);
+        rout += 32 * CP;
         RLFC_STEP_SYNC();
       };
       for (int t = 1; t <= t_end; t += 2) {
@@ -342,15 +355,18 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, const float* __
       float ninv[C], rv[C], d0[C];
       if (!(dbg & 8)) {
       ld_entry<F_NINV, F_CX>(cl + e0 * ES, ninv);
-      const bool rowok = (unsigned)(i0 - 1) < (unsigned)ni;
-      const float* rrow = rring + (size_t)slot0 * P + j0;
+      if (SKEW) {
+        ld_block<C>(Rl + e0 * 32 * CP, rv);          // entry t of the skewed residual (zero outside the domain)
+      } else {
+        const bool rowok = (unsigned)(i0 - 1) < (unsigned)ni;
+        const float* rrow = rring + (size_t)slot0 * P + j0;
 #pragma unroll
-      for (int c = 0; c < C; c++) {
-        rv[c] = (rowok && C * lane + c < mj) ? rrow[c] : 0.f;
-        d0[c] = rv[c] * (-ninv[c]);                 // MG.pde:80
+        for (int c = 0; c < C; c++) rv[c] = (rowok && C * lane + c < mj) ? rrow[c] : 0.f;
+        st_block<C>(Rl + e0 * 32 * CP, rv);
       }
+#pragma unroll
+      for (int c = 0; c < C; c++) d0[c] = rv[c] * (-ninv[c]);   // MG.pde:80
       st_block<C>(Sout + par * kSLanes * CP, d0);
-      st_block<C>(Rl + e0 * 32 * CP, rv);
       }
       if (lane == 0) {
         if (!(dbg & 128)) fence_proxy_async();
@@ -401,32 +417,20 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, const float* __
           }
         }
       }
-      {  // write-out of row t - lag: every lane's increment stages passed it at step t - 1 (+ r.r)
+      {  // write-out of row t - lag: every lane's x increment passed it at step t - 2
         const int w = t - lag;
         if (w >= 1 && w <= ni) {
-          const int ws = ring_mod(w);
-          const float* xs = xring + (size_t)ws * P;
-          const float* rs = rring + (size_t)ws * P;
-          float xo[C], rN[C];
+          const float* xs = xring + (size_t)ring_mod(w) * P;
+          float xo[C];
 #pragma unroll
           for (int c = 0; c < C; c++) {
             const int j = 1 + lane + 32 * c;
             xo[c] = (j <= mj) ? xs[j] : 0.f;
-            if (XMODE == 3) rN[c] = (j <= mj) ? rs[j] : 0.f;
           }
           float* xg = x + (size_t)w * P + 1 + lane;
-          float* rg = r_out + (size_t)w * P + 1 + lane;
 #pragma unroll
-          for (int c = 0; c < C; c++) {
-            if (1 + lane + 32 * c <= mj) {
-              xg[32 * c] = xo[c];
-              if (XMODE == 3) rg[32 * c] = rN[c];
-            }
-            if (XMODE == 3) {
-              const float prod = rN[c] * rN[c];          // float product, double accumulation (Field.pde:304-307)
-              rr += (double)prod;
-            }
-          }
+          for (int c = 0; c < C; c++)
+            if (1 + lane + 32 * c <= mj) xg[32 * c] = xo[c];
         }
       }
       i6++;
@@ -436,15 +440,15 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, const float* __
   } else {
     // ------------------------------------------------------------------ Field.sum of the new x (level 0 only)
     // Field.pde:311-318: a serial float accumulation over the interior in i-major order.  Row w is complete in the
-    // ring after step w + lag - 1; one lane-uniform chain of mj dependent adds per step keeps pace with the pipeline,
-    // so the sum is finished together with the smoother instead of costing a kernel of its own.
+    // ring after step w + lag - 1; one lane-uniform chain of mj dependent adds per step, so the sum is finished together
+    // with the smoother instead of costing a kernel of its own (only worth it when that chain is not the slowest stage).
     float s = 0.f;
     for (int t = 1; t <= t_end; t++) {
       const int w = t - lag;
       if (XMODE == 3 && psum_out && w >= 1 && w <= ni && !(dbg & 4)) {
         const float4* xs4 = reinterpret_cast<const float4*>(xring + (size_t)ring_mod(w) * P);   // columns 0..3, 4..7, ...
         // the chain runs over columns 1 .. mj (column 0 is the ghost); the row is fetched kSumB vectors at a time, one
-        // batch ahead of the adds, so the chain never waits for shared memory
+        // batch ahead of the adds
         constexpr int kSumB = 8;
         const int nv = (mj + 4) / 4;                 // vectors that hold columns 0 .. mj
         float4 cur[kSumB], nxt[kSumB];

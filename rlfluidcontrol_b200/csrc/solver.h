@@ -27,7 +27,7 @@ struct SkewLevel {
 // Pre-skewed static coefficient table of one level for the row-pipelined smoother (smooth_rows.cuh):
 // entry tau (stored at index tau + kTabFront) holds, for lane l, the coefficients of row tau - l of the
 // lane's C columns j0 = C*l+1 .. C*l+C as the float stream [ly[row][j0+c] (C+1) | -inv[row][j0+c] (C) |
-// lx[row][j0+c] (C) | diag[row][j0+c] (C)], packed into K = ceil((4C+1)/4) float4 vectors that are
+// lx[row][j0+c] (C)], packed into K = ceil((3C+1)/4) float4 vectors that are
 // lane-contiguous: vector k of lane l of entry e sits at T[(e*K + k)*32 + l].
 struct RowTab {
   const float4* T;
@@ -92,6 +92,8 @@ struct SolverParams {
   const BandFace *band_x, *band_y;
   int nband_x, nband_y;
   float *band_tmp;          // [B][nband_x + nband_y]
+  float *rsk;               // [B][rsk_stride] level-0 residual in the smoother's skewed layout (smooth_rows.cuh)
+  size_t rsk_stride;
   const ForcePt *force_pts; int nforce;
   const SamplePt *probe_pts; int nprobe;
   int rr_blocks;            // number of per-env partial sums written by the increment kernel
@@ -116,6 +118,8 @@ int launch_project_shift(const SolverParams& P, const float* p_in, float* p_out,
 int launch_mg_down0(const SolverParams& P, const float* r_in, float* r_out, cudaStream_t st);
 int launch_mg_coarse(const SolverParams& P, cudaStream_t st);
 int launch_mg_up0(const SolverParams& P, float* r, cudaStream_t st);
+// rows smoother only: plain level-0 residual <- skewed residual (needed before a further MG iteration's down0)
+int launch_unskew_r(const SolverParams& P, float* r, cudaStream_t st);
 int launch_smooth0(const SolverParams& P, const float* r_in, float* r_out, int which, cudaStream_t st);
 // last node of the MG iteration body inside a CUDA-graph WHILE node: cond = any env still active
 int launch_loopcond(const SolverParams& P, unsigned long long cond_handle, cudaStream_t st);

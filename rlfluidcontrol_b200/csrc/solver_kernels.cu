@@ -497,6 +497,8 @@ k_mg_coarse(const __grid_constant__ SolverParams q) {
 // ------------------------------------------------------------------------------------------------
 // level 0, up: d = prolongate(x1) (+setBC), x += d, r -= A d   (MG.pde:75-76)
 // ------------------------------------------------------------------------------------------------
+// SKEWED: the updated residual goes to the row smoother's skewed array (solver.h rsk) instead of back in place
+template <bool SKEWED>
 __global__ void __launch_bounds__(256)
 k_mg_up0(const __grid_constant__ SolverParams q, float* __restrict__ r_all) {
   const int e = blockIdx.z;
@@ -519,8 +521,30 @@ k_mg_up0(const __grid_constant__ SolverParams q, float* __restrict__ r_all) {
   if (i >= 1 && j >= 1 && i <= n - 2 && j <= m - 2) {
     float Ad = dc * L0.diag[k] + dval(i - 1, j) * L0.lx[k] + dval(i + 1, j) * L0.lx[k + P] + dval(i, j - 1) * L0.ly[k] +
                dval(i, j + 1) * L0.ly[k + 1];
-    r_all[eo + k] -= Ad;
+    if (SKEWED) {
+      const int C = L0.rt.C, CP = rows_CP(C);
+      const int ln = (j - 1) / C, c = (j - 1) - ln * C;
+      q.rsk[(size_t)e * q.rsk_stride + ((size_t)(i + ln) * 32 + ln) * CP + c] = r_all[eo + k] - Ad;
+    } else {
+      r_all[eo + k] -= Ad;
+    }
   }
+}
+
+// plain level-0 residual <- skewed residual (the row smoother leaves r - A d there); only environments that
+// go on to a further MG iteration need it
+__global__ void __launch_bounds__(256)
+k_unskew_r(const __grid_constant__ SolverParams q, float* __restrict__ r_all) {
+  const int e = blockIdx.z;
+  if (!q.sc.active[e]) return;
+  const DevLevel& L0 = q.lev[0];
+  const int P = L0.P, n = L0.n, m = L0.m;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i < 1 || j < 1 || i > n - 2 || j > m - 2) return;
+  const int C = L0.rt.C, CP = rows_CP(C);
+  const int ln = (j - 1) / C, c = (j - 1) - ln * C;
+  r_all[(size_t)e * L0.stride + IDX(i, j)] = q.rsk[(size_t)e * q.rsk_stride + ((size_t)(i + ln) * 32 + ln) * CP + c];
 }
 
 // level 0 smooth(4) complete (MG.pde:79-97) + the MGsolver loop test (MG.pde:32-35), one CTA per env with one
@@ -566,12 +590,12 @@ k_smooth0(const __grid_constant__ SolverParams q, const float* r_in_all, float* 
 // Row-pipelined variants (smooth_rows.cuh): one warp per sweep, C columns per lane.
 // ------------------------------------------------------------------------------------------------
 template <int XMODE>
-__device__ __forceinline__ void rows_dispatch(const DevLevel& L, const float* r, float* x, unsigned char* smem) {
+__device__ __forceinline__ void rows_dispatch(const DevLevel& L, float* r, float* x, unsigned char* smem) {
   switch (L.rt.C) {
-    case 1: rows_smooth<1, XMODE>(L, r, x, nullptr, smem, nullptr); break;
-    case 2: rows_smooth<2, XMODE>(L, r, x, nullptr, smem, nullptr); break;
-    case 3: rows_smooth<3, XMODE>(L, r, x, nullptr, smem, nullptr); break;
-    default: rows_smooth<4, XMODE>(L, r, x, nullptr, smem, nullptr); break;
+    case 1: rows_smooth<1, XMODE>(L, r, x, smem, nullptr); break;
+    case 2: rows_smooth<2, XMODE>(L, r, x, smem, nullptr); break;
+    case 3: rows_smooth<3, XMODE>(L, r, x, smem, nullptr); break;
+    default: rows_smooth<4, XMODE>(L, r, x, smem, nullptr); break;
   }
 }
 
@@ -611,16 +635,16 @@ k_mg_coarse_rows(const __grid_constant__ SolverParams q) {
 
 template <int C>
 __global__ void __launch_bounds__(kRowsThreads)
-k_smooth0_rows(const __grid_constant__ SolverParams q, const float* r_in_all, float* r_out_all, int which) {
+k_smooth0_rows(const __grid_constant__ SolverParams q, int which) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const DevLevel& L = q.lev[0];
   const int n = L.n, m = L.m, P = L.P, ni = n - 2, mj = m - 2;
-  float* gbuf = reinterpret_cast<float*>(smem_raw + rows_smem_bytes(C, P));
+  float* gbuf = reinterpret_cast<float*>(smem_raw + rows_smem_bytes(C, P, true));
   __shared__ double wsum[32];
   const int e = blockIdx.x;
   if (!q.sc.active[e]) return;
   float* p = L.x + (size_t)e * L.stride;
-  double rr = rows_smooth<C, 3>(L, r_in_all + (size_t)e * L.stride, p, r_out_all + (size_t)e * L.stride, smem_raw, gbuf, q.fuse_psum ? q.sc.psum + e : nullptr, q.dbg);
+  double rr = rows_smooth<C, 3>(L, q.rsk + (size_t)e * q.rsk_stride, p, smem_raw, gbuf, q.fuse_psum ? q.sc.psum + e : nullptr, q.dbg);
   // ghost cells of x: x.plusEq(d) runs over all cells and d.setBC copied the adjacent interior value (MG.pde:90,95)
   const float *gtop = gbuf, *gbot = gbuf + mj, *gleft = gbuf + 2 * mj, *gright = gbuf + 2 * mj + ni;
   for (int c = threadIdx.x; c < mj; c += blockDim.x) { p[IDX(0, c + 1)] += gtop[c]; p[IDX(n - 1, c + 1)] += gbot[c]; }
@@ -941,11 +965,11 @@ static size_t smooth0_smem(const SolverParams& q) {
 // opt-in shared-memory sizes; called once per handle, outside any stream capture
 static size_t coarse_rows_smem(const SolverParams& q) {
   size_t s = 0;
-  for (int l = 1; l < q.nlevels; l++) s = max(s, rows_smem_bytes(min(q.lev[l].rt.C, 4), q.lev[l].P));
+  for (int l = 1; l < q.nlevels; l++) s = max(s, rows_smem_bytes(min(q.lev[l].rt.C, 4), q.lev[l].P, false));
   return s;
 }
 static size_t smooth0_rows_smem(const SolverParams& q) {
-  return rows_smem_bytes(q.lev[0].rt.C, q.P) + sizeof(float) * (2 * (q.n - 2) + 2 * (q.m - 2));
+  return rows_smem_bytes(q.lev[0].rt.C, q.P, true) + sizeof(float) * (2 * (q.n - 2) + 2 * (q.m - 2));
 }
 
 template <int C>
@@ -983,7 +1007,15 @@ int launch_mg_coarse(const SolverParams& q, cudaStream_t st) {
 
 int launch_mg_up0(const SolverParams& q, float* r, cudaStream_t st) {
   dim3 blk(32, 8);
-  k_mg_up0<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, r);
+  if (q.use_rows) k_mg_up0<true><<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, r);
+  else k_mg_up0<false><<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, r);
+  return 1;
+}
+
+int launch_unskew_r(const SolverParams& q, float* r, cudaStream_t st) {
+  if (!q.use_rows) return 0;
+  dim3 blk(32, 8);
+  k_unskew_r<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, r);
   return 1;
 }
 
@@ -991,14 +1023,14 @@ int launch_smooth0(const SolverParams& q, const float* r_in, float* r_out, int w
   if (q.use_rows) {
     const size_t sm = smooth0_rows_smem(q);
     switch (q.lev[0].rt.C) {
-      case 1: k_smooth0_rows<1><<<q.B, kRowsThreads, sm, st>>>(q, r_in, r_out, which); break;
-      case 2: k_smooth0_rows<2><<<q.B, kRowsThreads, sm, st>>>(q, r_in, r_out, which); break;
-      case 3: k_smooth0_rows<3><<<q.B, kRowsThreads, sm, st>>>(q, r_in, r_out, which); break;
-      case 4: k_smooth0_rows<4><<<q.B, kRowsThreads, sm, st>>>(q, r_in, r_out, which); break;
-      case 5: k_smooth0_rows<5><<<q.B, kRowsThreads, sm, st>>>(q, r_in, r_out, which); break;
-      case 6: k_smooth0_rows<6><<<q.B, kRowsThreads, sm, st>>>(q, r_in, r_out, which); break;
-      case 7: k_smooth0_rows<7><<<q.B, kRowsThreads, sm, st>>>(q, r_in, r_out, which); break;
-      default: k_smooth0_rows<8><<<q.B, kRowsThreads, sm, st>>>(q, r_in, r_out, which); break;
+      case 1: k_smooth0_rows<1><<<q.B, kRowsThreads, sm, st>>>(q, which); break;
+      case 2: k_smooth0_rows<2><<<q.B, kRowsThreads, sm, st>>>(q, which); break;
+      case 3: k_smooth0_rows<3><<<q.B, kRowsThreads, sm, st>>>(q, which); break;
+      case 4: k_smooth0_rows<4><<<q.B, kRowsThreads, sm, st>>>(q, which); break;
+      case 5: k_smooth0_rows<5><<<q.B, kRowsThreads, sm, st>>>(q, which); break;
+      case 6: k_smooth0_rows<6><<<q.B, kRowsThreads, sm, st>>>(q, which); break;
+      case 7: k_smooth0_rows<7><<<q.B, kRowsThreads, sm, st>>>(q, which); break;
+      default: k_smooth0_rows<8><<<q.B, kRowsThreads, sm, st>>>(q, which); break;
     }
     return 1;
   }
