@@ -506,7 +506,6 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   sp.use_rows = 1;
   sp.fuse_psum = 0;
   if (const char* ev = std::getenv("RLFC_FUSE_PSUM")) sp.fuse_psum = std::atoi(ev) != 0;
-  if (const char* ev = std::getenv("RLFC_DBG")) sp.dbg = std::atoi(ev);
   if (const char* ev = std::getenv("RLFC_SMOOTHER")) sp.use_rows = std::string(ev) != "strip";
   if (!sp.use_rows) sp.fuse_psum = 0;
   sp.nlevels = (int)g.levels.size();

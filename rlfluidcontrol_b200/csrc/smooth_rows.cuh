@@ -171,8 +171,7 @@ __host__ __device__ constexpr int ring_mod(int row) { return ((row % kRowRing) +
 // arrays of the level.  Returns this thread's share of r.r (XMODE 3; non-zero only in the residual warp).
 template <int C, int XMODE>
 __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restrict__ r, float* __restrict__ x,
-                                              unsigned char* smem_raw, float* gbuf, float* psum_out = nullptr,
-                                              const int dbg = 0) {
+                                              unsigned char* smem_raw, float* gbuf, float* psum_out = nullptr) {
   using namespace rows_detail;
   constexpr int K = rows_K(C), CP = rows_CP(C);
   // float offsets inside a lane-entry
@@ -258,7 +257,6 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
     fetch();
     auto step = [&](auto par_c) {
       constexpr int par = decltype(par_c)::value;
-      if (dbg & 64) { RLFC_STEP_SYNC(); return; }
       float E[C];
       float Sl = __shfl_up_sync(0xffffffffu, prev[C - 1], 1);
       const float* Sp = Sin + (par ^ 1) * kSLanes * CP;
@@ -268,15 +266,15 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
       float res[C];
 #pragma unroll
       for (int c = 0; c < C; c++) {
-        const float Sop = (c == 0 || (dbg & 32)) ? Sl : res[c == 0 ? 0 : c - 1];
+        const float Sop = (c == 0) ? Sl : res[c == 0 ? 0 : c - 1];
         const float Nop = (c == C - 1) ? Nx : Ep[c == C - 1 ? c : c + 1];
         res[c] = (prev[c] * cxW[c] + E[c] * cxE[c] + Sop * cyn[c] + Nop * cyn[c + 1] - rv[c]) * cyn[C + 1 + c];
       }
-      if (!(dbg & 256)) st_block<C>(Sout + par * kSLanes * CP, res);
+      st_block<C>(Sout + par * kSLanes * CP, res);
 #pragma unroll
       for (int c = 0; c < C; c++) { prev[c] = res[c]; Ep[c] = E[c]; cxW[c] = cxE[c]; }
       e0 = (e0 + 1) & (kCoefSlots - 1);
-      if (!(dbg & 512)) fetch();
+      fetch();
       RLFC_STEP_SYNC();
     };
     for (int t = 1; t <= t_end; t += 2) {
@@ -300,7 +298,6 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
       const int clast = (lane == nl - 1) ? (mj - 1) - C * lane : -1;
       auto step = [&](auto par_c) {
         constexpr int par = decltype(par_c)::value;
-        if (dbg & 1) { RLFC_STEP_SYNC(); return; }
         const int e1 = (e0 + 1) & (kCoefSlots - 1);
         const float* Sp = Sin + (par ^ 1) * kSLanes * CP;
         float dE[C], cxE[C], cy[C + 1], rv[C], rN[C];
@@ -351,9 +348,8 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
     const float4* cl = coef + lane;
     for (int t = 1; t <= t_end; t++) {
       const int par = t & 1, e0 = t & (kCoefSlots - 1);
-      if (dbg & 16) { RLFC_STEP_SYNC(); continue; }
       float ninv[C], rv[C], d0[C];
-      if (!(dbg & 8)) {
+      {
       ld_entry<F_NINV, F_CX>(cl + e0 * ES, ninv);
       if (SKEW) {
         ld_block<C>(Rl + e0 * 32 * CP, rv);          // entry t of the skewed residual (zero outside the domain)
@@ -369,7 +365,7 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
       st_block<C>(Sout + par * kSLanes * CP, d0);
       }
       if (lane == 0) {
-        if (!(dbg & 128)) fence_proxy_async();
+        fence_proxy_async();
         issue(t + kPF);
       }
       mbar_wait(bars + (t & (kCoefSlots - 1)), ((unsigned)t >> kCoefShift) & 1u);   // entry / row t + 1 has landed
@@ -378,7 +374,7 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
       RLFC_STEP_SYNC();
     }
     // drain: every issued copy must have landed before the shared memory is reused
-    if (!(dbg & 16)) for (int q = t_end + 2; q <= t_end + kPF; q++) mbar_wait(bars + ((q - 1) & (kCoefSlots - 1)), ((unsigned)(q - 1) >> kCoefShift) & 1u);
+    for (int q = t_end + 2; q <= t_end + kPF; q++) mbar_wait(bars + ((q - 1) & (kCoefSlots - 1)), ((unsigned)(q - 1) >> kCoefShift) & 1u);
   } else if (warp == 6) {
     // ------------------------------------------------------------------ x increment: row t - L - 9 (sweep 4's last row)
     int i6 = 1 - lane - 9;
@@ -390,7 +386,6 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
     float* gright = gbuf + 2 * mj + ni;
     for (int t = 1; t <= t_end; t++) {
       const int par = t & 1;
-      if (dbg & 2) { RLFC_STEP_SYNC(); continue; }
       float d[C], xv[C];
       ld_block<C>(Sin + (par ^ 1) * kSLanes * CP, d);
       const bool rowok = (unsigned)(i6 - 1) < (unsigned)ni;
@@ -445,7 +440,7 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
     float s = 0.f;
     for (int t = 1; t <= t_end; t++) {
       const int w = t - lag;
-      if (XMODE == 3 && psum_out && w >= 1 && w <= ni && !(dbg & 4)) {
+      if (XMODE == 3 && psum_out && w >= 1 && w <= ni) {
         const float4* xs4 = reinterpret_cast<const float4*>(xring + (size_t)ring_mod(w) * P);   // columns 0..3, 4..7, ...
         // the chain runs over columns 1 .. mj (column 0 is the ghost); the row is fetched kSumB vectors at a time, one
         // batch ahead of the adds

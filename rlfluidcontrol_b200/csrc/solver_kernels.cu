@@ -644,7 +644,7 @@ k_smooth0_rows(const __grid_constant__ SolverParams q, int which) {
   const int e = blockIdx.x;
   if (!q.sc.active[e]) return;
   float* p = L.x + (size_t)e * L.stride;
-  double rr = rows_smooth<C, 3>(L, q.rsk + (size_t)e * q.rsk_stride, p, smem_raw, gbuf, q.fuse_psum ? q.sc.psum + e : nullptr, q.dbg);
+  double rr = rows_smooth<C, 3>(L, q.rsk + (size_t)e * q.rsk_stride, p, smem_raw, gbuf, q.fuse_psum ? q.sc.psum + e : nullptr);
   // ghost cells of x: x.plusEq(d) runs over all cells and d.setBC copied the adjacent interior value (MG.pde:90,95)
   const float *gtop = gbuf, *gbot = gbuf + mj, *gleft = gbuf + 2 * mj, *gright = gbuf + 2 * mj + ni;
   for (int c = threadIdx.x; c < mj; c += blockDim.x) { p[IDX(0, c + 1)] += gtop[c]; p[IDX(n - 1, c + 1)] += gbot[c]; }

@@ -144,3 +144,41 @@ def test_reset_and_field_roundtrip(rlfc, init_state, tmp_path):
             assert_same(y, x, f"{nm} text checkpoint round trip")
         lines = path.read_text().splitlines()
         assert len(lines) == 2 + env.n * env.m and lines[2].count(",") == 2
+
+
+@pytest.mark.parametrize("resolution,xl,yl", [(16, 16, 8), (8, 16, 8), (12, 8, 4), (24, 8, 4)])
+def test_other_grids(rlfc, oracle, resolution, xl, yl):
+    """Other AFCCylinder grids (different columns-per-lane of the row smoother, different MG depths): impulsive
+    start, non-zero actions, every float equal to the oracle's."""
+    ref = oracle.OracleEnv(literal=False, resolution=resolution, xLengths=xl, yLengths=yl)
+    ref.set_xi(0.4, -0.7)
+    act = np.array([[0.4, -0.7], [0.0, 0.0]], np.float32)
+    with rlfc.AFCCylinderBatch(2, init_state=None, resolution=resolution, x_lengths=xl, y_lengths=yl) as env:
+        assert (env.n, env.m) == (ref.n, ref.m)
+        for k in range(4):
+            f = env.update2(act if k == 0 else None)
+            ref.update2()
+            assert_same(f[0], np.array(ref.force(), np.float32), f"force step {k}")
+            assert tuple(env.mg_iters()[0]) == ref.mg_iters()
+        for nm, a, b in zip(("ux", "uy", "p"), env.get_fields(0), ref.get_state()):
+            assert_same(a, b, nm)
+
+
+@pytest.mark.parametrize("envvar,value", [("RLFC_SMOOTHER", "strip"), ("RLFC_FUSE_PSUM", "1"), ("RLFC_NO_GRAPH", "1"),
+                                          ("RLFC_GROUPS", "3")])
+def test_alternative_execution_paths(rlfc, oracle, init_state, monkeypatch, envvar, value):
+    """The strip smoother, the smoother-fused Field.sum, eager launches and odd env-group splits are different
+    schedules of the same arithmetic: all must reproduce the oracle bit for bit."""
+    monkeypatch.setenv(envvar, value)
+    ref = make_oracle(oracle, init_state)
+    ref.set_xi(-0.6, 0.9)
+    B = 7
+    act = np.zeros((B, 2), np.float32)
+    act[3] = (-0.6, 0.9)
+    with rlfc.AFCCylinderBatch(B) as env:
+        for k in range(3):
+            f = env.update2(act if k == 0 else None)
+            ref.update2()
+            assert_same(f[3], np.array(ref.force(), np.float32), f"force step {k}")
+        for nm, a, b in zip(("ux", "uy", "p"), env.get_fields(3), ref.get_state()):
+            assert_same(a, b, nm)
