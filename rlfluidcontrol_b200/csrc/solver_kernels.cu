@@ -531,6 +531,53 @@ k_mg_up0(const __grid_constant__ SolverParams q, float* __restrict__ r_all) {
   }
 }
 
+// level 0, up, one thread per COARSE cell (rows smoother path): the four children share the injected value
+// xc[I][J]; their outward neighbours take the adjacent coarse cell's value, or -- at the domain edge, where
+// d.setBC copies the adjacent interior value (MG.pde:139-152) -- the cell's own.  x += d on the children and on the
+// ghost cells they border, r -= A d written to the smoother's skewed array.
+__global__ void __launch_bounds__(256)
+k_mg_up0_blk(const __grid_constant__ SolverParams q, const float* __restrict__ r_all) {
+  const int e = blockIdx.z;
+  if (!q.sc.active[e]) return;
+  const DevLevel& L0 = q.lev[0];
+  const DevLevel& L1 = q.lev[1];
+  const int P = L0.P, n = L0.n, m = L0.m, CPc = L1.P;
+  const int nci = L1.n - 2, ncj = L1.m - 2;
+  const int J = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int I = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (I > nci || J > ncj) return;
+  const float* __restrict__ xc = L1.x + (size_t)e * L1.stride;
+  const size_t eo = (size_t)e * L0.stride;
+  float* __restrict__ x = L0.x + eo;
+  const float* __restrict__ r = r_all + eo;
+  float* __restrict__ rsk = q.rsk + (size_t)e * q.rsk_stride;
+  const float dc = xc[I * CPc + J];
+  const float dWc = (I > 1) ? xc[(I - 1) * CPc + J] : dc, dEc = (I < nci) ? xc[(I + 1) * CPc + J] : dc;
+  const float dSc = (J > 1) ? xc[I * CPc + J - 1] : dc, dNc = (J < ncj) ? xc[I * CPc + J + 1] : dc;
+  const int i0 = 2 * I - 1, j0 = 2 * J - 1;
+  const int C = L0.rt.C, CP = rows_CP(C);
+  float xo[2][2], ro[2][2];
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++) { xo[a][b] = x[IDX(i0 + a, j0 + b)]; ro[a][b] = r[IDX(i0 + a, j0 + b)]; }
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      const int i = i0 + a, j = j0 + b, k = IDX(i, j);
+      const float dW = a ? dc : dWc, dE = a ? dEc : dc, dS = b ? dc : dSc, dN = b ? dNc : dc;
+      const float Ad = dc * L0.diag[k] + dW * L0.lx[k] + dE * L0.lx[k + P] + dS * L0.ly[k] + dN * L0.ly[k + 1];
+      x[k] = xo[a][b] + dc;
+      const int ln = (j - 1) / C, c = (j - 1) - ln * C;
+      rsk[((size_t)(i + ln) * 32 + ln) * CP + c] = ro[a][b] - Ad;
+      const int di = (i == 1) ? -1 : (i == n - 2 ? 1 : 0), dj = (j == 1) ? -1 : (j == m - 2 ? 1 : 0);
+      if (di) x[IDX(i + di, j)] += dc;
+      if (dj) x[IDX(i, j + dj)] += dc;
+      if (di && dj) x[IDX(i + di, j + dj)] += dc;
+    }
+}
+
 // plain level-0 residual <- skewed residual (the row smoother leaves r - A d there); only environments that
 // go on to a further MG iteration need it
 __global__ void __launch_bounds__(256)
@@ -1007,7 +1054,7 @@ int launch_mg_coarse(const SolverParams& q, cudaStream_t st) {
 
 int launch_mg_up0(const SolverParams& q, float* r, cudaStream_t st) {
   dim3 blk(32, 8);
-  if (q.use_rows) k_mg_up0<true><<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, r);
+  if (q.use_rows) k_mg_up0_blk<<<grid2d(q.lev[1].m - 2, q.lev[1].n - 2, q.B, blk), blk, 0, st>>>(q, r);
   else k_mg_up0<false><<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, r);
   return 1;
 }
