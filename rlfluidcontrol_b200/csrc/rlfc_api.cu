@@ -613,6 +613,13 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
           by.push_back({i, j, g.del_y[k], g.del1_y[k], g.wnx_y[k], g.wny_y[k]});
       }
     sp.nband_x = (int)bx.size(); sp.nband_y = (int)by.size();
+    // the two-phase setBC kernel fetches rows 1, n-2 and columns 1, m-2 before the band is blended: no band face may
+    // sit on them, and one 1024-thread CTA must cover a row and a column
+    sp.fast_bc = (g.n <= 1024 && g.m <= 1024) ? 1 : 0;
+    for (const auto* v : {&bx, &by})
+      for (const BandFace& f : *v)
+        if (f.i <= 1 || f.i >= g.n - 2 || f.j <= 1 || f.j >= g.m - 2) sp.fast_bc = 0;
+    if (const char* ev = std::getenv("RLFC_FAST_BC")) sp.fast_bc = sp.fast_bc && std::atoi(ev) != 0;
     TRY(upload_vec(E, bx, &sp.band_x));
     TRY(upload_vec(E, by, &sp.band_y));
     TRY(E->dmalloc(&sp.band_tmp, (size_t)B * (bx.size() + by.size())));

@@ -259,6 +259,114 @@ k_bc(const __grid_constant__ SolverParams q, float* ux_all, float* uy_all) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// u.setBC (and optionally the BDIM band blend before it) with TWO global-memory phases per environment: every
+// operand Field.setBC reads (rows 1 and n-2, columns 1 and m-2 of both components) is fetched up front, the
+// statement sequence of Field.pde:209-234 is then replayed on shared-memory copies (same order, same corner
+// hand-offs, same serial outflow sum), and the ghost ring is written in one go.  Valid when no band face lies on
+// those four lines (checked on the host; the literal kernels above remain the fallback).
+// ------------------------------------------------------------------------------------------------
+struct BcLines {            // shared-memory image of one component's boundary lines
+  float *r0, *r1, *rn1;     // new rows 0, 1, n-1            [m]
+  float *c1, *cm2;          // columns 1 and m-2 as loaded    [n]
+};
+
+// rows: thread j < m holds a[1][j], a[n-2][j]; cols: thread i < n holds a[i][1], a[i][m-2]
+__device__ __forceinline__ void bc_stage(const BcLines& s, int tid, int n, int m, int btype, float bval, bool gexit, float row1,
+                                         float rown2, float col1, float colm2) {
+  if (tid < m) {
+    s.r0[tid] = row1;                                   // a[0][j] = a[1][j]
+    s.rn1[tid] = (btype == 1 && !gexit) ? bval : rown2; // a[n-1][j] = a[n-2][j]; btype 1 without gradientExit: = bval
+    s.r1[tid] = (btype == 1) ? bval : row1;             // btype 1: a[1][j] = bval
+  }
+  if (tid < n) { s.c1[tid] = col1; s.cm2[tid] = colm2; }
+}
+
+// final values after the column loop and the outflow correction; `mean` = s/(m-2) of the gradientExit sum
+__device__ __forceinline__ void bc_store(const BcLines& s, float* a, int tid, int n, int m, int P, int btype, float bval, bool gexit,
+                                         float mean) {
+  if (tid >= 1 && tid <= m - 2) {                       // rows 0, 1, n-1, interior columns
+    const int j = tid;
+    const bool b2 = btype == 2 && j == 1;               // btype 2: a[i][1] = bval on every row
+    a[IDX(0, j)] = b2 ? bval : s.r0[j];
+    if (btype == 1 || b2) a[IDX(1, j)] = b2 ? bval : s.r1[j];
+    float v = s.rn1[j];
+    if (gexit) v += bval - mean;                        // a[n-1][j] += bval - s for interior j
+    a[IDX(n - 1, j)] = b2 ? bval : v;
+  }
+  if (tid < n) {                                        // columns 0, (1), m-1 on every row, corners included
+    const int i = tid;
+    const float src1 = (i == 0) ? s.r0[1] : (i == 1) ? s.r1[1] : (i == n - 1) ? s.rn1[1] : s.c1[i];
+    const float src2 = (i == 0) ? s.r0[m - 2] : (i == 1) ? s.r1[m - 2] : (i == n - 1) ? s.rn1[m - 2] : s.cm2[i];
+    a[IDX(i, 0)] = src1;                                // a[i][0] = a[i][1]
+    a[IDX(i, m - 1)] = (btype == 2) ? bval : src2;      // a[i][m-1] = a[i][m-2]; btype 2: = bval
+    if (btype == 2) a[IDX(i, 1)] = bval;
+  }
+}
+
+template <bool BAND>
+__global__ void __launch_bounds__(1024)
+k_bc2(const __grid_constant__ SolverParams q, float* ux_all, float* uy_all) {
+  extern __shared__ float bc_smem[];
+  const int e = blockIdx.x, P = q.P, n = q.n, m = q.m, tid = threadIdx.x;
+  float* ux = ux_all + (size_t)e * q.stride;
+  float* uy = uy_all + (size_t)e * q.stride;
+  BcLines sx, sy;
+  float* w = bc_smem;
+  sx.r0 = w; sx.r1 = w + m; sx.rn1 = w + 2 * m; sx.c1 = w + 3 * m; sx.cm2 = w + 3 * m + n;
+  w += 3 * m + 2 * n;
+  sy.r0 = w; sy.r1 = w + m; sy.rn1 = w + 2 * m; sy.c1 = w + 3 * m; sy.cm2 = w + 3 * m + n;
+  w += 3 * m + 2 * n;
+  float* tmp = w;                                        // [nband_x + nband_y] blended band values
+  __shared__ float s_mean;
+  // ---- phase 1: every load ----
+  float xr1 = 0, xrn2 = 0, xc1 = 0, xcm2 = 0, yr1 = 0, yrn2 = 0, yc1 = 0, ycm2 = 0;
+  if (tid < m) { xr1 = ux[IDX(1, tid)]; xrn2 = ux[IDX(n - 2, tid)]; yr1 = uy[IDX(1, tid)]; yrn2 = uy[IDX(n - 2, tid)]; }
+  if (tid < n) { xc1 = ux[IDX(tid, 1)]; xcm2 = ux[IDX(tid, m - 2)]; yc1 = uy[IDX(tid, 1)]; ycm2 = uy[IDX(tid, m - 2)]; }
+  if (BAND) {
+    // BDIM.updateUP blend on the body band (BDIM.pde:109-122), identical arithmetic to k_band_bc
+    const float xi1_m = q.action_scale * q.sc.xi[2 * e], xi2_m = q.action_scale * q.sc.xi[2 * e + 1];
+    const float dphi1 = (2 * xi1_m * q.dt) / q.dRD, dphi2 = (2 * xi2_m * q.dt) / q.dRD;
+    for (int b = tid; b < q.nband_x; b += blockDim.x) {
+      const BandFace f = q.band_x[b];
+      const int k = IDX(f.i, f.j);
+      float R = ux[k], ub = ub_x(q, k, dphi1, dphi2);
+      float v = f.del * R - ub * (f.del + (-1.f));
+      float duE = ux[k + P] - ub_x(q, k + P, dphi1, dphi2), duW = ux[k - P] - ub_x(q, k - P, dphi1, dphi2);
+      float duN = ux[k + 1] - ub_x(q, k + 1, dphi1, dphi2), duS = ux[k - 1] - ub_x(q, k - 1, dphi1, dphi2);
+      float g = 0.5f * (f.wnx * (duE - duW) + f.wny * (duN - duS));       // VectorField.pde:50
+      tmp[b] = v + f.del1 * g;
+    }
+    for (int b = tid; b < q.nband_y; b += blockDim.x) {
+      const BandFace f = q.band_y[b];
+      const int k = IDX(f.i, f.j);
+      float R = uy[k], ub = ub_y(q, k, dphi1, dphi2);
+      float v = f.del * R - ub * (f.del + (-1.f));
+      float duE = uy[k + P] - ub_y(q, k + P, dphi1, dphi2), duW = uy[k - P] - ub_y(q, k - P, dphi1, dphi2);
+      float duN = uy[k + 1] - ub_y(q, k + 1, dphi1, dphi2), duS = uy[k - 1] - ub_y(q, k - 1, dphi1, dphi2);
+      float g = 0.5f * (f.wnx * (duE - duW) + f.wny * (duN - duS));       // VectorField.pde:51
+      tmp[q.nband_x + b] = v + f.del1 * g;
+    }
+  }
+  // u.x: btype 1, bval 1, gradientExit (BDIM.pde:52); u.y: btype 2, bval 0
+  bc_stage(sx, tid, n, m, 1, 1.f, true, xr1, xrn2, xc1, xcm2);
+  bc_stage(sy, tid, n, m, 2, 0.f, false, yr1, yrn2, yc1, ycm2);
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0;
+    for (int j = 1; j < m - 1; j++) s += sx.rn1[j];      // serial float sum in j order (Field.pde:216-217)
+    s_mean = s / (float)(m - 2);
+  }
+  // ---- phase 2: every store ----
+  if (BAND) {
+    for (int b = tid; b < q.nband_x; b += blockDim.x) ux[IDX(q.band_x[b].i, q.band_x[b].j)] = tmp[b];
+    for (int b = tid; b < q.nband_y; b += blockDim.x) uy[IDX(q.band_y[b].i, q.band_y[b].j)] = tmp[q.nband_x + b];
+  }
+  __syncthreads();
+  bc_store(sx, ux, tid, n, m, P, 1, 1.f, true, s_mean);
+  bc_store(sy, uy, tid, n, m, P, 2, 0.f, false, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
 // residual r = div(u) - A p   (VectorField.pde:56-65, PoissonMatrix.pde:53-68); also opens the solve
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float apply_A(const float* x, const float* __restrict__ lx, const float* __restrict__ ly,
@@ -959,13 +1067,17 @@ int launch_advdif(const SolverParams& q, const float* srcx, const float* srcy, c
   return 1;
 }
 
+static size_t bc2_smem(const SolverParams& q) { return sizeof(float) * (2 * (3 * q.m + 2 * q.n) + q.nband_x + q.nband_y); }
+
 int launch_band_bc(const SolverParams& q, float* ux, float* uy, cudaStream_t st) {
-  k_band_bc<<<q.B, 1024, sizeof(float) * q.m, st>>>(q, ux, uy);
+  if (q.fast_bc) k_bc2<true><<<q.B, 1024, bc2_smem(q), st>>>(q, ux, uy);
+  else k_band_bc<<<q.B, 1024, sizeof(float) * q.m, st>>>(q, ux, uy);
   return 1;
 }
 
 int launch_bc(const SolverParams& q, float* ux, float* uy, cudaStream_t st) {
-  k_bc<<<q.B, 512, sizeof(float) * q.m, st>>>(q, ux, uy);
+  if (q.fast_bc) k_bc2<false><<<q.B, 1024, bc2_smem(q), st>>>(q, ux, uy);
+  else k_bc<<<q.B, 512, sizeof(float) * q.m, st>>>(q, ux, uy);
   return 1;
 }
 
@@ -1027,6 +1139,11 @@ static cudaError_t set_smooth0_rows_attr(const SolverParams& q) {
 int configure_kernels(const SolverParams& q) {
   cudaError_t e1 = cudaFuncSetAttribute(k_mg_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)strip_smem(q.coarse_strips));
   cudaError_t e2 = cudaFuncSetAttribute(k_smooth0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smooth0_smem(q));
+  if (q.fast_bc) {
+    if (cudaFuncSetAttribute(k_bc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc2_smem(q)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_bc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc2_smem(q)) != cudaSuccess)
+      return -1;
+  }
   cudaError_t e3 = cudaFuncSetAttribute(k_mg_coarse_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coarse_rows_smem(q));
   cudaError_t e4 = cudaSuccess;
   switch (q.lev[0].rt.C) {
