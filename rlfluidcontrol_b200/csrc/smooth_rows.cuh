@@ -63,7 +63,7 @@ __host__ __device__ inline int rows_table_entries(int ni, int nl) { return kTabF
 // stage buffers | mbarriers]; `skewed_r` = level-0 mode, where r arrives pre-skewed and needs no row ring
 __host__ __device__ inline size_t rows_smem_bytes(int C, int P, bool skewed_r) {
   return (size_t)kCoefSlots * rows_K(C) * 32 * 16 + (skewed_r ? 1 : 2) * (size_t)kRowRing * P * 4 +
-         (size_t)(kRSlots * 32 + 5 * 2 * kSLanes) * rows_CP(C) * 4 + 16 + kCoefSlots * 8;
+         (size_t)(kRSlots * 32 + 5 * 2 * kSLanes) * rows_CP(C) * 4 + 16 + kCoefSlots * 8 + (skewed_r ? 16 + 2 * (size_t)P * 4 : 0);
 }
 // skewed residual array of one environment (level 0): entry tau = i + l holds row i of lane l's columns,
 // [tau][32][CP] floats; entries the smoother touches: 1 .. ni + nl + kStageLag + kPF + 2
@@ -199,7 +199,10 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
   // loader (one lane of warp 5): row q of r (and x) and table entry q as bulk copies completing on bars[(q-1) & 15]
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(
       (reinterpret_cast<uintptr_t>(S + (size_t)5 * 2 * kSLanes * CP) + 15) & ~(uintptr_t)15);
+  volatile int* progress = reinterpret_cast<volatile int*>(bars + kCoefSlots);   // rows of the new x written out so far
+  float* sumbuf = reinterpret_cast<float*>(bars + kCoefSlots + 2);                // [2][P] row staging of the sum warp
   if (threadIdx.x == 0) {
+    *progress = 0;
     for (int k = 0; k < kCoefSlots; k++) mbar_init(bars + k, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -226,13 +229,14 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
   }
   __syncthreads();
 
-#ifdef RLFC_ROLE_TIMING
-  long long wait_cycles = 0;
-  const long long role_t0 = clock64();
-#define RLFC_STEP_SYNC() do { long long a_ = clock64(); __syncthreads(); wait_cycles += clock64() - a_; } while (0)
-#else
-#define RLFC_STEP_SYNC() __syncthreads()
-#endif
+  // per-step barrier of the pipeline warps.  With the fused Field.sum (level 0) warp 7 runs DECOUPLED from the pipeline
+  // (it only follows the write-out's progress counter), so warps 0..6 synchronise on named barrier 1 by themselves.
+  const bool decoupled = (XMODE == 3) && psum_out != nullptr;
+#define RLFC_STEP_SYNC()                                                               \
+  do {                                                                                 \
+    if (decoupled) asm volatile("bar.sync 1, %0;" ::"n"(kRowsThreads - 32) : "memory"); \
+    else __syncthreads();                                                              \
+  } while (0)
   double rr = 0.0;
   if (warp < 4) {
     // ------------------------------------------------------------------ sweep g = warp + 1, row t - L - 2g
@@ -426,6 +430,11 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
 #pragma unroll
           for (int c = 0; c < C; c++)
             if (1 + lane + 32 * c <= mj) xg[32 * c] = xo[c];
+          if (decoupled) {                           // row w of the new x is in global memory: let the sum warp have it
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) *progress = w;
+          }
         }
       }
       i6++;
@@ -434,45 +443,52 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
     }
   } else {
     // ------------------------------------------------------------------ Field.sum of the new x (level 0 only)
-    // Field.pde:311-318: a serial float accumulation over the interior in i-major order.  Row w is complete in the
-    // ring after step w + lag - 1; one lane-uniform chain of mj dependent adds per step, so the sum is finished together
-    // with the smoother instead of costing a kernel of its own (only worth it when that chain is not the slowest stage).
+    // Field.pde:311-318: a serial float accumulation over the interior in i-major order: one lane-uniform chain of
+    // dependent adds, pure latency.  It starts as soon as the first rows are written out and ends about one chain
+    // length after the smoother began, instead of costing a kernel of its own after it.
     float s = 0.f;
-    for (int t = 1; t <= t_end; t++) {
-      const int w = t - lag;
-      if (XMODE == 3 && psum_out && w >= 1 && w <= ni) {
-        const float4* xs4 = reinterpret_cast<const float4*>(xring + (size_t)ring_mod(w) * P);   // columns 0..3, 4..7, ...
-        // the chain runs over columns 1 .. mj (column 0 is the ghost); the row is fetched kSumB vectors at a time, one
-        // batch ahead of the adds
-        constexpr int kSumB = 8;
-        const int nv = (mj + 4) / 4;                 // vectors that hold columns 0 .. mj
-        float4 cur[kSumB], nxt[kSumB];
+    if (decoupled) {
+      // rows are taken from global memory (L2) as soon as the write-out has published them; this lane's vectors of the
+      // next row are requested before the current row's chain starts
+      const int nv = (mj + 4) / 4;                   // vectors that hold columns 0 .. mj
+      auto load_row = [&](int w, float4 (&v)[2]) {
 #pragma unroll
-        for (int u = 0; u < kSumB; u++) cur[u] = (u < nv) ? xs4[u] : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int b = 0; b < nv; b += kSumB) {
-#pragma unroll
-          for (int u = 0; u < kSumB; u++) nxt[u] = (b + kSumB + u < nv) ? xs4[b + kSumB + u] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int u = 0; u < kSumB; u++) {
-            const int j = 4 * (b + u);               // column of cur[u].x
-            if (j >= 1 && j <= mj) s += cur[u].x;
-            if (j + 1 <= mj) s += cur[u].y;
-            if (j + 2 <= mj) s += cur[u].z;
-            if (j + 3 <= mj) s += cur[u].w;
-          }
-#pragma unroll
-          for (int u = 0; u < kSumB; u++) cur[u] = nxt[u];
+        for (int u = 0; u < 2; u++) {
+          const int vi = lane + 32 * u, j = 4 * vi;
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (vi < nv) t = __ldcg(reinterpret_cast<const float4*>(x + (size_t)w * P) + vi);
+          if (j < 1 || j > mj) t.x = 0.f;            // ghost column / beyond the interior: s + 0.f == s
+          if (j + 1 > mj) t.y = 0.f;
+          if (j + 2 > mj) t.z = 0.f;
+          if (j + 3 > mj) t.w = 0.f;
+          v[u] = t;
         }
+      };
+      auto wait_row = [&](int w) { while (*progress < w) __nanosleep(64); };
+      float4 cur[2], nxt[2];
+      wait_row(1);
+      load_row(1, cur);
+      for (int w = 1; w <= ni; w++) {
+        float4* st = reinterpret_cast<float4*>(sumbuf + (size_t)(w & 1) * P);
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+          if (lane + 32 * u < nv) st[lane + 32 * u] = cur[u];
+        __syncwarp();
+        if (w < ni) { wait_row(w + 1); load_row(w + 1, nxt); }
+        for (int b = 0; b < nv; b += 8) {
+          float4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) v[u] = (b + u < nv) ? st[b + u] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < 8; u++) { s += v[u].x; s += v[u].y; s += v[u].z; s += v[u].w; }
+        }
+        cur[0] = nxt[0]; cur[1] = nxt[1];
       }
-      RLFC_STEP_SYNC();
+    } else {
+      for (int t = 1; t <= t_end; t++) __syncthreads();
     }
     if (XMODE == 3 && lane == 0 && psum_out) *psum_out = s;
   }
-#ifdef RLFC_ROLE_TIMING
-  if (blockIdx.x == 0 && lane == 0 && XMODE == 3)
-    printf("role warp %d: total %lld cycles, barrier wait %lld (%.1f%%), steps %d\n", warp, clock64() - role_t0, wait_cycles,
-           100.0 * wait_cycles / (double)(clock64() - role_t0), t_end);
-#endif
 #undef RLFC_STEP_SYNC
   __syncthreads();
   if (threadIdx.x == 0)
