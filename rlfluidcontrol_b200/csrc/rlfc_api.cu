@@ -228,6 +228,12 @@ int project_eager(rlfc_env* E, Group& G, float* Ux, float* Uy, int which) {
     if (!*E->h_any) break;
   }
   if (!sp.fuse_psum) E->run("k_psum", 1, [&] { return launch_psum(sb, st); }, st, gi);
+  if (E->fused && which == 1 && sp.fast_bc) {
+    // corrector: Heun average fused into the projection and the boundary-condition kernels (BDIM.pde:95-96)
+    E->run("k_project_shift_heun", 8, [&] { return launch_project_shift_heun(sp, pB, pA, Ux, Uy, G.uBx, G.uBy, G.uAx, G.uAy, st); }, st, gi);
+    E->run("k_bc_heun", 0, [&] { return launch_bc_heun(sp, Ux, Uy, G.uBx, G.uBy, G.uAx, G.uAy, st); }, st, gi);
+    return RLFC_OK;
+  }
   if (E->fused) {
     E->run("k_project_shift", 6, [&] { return launch_project_shift(sp, pB, pA, Ux, Uy, st); }, st, gi);
   } else {
@@ -252,7 +258,8 @@ int solver_step_eager(rlfc_env* E, Group& G, int accumulate) {
   E->run("k_advdif", 5, [&] { return launch_advdif(sp, G.uBx, G.uBy, G.uAx, G.uAy, G.uCx, G.uCy, st); }, st, gi);
   E->run("k_band_bc", 0, [&] { return launch_band_bc(sp, G.uCx, G.uCy, st); }, st, gi);
   if ((rc = project_eager(E, G, G.uCx, G.uCy, 1))) return rc;
-  E->run("k_heun", 6, [&] { return launch_heun(sp, G.uCx, G.uCy, G.uBx, G.uBy, G.uAx, G.uAy, st); }, st, gi);
+  if (!(E->fused && sp.fast_bc))
+    E->run("k_heun", 6, [&] { return launch_heun(sp, G.uCx, G.uCy, G.uBx, G.uBy, G.uAx, G.uAy, st); }, st, gi);
   E->run("k_force", 0, [&] { return launch_force(sp, accumulate, st); }, st, gi);
   CU(cudaGetLastError());
   return RLFC_OK;
@@ -315,8 +322,13 @@ int capture_half_step(rlfc_env* E, Group& G, cudaStream_t st, const float* sx, c
   }
   // ---- projection tail ----
   if (!sp.fuse_psum) *n_outer += launch_psum(sb, st);
-  *n_outer += launch_project_shift(sp, pB, pA, dx, dy, st);
-  *n_outer += launch_bc(sp, dx, dy, st);
+  if (which == 1 && sp.fast_bc) {   // corrector: Heun average fused in (BDIM.pde:95-96); sx, sy = us, u0x, u0y = step-start buffer
+    *n_outer += launch_project_shift_heun(sp, pB, pA, dx, dy, sx, sy, const_cast<float*>(u0x), const_cast<float*>(u0y), st);
+    *n_outer += launch_bc_heun(sp, dx, dy, sx, sy, const_cast<float*>(u0x), const_cast<float*>(u0y), st);
+  } else {
+    *n_outer += launch_project_shift(sp, pB, pA, dx, dy, st);
+    *n_outer += launch_bc(sp, dx, dy, st);
+  }
   return RLFC_OK;
 }
 
@@ -327,7 +339,7 @@ int build_step_graph(rlfc_env* E, Group& G, int accumulate) {
   int rc = capture_half_step(E, G, st, G.uAx, G.uAy, G.uAx, G.uAy, G.uBx, G.uBy, 0, &n_outer, &n_body);
   if (!rc) rc = capture_half_step(E, G, st, G.uBx, G.uBy, G.uAx, G.uAy, G.uCx, G.uCy, 1, &n_outer, &n_body);
   if (!rc) {
-    n_outer += launch_heun(G.sp, G.uCx, G.uCy, G.uBx, G.uBy, G.uAx, G.uAy, st);
+    if (!G.sp.fast_bc) n_outer += launch_heun(G.sp, G.uCx, G.uCy, G.uBx, G.uBy, G.uAx, G.uAy, st);
     n_outer += launch_force(G.sp, accumulate, st);
   }
   cudaGraph_t graph = nullptr;

@@ -113,6 +113,12 @@ int launch_resid_down0(const SolverParams& P, const float* ux, const float* uy, 
                        int which, cudaStream_t st);
 // projection tail fused: p_out = p_in + shift (different buffers), u -= c * grad(p_in + shift)
 int launch_project_shift(const SolverParams& P, const float* p_in, float* p_out, float* ux, float* uy, cudaStream_t st);
+// corrector (P.fast_bc only): projection + Heun average u_out = (u + us)/2 away from the boundary lines, then u.setBC and
+// the Heun average on the remaining zone
+int launch_project_shift_heun(const SolverParams& P, const float* p_in, float* p_out, float* ux, float* uy, const float* usx,
+                              const float* usy, float* uox, float* uoy, cudaStream_t st);
+int launch_bc_heun(const SolverParams& P, float* ux, float* uy, const float* usx, const float* usy, float* uox, float* uoy,
+                   cudaStream_t st);
 // one MG iteration (V-cycle + smooth(4)) on active envs = down0, coarse, up0, smooth0;
 // r_in/r_out are the level-0 ping-pong residual buffers
 int launch_mg_down0(const SolverParams& P, const float* r_in, float* r_out, cudaStream_t st);

@@ -303,9 +303,10 @@ __device__ __forceinline__ void bc_store(const BcLines& s, float* a, int tid, in
   }
 }
 
-template <bool BAND>
+template <bool BAND, bool HEUN>
 __global__ void __launch_bounds__(1024)
-k_bc2(const __grid_constant__ SolverParams q, float* ux_all, float* uy_all) {
+k_bc2(const __grid_constant__ SolverParams q, float* ux_all, float* uy_all, const float* usx_all, const float* usy_all,
+      float* uox_all, float* uoy_all) {
   extern __shared__ float bc_smem[];
   const int e = blockIdx.x, P = q.P, n = q.n, m = q.m, tid = threadIdx.x;
   float* ux = ux_all + (size_t)e * q.stride;
@@ -364,6 +365,30 @@ k_bc2(const __grid_constant__ SolverParams q, float* ux_all, float* uy_all) {
   __syncthreads();
   bc_store(sx, ux, tid, n, m, P, 1, 1.f, true, s_mean);
   bc_store(sy, uy, tid, n, m, P, 2, 0.f, false, 0.f);
+  if (HEUN) {
+    // u = (u + us) * 0.5 on the zone k_project_shift<true> left to us (rows 0, 1, n-2, n-1; the first float4 of every
+    // row; the float4s from the one holding column m-2 on): the values the boundary conditions just produced
+    __syncthreads();
+    const float* usx = usx_all + (size_t)e * q.stride;
+    const float* usy = usy_all + (size_t)e * q.stride;
+    float* uox = uox_all + (size_t)e * q.stride;
+    float* uoy = uoy_all + (size_t)e * q.stride;
+    const int jz = 4 * ((m - 2) / 4), wz = 4 + (P - jz);      // zone columns of an interior row: [0, 4) and [jz, P)
+    for (int t = tid; t < 4 * P; t += blockDim.x) {           // the four full rows
+      const int r = t / P, j = t - r * P;
+      const int i = (r < 2) ? r : n - 4 + r;
+      const int k = IDX(i, j);
+      uox[k] = (ux[k] + usx[k]) * 0.5f;
+      uoy[k] = (uy[k] + usy[k]) * 0.5f;
+    }
+    for (int t = tid; t < (n - 4) * wz; t += blockDim.x) {    // the column strips of rows 2 .. n-3
+      const int r = t / wz, c = t - r * wz;
+      const int i = 2 + r, j = (c < 4) ? c : jz + (c - 4);
+      const int k = IDX(i, j);
+      uox[k] = (ux[k] + usx[k]) * 0.5f;
+      uoy[k] = (uy[k] + usy[k]) * 0.5f;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -914,9 +939,18 @@ k_shift_p(const __grid_constant__ SolverParams q) {
 // projection tail fused (VectorField.pde:136-139): p_out = p_in + shift on all cells (p ping-pongs B -> A, so no
 // thread reads a value another thread has already shifted), u += c * (grad(p_in + shift) * -1) on the interior.
 // One thread handles four consecutive columns (aligned float4 accesses; the pitch is a multiple of 8 floats).
+// HEUN (corrector, BDIM.pde:95-96): away from the lines u.setBC touches the projected velocity goes straight into
+// the Heun average  u = (u + us) * 0.5  written to the step-start buffer; inside that zone (heun_zone) the projected
+// value is stored as before and k_bc2<.., true> averages after the boundary conditions.
+__device__ __forceinline__ bool heun_zone(int i, int j4, int n, int m) {           // j4 = first column of a float4
+  return i < 2 || i > n - 3 || j4 < 4 || j4 >= 4 * ((m - 2) / 4);
+}
+
+template <bool HEUN>
 __global__ void __launch_bounds__(256)
 k_project_shift(const __grid_constant__ SolverParams q, const float* __restrict__ pin_all, float* __restrict__ pout_all,
-                float* __restrict__ ux_all, float* __restrict__ uy_all) {
+                float* __restrict__ ux_all, float* __restrict__ uy_all, const float* __restrict__ usx_all,
+                const float* __restrict__ usy_all, float* __restrict__ uox_all, float* __restrict__ uoy_all) {
   const int P = q.P, n = q.n, m = q.m, nv = P >> 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int e = blockIdx.y;
@@ -928,34 +962,46 @@ k_project_shift(const __grid_constant__ SolverParams q, const float* __restrict_
   const float4 pv = *reinterpret_cast<const float4*>(pin_all + eo + k);
   const float pc[4] = {pv.x + shift, pv.y + shift, pv.z + shift, pv.w + shift};
   *reinterpret_cast<float4*>(pout_all + eo + k) = make_float4(pc[0], pc[1], pc[2], pc[3]);
-  if (i < 1 || i > n - 2 || j4 > m - 2) return;
+  const bool zone = !HEUN || heun_zone(i, j4, n, m);
+  if ((i < 1 || i > n - 2 || j4 > m - 2) && zone) return;    // nothing to project here; zone cells are averaged later
   float4 uxv = *reinterpret_cast<const float4*>(ux_all + eo + k);
   float4 uyv = *reinterpret_cast<const float4*>(uy_all + eo + k);
-  const float4 cxv = *reinterpret_cast<const float4*>(q.c_x + k);
-  const float4 cyv = *reinterpret_cast<const float4*>(q.c_y + k);
   float uxa[4] = {uxv.x, uxv.y, uxv.z, uxv.w}, uya[4] = {uyv.x, uyv.y, uyv.z, uyv.w};
-  const float cxa[4] = {cxv.x, cxv.y, cxv.z, cxv.w}, cya[4] = {cyv.x, cyv.y, cyv.z, cyv.w};
-  float pw[4] = {0.f, 0.f, 0.f, 0.f};
-  if (i >= 2) {
-    const float4 w = *reinterpret_cast<const float4*>(pin_all + eo + k - P);
-    pw[0] = w.x + shift; pw[1] = w.y + shift; pw[2] = w.z + shift; pw[3] = w.w + shift;
-  }
-  const float psm = (j4 >= 1) ? pin_all[eo + k - 1] + shift : 0.f;       // column j4 - 1
-#pragma unroll
-  for (int c = 0; c < 4; c++) {
-    const int j = j4 + c;
-    if (j < 1 || j > m - 2) continue;
+  if (i >= 1 && i <= n - 2 && j4 <= m - 2) {
+    const float4 cxv = *reinterpret_cast<const float4*>(q.c_x + k);
+    const float4 cyv = *reinterpret_cast<const float4*>(q.c_y + k);
+    const float cxa[4] = {cxv.x, cxv.y, cxv.z, cxv.w}, cya[4] = {cyv.x, cyv.y, cyv.z, cyv.w};
+    float pw[4] = {0.f, 0.f, 0.f, 0.f};
     if (i >= 2) {
-      const float dpx = pc[c] - pw[c];
-      uxa[c] += cxa[c] * (dpx * -1);
+      const float4 w = *reinterpret_cast<const float4*>(pin_all + eo + k - P);
+      pw[0] = w.x + shift; pw[1] = w.y + shift; pw[2] = w.z + shift; pw[3] = w.w + shift;
     }
-    if (j >= 2) {
-      const float dpy = pc[c] - (c == 0 ? psm : pc[c == 0 ? 0 : c - 1]);
-      uya[c] += cya[c] * (dpy * -1);
+    const float psm = (j4 >= 1) ? pin_all[eo + k - 1] + shift : 0.f;       // column j4 - 1
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int j = j4 + c;
+      if (j < 1 || j > m - 2) continue;
+      if (i >= 2) {
+        const float dpx = pc[c] - pw[c];
+        uxa[c] += cxa[c] * (dpx * -1);
+      }
+      if (j >= 2) {
+        const float dpy = pc[c] - (c == 0 ? psm : pc[c == 0 ? 0 : c - 1]);
+        uya[c] += cya[c] * (dpy * -1);
+      }
     }
   }
-  *reinterpret_cast<float4*>(ux_all + eo + k) = make_float4(uxa[0], uxa[1], uxa[2], uxa[3]);
-  *reinterpret_cast<float4*>(uy_all + eo + k) = make_float4(uya[0], uya[1], uya[2], uya[3]);
+  if (zone) {
+    *reinterpret_cast<float4*>(ux_all + eo + k) = make_float4(uxa[0], uxa[1], uxa[2], uxa[3]);
+    *reinterpret_cast<float4*>(uy_all + eo + k) = make_float4(uya[0], uya[1], uya[2], uya[3]);
+  } else {                                                  // u = (u + us) * 0.5
+    const float4 sx = *reinterpret_cast<const float4*>(usx_all + eo + k);
+    const float4 sy = *reinterpret_cast<const float4*>(usy_all + eo + k);
+    *reinterpret_cast<float4*>(uox_all + eo + k) =
+        make_float4((uxa[0] + sx.x) * 0.5f, (uxa[1] + sx.y) * 0.5f, (uxa[2] + sx.z) * 0.5f, (uxa[3] + sx.w) * 0.5f);
+    *reinterpret_cast<float4*>(uoy_all + eo + k) =
+        make_float4((uya[0] + sy.x) * 0.5f, (uya[1] + sy.y) * 0.5f, (uya[2] + sy.z) * 0.5f, (uya[3] + sy.w) * 0.5f);
+  }
 }
 
 // BDIM.update2: u.plusEq(us); u.timesEq(0.5) over all cells (BDIM.pde:95-96)
@@ -1070,13 +1116,13 @@ int launch_advdif(const SolverParams& q, const float* srcx, const float* srcy, c
 static size_t bc2_smem(const SolverParams& q) { return sizeof(float) * (2 * (3 * q.m + 2 * q.n) + q.nband_x + q.nband_y); }
 
 int launch_band_bc(const SolverParams& q, float* ux, float* uy, cudaStream_t st) {
-  if (q.fast_bc) k_bc2<true><<<q.B, 1024, bc2_smem(q), st>>>(q, ux, uy);
+  if (q.fast_bc) k_bc2<true, false><<<q.B, 1024, bc2_smem(q), st>>>(q, ux, uy, nullptr, nullptr, nullptr, nullptr);
   else k_band_bc<<<q.B, 1024, sizeof(float) * q.m, st>>>(q, ux, uy);
   return 1;
 }
 
 int launch_bc(const SolverParams& q, float* ux, float* uy, cudaStream_t st) {
-  if (q.fast_bc) k_bc2<false><<<q.B, 1024, bc2_smem(q), st>>>(q, ux, uy);
+  if (q.fast_bc) k_bc2<false, false><<<q.B, 1024, bc2_smem(q), st>>>(q, ux, uy, nullptr, nullptr, nullptr, nullptr);
   else k_bc<<<q.B, 512, sizeof(float) * q.m, st>>>(q, ux, uy);
   return 1;
 }
@@ -1099,7 +1145,21 @@ int launch_resid_down0(const SolverParams& q, const float* ux, const float* uy, 
 int launch_project_shift(const SolverParams& q, const float* p_in, float* p_out, float* ux, float* uy, cudaStream_t st) {
   const int items = q.n * (q.P >> 2);
   dim3 grid((items + 255) / 256, q.B);
-  k_project_shift<<<grid, 256, 0, st>>>(q, p_in, p_out, ux, uy);
+  k_project_shift<false><<<grid, 256, 0, st>>>(q, p_in, p_out, ux, uy, nullptr, nullptr, nullptr, nullptr);
+  return 1;
+}
+
+int launch_project_shift_heun(const SolverParams& q, const float* p_in, float* p_out, float* ux, float* uy, const float* usx,
+                              const float* usy, float* uox, float* uoy, cudaStream_t st) {
+  const int items = q.n * (q.P >> 2);
+  dim3 grid((items + 255) / 256, q.B);
+  k_project_shift<true><<<grid, 256, 0, st>>>(q, p_in, p_out, ux, uy, usx, usy, uox, uoy);
+  return 1;
+}
+
+int launch_bc_heun(const SolverParams& q, float* ux, float* uy, const float* usx, const float* usy, float* uox, float* uoy,
+                   cudaStream_t st) {
+  k_bc2<false, true><<<q.B, 1024, bc2_smem(q), st>>>(q, ux, uy, usx, usy, uox, uoy);
   return 1;
 }
 
@@ -1140,8 +1200,9 @@ int configure_kernels(const SolverParams& q) {
   cudaError_t e1 = cudaFuncSetAttribute(k_mg_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)strip_smem(q.coarse_strips));
   cudaError_t e2 = cudaFuncSetAttribute(k_smooth0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smooth0_smem(q));
   if (q.fast_bc) {
-    if (cudaFuncSetAttribute(k_bc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc2_smem(q)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_bc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc2_smem(q)) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_bc2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc2_smem(q)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_bc2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc2_smem(q)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_bc2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc2_smem(q)) != cudaSuccess)
       return -1;
   }
   cudaError_t e3 = cudaFuncSetAttribute(k_mg_coarse_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coarse_rows_smem(q));
