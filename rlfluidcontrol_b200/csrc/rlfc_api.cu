@@ -227,7 +227,7 @@ int project_eager(rlfc_env* E, Group& G, float* Ux, float* Uy, int which) {
     CU(cudaStreamSynchronize(st));
     if (!*E->h_any) break;
   }
-  if (!sp.fuse_psum) E->run("k_psum", 1, [&] { return launch_psum(sb, st); }, st, gi);
+  E->run("k_psum", 1, [&] { return launch_psum(sb, st); }, st, gi);
   if (E->fused && which == 1 && sp.fast_bc) {
     // corrector: Heun average fused into the projection and the boundary-condition kernels (BDIM.pde:95-96)
     E->run("k_project_shift_heun", 8, [&] { return launch_project_shift_heun(sp, pB, pA, Ux, Uy, G.uBx, G.uBy, G.uAx, G.uAy, st); }, st, gi);
@@ -321,7 +321,7 @@ int capture_half_step(rlfc_env* E, Group& G, cudaStream_t st, const float* sx, c
     }
   }
   // ---- projection tail ----
-  if (!sp.fuse_psum) *n_outer += launch_psum(sb, st);
+  *n_outer += launch_psum(sb, st);
   if (which == 1 && sp.fast_bc) {   // corrector: Heun average fused in (BDIM.pde:95-96); sx, sy = us, u0x, u0y = step-start buffer
     *n_outer += launch_project_shift_heun(sp, pB, pA, dx, dy, sx, sy, const_cast<float*>(u0x), const_cast<float*>(u0y), st);
     *n_outer += launch_bc_heun(sp, dx, dy, sx, sy, const_cast<float*>(u0x), const_cast<float*>(u0y), st);
@@ -516,10 +516,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   sp.inv_cells = (float)((g.n - 2) * (g.m - 2));
   sp.mg_tol = g.mg_tol;
   sp.use_rows = 1;
-  sp.fuse_psum = 0;   // measured on B200: the chain is faster in its own one-warp-per-env kernel (no SMSP sharing)
-  if (const char* ev = std::getenv("RLFC_FUSE_PSUM")) sp.fuse_psum = std::atoi(ev) != 0;
   if (const char* ev = std::getenv("RLFC_SMOOTHER")) sp.use_rows = std::string(ev) != "strip";
-  if (!sp.use_rows || (g.m - 2 + 4) / 4 > 64) sp.fuse_psum = 0;   // the sum warp holds two float4 per lane and row
   sp.nlevels = (int)g.levels.size();
   sp.resolution = cfg->resolution; sp.substeps = cfg->substeps; sp.mg_max_iters = cfg->mg_max_iters;
   sp.init_time = cfg->init_time; sp.episode_time = cfg->episode_time;

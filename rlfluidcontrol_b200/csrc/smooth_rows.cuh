@@ -12,9 +12,8 @@
 //     finds the previous sweep's values at (i+1,j), (i,j+1)), the increment stage (row t - L - 10) applies
 //     d.setBC, x += d and, on level 0, r -= A d;
 //   * every stage runs in its OWN warp, so a step costs one sweep of one row (C*9 flops per lane) instead
-//     of five:  warps 0..3 = sweeps 1..4,  warp 4 = residual increment + r.r (level 0),  warp 5 = stage 0 +
-//     bulk-copy loader,  warp 6 = x increment + coalesced write-out,  warp 7 = the serial Field.sum of
-//     the new x (level 0).  Stages hand rows to
+//     of five:  warps 0..3 = sweeps 1..4,  warp 4 = residual increment + r.r (level 0),  warp 5 = stage 0,
+//     warp 6 = x increment + coalesced write-out,  warp 7 = bulk-copy loader.  Stages hand rows to
 //     each other through small shared-memory buffers indexed by step ([lane][C] blocks, read and written
 //     with vector accesses), with one __syncthreads per step;
 //   * static coefficients come from a host-built, pre-skewed table: entry tau holds, for lane L, the
@@ -63,7 +62,7 @@ __host__ __device__ inline int rows_table_entries(int ni, int nl) { return kTabF
 // stage buffers | mbarriers]; `skewed_r` = level-0 mode, where r arrives pre-skewed and needs no row ring
 __host__ __device__ inline size_t rows_smem_bytes(int C, int P, bool skewed_r) {
   return (size_t)kCoefSlots * rows_K(C) * 32 * 16 + (skewed_r ? 1 : 2) * (size_t)kRowRing * P * 4 +
-         (size_t)(kRSlots * 32 + 5 * 2 * kSLanes) * rows_CP(C) * 4 + 16 + kCoefSlots * 8 + (skewed_r ? 16 + 2 * (size_t)P * 4 : 0);
+         (size_t)(kRSlots * 32 + 5 * 2 * kSLanes) * rows_CP(C) * 4 + 16 + kCoefSlots * 8;
 }
 // skewed residual array of one environment (level 0): entry tau = i + l holds row i of lane l's columns,
 // [tau][32][CP] floats; entries the smoother touches: 1 .. ni + nl + kStageLag + kPF + 2
@@ -171,7 +170,7 @@ __host__ __device__ constexpr int ring_mod(int row) { return ((row % kRowRing) +
 // arrays of the level.  Returns this thread's share of r.r (XMODE 3; non-zero only in the residual warp).
 template <int C, int XMODE>
 __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restrict__ r, float* __restrict__ x,
-                                              unsigned char* smem_raw, float* gbuf, float* psum_out = nullptr) {
+                                              unsigned char* smem_raw, float* gbuf) {
   using namespace rows_detail;
   constexpr int K = rows_K(C), CP = rows_CP(C);
   // float offsets inside a lane-entry
@@ -199,10 +198,7 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
   // loader (one lane of warp 5): row q of r (and x) and table entry q as bulk copies completing on bars[(q-1) & 15]
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(
       (reinterpret_cast<uintptr_t>(S + (size_t)5 * 2 * kSLanes * CP) + 15) & ~(uintptr_t)15);
-  volatile int* progress = reinterpret_cast<volatile int*>(bars + kCoefSlots);   // rows of the new x written out so far
-  float* sumbuf = reinterpret_cast<float*>(bars + kCoefSlots + 2);                // [2][P] row staging of the sum warp
   if (threadIdx.x == 0) {
-    *progress = 0;
     for (int k = 0; k < kCoefSlots; k++) mbar_init(bars + k, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -220,7 +216,7 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
     if (SKEW) bulk_g2s(R + (size_t)(q & (kRSlots - 1)) * 32 * CP, r + (size_t)q * 32 * CP, rsk_bytes, bar);
     bulk_g2s(coef + (size_t)(q & (kCoefSlots - 1)) * ES, tab + (size_t)(q + kTabFront) * ES, ent_bytes, bar);
   };
-  if (warp == 5) {
+  if (warp == 7) {
     if (lane == 0) {
       fence_proxy_async();
       for (int q = 1; q <= kPF; q++) issue(q);
@@ -229,14 +225,7 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
   }
   __syncthreads();
 
-  // per-step barrier of the pipeline warps.  With the fused Field.sum (level 0) warp 7 runs DECOUPLED from the pipeline
-  // (it only follows the write-out's progress counter), so warps 0..6 synchronise on named barrier 1 by themselves.
-  const bool decoupled = (XMODE == 3) && psum_out != nullptr;
-#define RLFC_STEP_SYNC()                                                               \
-  do {                                                                                 \
-    if (decoupled) asm volatile("bar.sync 1, %0;" ::"n"(kRowsThreads - 32) : "memory"); \
-    else __syncthreads();                                                              \
-  } while (0)
+#define RLFC_STEP_SYNC() __syncthreads()
   double rr = 0.0;
   if (warp < 4) {
     // ------------------------------------------------------------------ sweep g = warp + 1, row t - L - 2g
@@ -368,17 +357,10 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
       for (int c = 0; c < C; c++) d0[c] = rv[c] * (-ninv[c]);   // MG.pde:80
       st_block<C>(Sout + par * kSLanes * CP, d0);
       }
-      if (lane == 0) {
-        fence_proxy_async();
-        issue(t + kPF);
-      }
-      mbar_wait(bars + (t & (kCoefSlots - 1)), ((unsigned)t >> kCoefShift) & 1u);   // entry / row t + 1 has landed
       i0++;
       slot0 = ring_inc(slot0);
       RLFC_STEP_SYNC();
     }
-    // drain: every issued copy must have landed before the shared memory is reused
-    for (int q = t_end + 2; q <= t_end + kPF; q++) mbar_wait(bars + ((q - 1) & (kCoefSlots - 1)), ((unsigned)(q - 1) >> kCoefShift) & 1u);
   } else if (warp == 6) {
     // ------------------------------------------------------------------ x increment: row t - L - 9 (sweep 4's last row)
     int i6 = 1 - lane - 9;
@@ -430,11 +412,6 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
 #pragma unroll
           for (int c = 0; c < C; c++)
             if (1 + lane + 32 * c <= mj) xg[32 * c] = xo[c];
-          if (decoupled) {                           // row w of the new x is in global memory: let the sum warp have it
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) *progress = w;
-          }
         }
       }
       i6++;
@@ -442,52 +419,17 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
       RLFC_STEP_SYNC();
     }
   } else {
-    // ------------------------------------------------------------------ Field.sum of the new x (level 0 only)
-    // Field.pde:311-318: a serial float accumulation over the interior in i-major order: one lane-uniform chain of
-    // dependent adds, pure latency.  It starts as soon as the first rows are written out and ends about one chain
-    // length after the smoother began, instead of costing a kernel of its own after it.
-    float s = 0.f;
-    if (decoupled) {
-      // rows are taken from global memory (L2) as soon as the write-out has published them; this lane's vectors of the
-      // next row are requested before the current row's chain starts
-      const int nv = (mj + 4) / 4;                   // vectors that hold columns 0 .. mj
-      auto load_row = [&](int w, float4 (&v)[2]) {
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-          const int vi = lane + 32 * u, j = 4 * vi;
-          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (vi < nv) t = __ldcg(reinterpret_cast<const float4*>(x + (size_t)w * P) + vi);
-          if (j < 1 || j > mj) t.x = 0.f;            // ghost column / beyond the interior: s + 0.f == s
-          if (j + 1 > mj) t.y = 0.f;
-          if (j + 2 > mj) t.z = 0.f;
-          if (j + 3 > mj) t.w = 0.f;
-          v[u] = t;
-        }
-      };
-      auto wait_row = [&](int w) { while (*progress < w) __nanosleep(64); };
-      float4 cur[2], nxt[2];
-      wait_row(1);
-      load_row(1, cur);
-      for (int w = 1; w <= ni; w++) {
-        float4* st = reinterpret_cast<float4*>(sumbuf + (size_t)(w & 1) * P);
-#pragma unroll
-        for (int u = 0; u < 2; u++)
-          if (lane + 32 * u < nv) st[lane + 32 * u] = cur[u];
-        __syncwarp();
-        if (w < ni) { wait_row(w + 1); load_row(w + 1, nxt); }
-        for (int b = 0; b < nv; b += 8) {
-          float4 v[8];
-#pragma unroll
-          for (int u = 0; u < 8; u++) v[u] = (b + u < nv) ? st[b + u] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int u = 0; u < 8; u++) { s += v[u].x; s += v[u].y; s += v[u].z; s += v[u].w; }
-        }
-        cur[0] = nxt[0]; cur[1] = nxt[1];
+    // ------------------------------------------------------------------ loader: bulk copies kPF steps ahead
+    for (int t = 1; t <= t_end; t++) {
+      if (lane == 0) {
+        fence_proxy_async();
+        issue(t + kPF);
       }
-    } else {
-      for (int t = 1; t <= t_end; t++) __syncthreads();
+      mbar_wait(bars + (t & (kCoefSlots - 1)), ((unsigned)t >> kCoefShift) & 1u);   // entry / row t + 1 has landed
+      RLFC_STEP_SYNC();
     }
-    if (XMODE == 3 && lane == 0 && psum_out) *psum_out = s;
+    // drain: every issued copy must have landed before the shared memory is reused
+    for (int q = t_end + 2; q <= t_end + kPF; q++) mbar_wait(bars + ((q - 1) & (kCoefSlots - 1)), ((unsigned)(q - 1) >> kCoefShift) & 1u);
   }
 #undef RLFC_STEP_SYNC
   __syncthreads();

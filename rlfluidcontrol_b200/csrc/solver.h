@@ -81,7 +81,6 @@ struct SolverParams {
   int   nlevels;
   int   coarse_strips;      // max strip count over levels >= 1 (warps of k_mg_coarse)
   int   fast_bc;            // 1 = two-phase setBC kernels (no band face on the lines setBC reads; grid fits one CTA)
-  int   fuse_psum;          // 1 = the level-0 smoother also produces Field.sum(p) (no k_psum launch)
   int   use_rows;           // 1 = row-pipelined smoother (smooth_rows.cuh), 0 = strip smoother (smooth_strip.cuh)
   int   resolution, substeps, mg_max_iters;
   float init_time, episode_time;

@@ -786,6 +786,15 @@ k_mg_coarse_rows(const __grid_constant__ SolverParams q) {
   if (!q.sc.active[e]) return;
   const int last = q.nlevels - 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#ifdef RLFC_COARSE_TIMING
+  long long tk = clock64();
+  __shared__ long long tick_log[40];
+  __shared__ int tick_n;
+  if (threadIdx.x == 0) tick_n = 0;
+#define TICK(what, l) do { __syncthreads(); if (threadIdx.x == 0) { long long n_ = clock64(); tick_log[tick_n++] = n_ - tk; tk = n_; } } while (0)
+#else
+#define TICK(what, l)
+#endif
   for (int l = 1; l < last; l++) {
     const DevLevel& L = q.lev[l];
     const DevLevel& C = q.lev[l + 1];
@@ -796,10 +805,12 @@ k_mg_coarse_rows(const __grid_constant__ SolverParams q) {
       for (int I = 1 + warp; I <= nci; I += nw)
         down_block<false>(L, C, L.r + eo, L.d + eo, L.x + eo, C.r + (size_t)e * C.stride, I, J);
     __syncthreads();
+    TICK("down", l);
   }
   {
     const DevLevel& L = q.lev[last];
     rows_dispatch<1>(L, L.r + (size_t)e * L.stride, L.x + (size_t)e * L.stride, smem_raw);
+    TICK("smooth", last);
   }
   for (int l = last - 1; l >= 1; l--) {
     const DevLevel& L = q.lev[l];
@@ -809,8 +820,18 @@ k_mg_coarse_rows(const __grid_constant__ SolverParams q) {
     float* x = L.x + eo;
     coarse_up_pass(L, C, r, x, C.x + (size_t)e * C.stride);
     __syncthreads();
+    TICK("up", l);
     rows_dispatch<2>(L, r, x, smem_raw);
+    TICK("smooth", l);
   }
+#undef TICK
+#ifdef RLFC_COARSE_TIMING
+  if (e == 0 && threadIdx.x == 0) {
+    printf("coarse ticks:");
+    for (int k = 0; k < tick_n; k++) printf(" %lld", tick_log[k]);
+    printf("\n");
+  }
+#endif
 }
 
 template <int C>
@@ -824,7 +845,7 @@ k_smooth0_rows(const __grid_constant__ SolverParams q, int which) {
   const int e = blockIdx.x;
   if (!q.sc.active[e]) return;
   float* p = L.x + (size_t)e * L.stride;
-  double rr = rows_smooth<C, 3>(L, q.rsk + (size_t)e * q.rsk_stride, p, smem_raw, gbuf, q.fuse_psum ? q.sc.psum + e : nullptr);
+  double rr = rows_smooth<C, 3>(L, q.rsk + (size_t)e * q.rsk_stride, p, smem_raw, gbuf);
   // ghost cells of x: x.plusEq(d) runs over all cells and d.setBC copied the adjacent interior value (MG.pde:90,95)
   const float *gtop = gbuf, *gbot = gbuf + mj, *gleft = gbuf + 2 * mj, *gright = gbuf + 2 * mj + ni;
   for (int c = threadIdx.x; c < mj; c += blockDim.x) { p[IDX(0, c + 1)] += gtop[c]; p[IDX(n - 1, c + 1)] += gbot[c]; }
@@ -1266,7 +1287,6 @@ int launch_smooth0(const SolverParams& q, const float* r_in, float* r_out, int w
 }
 
 int launch_psum(const SolverParams& q, cudaStream_t st) {
-  if (q.fuse_psum) return 0;   // the row-pipelined level-0 smoother produces Field.sum itself (smooth_rows.cuh, warp 7)
   k_psum<<<q.B, 32, 0, st>>>(q);
   return 1;
 }

@@ -164,10 +164,10 @@ def test_other_grids(rlfc, oracle, resolution, xl, yl):
             assert_same(a, b, nm)
 
 
-@pytest.mark.parametrize("envvar,value", [("RLFC_SMOOTHER", "strip"), ("RLFC_FUSE_PSUM", "1"), ("RLFC_NO_GRAPH", "1"),
-                                          ("RLFC_GROUPS", "3")])
+@pytest.mark.parametrize("envvar,value", [("RLFC_SMOOTHER", "strip"), ("RLFC_NO_GRAPH", "1"), ("RLFC_GROUPS", "3"),
+                                          ("RLFC_FAST_BC", "0")])
 def test_alternative_execution_paths(rlfc, oracle, init_state, monkeypatch, envvar, value):
-    """The strip smoother, the smoother-fused Field.sum, eager launches and odd env-group splits are different
+    """The strip smoother, eager launches, odd env-group splits and the literal setBC kernels are different
     schedules of the same arithmetic: all must reproduce the oracle bit for bit."""
     monkeypatch.setenv(envvar, value)
     ref = make_oracle(oracle, init_state)
