@@ -217,6 +217,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` summary (profiles/r01_ncu_summary.json,
+    same workload: 256 envs, default grid), or None."""
+    p = ROOT / "profiles" / "r01_ncu_summary.json"
+    if not p.exists():
+        return None
+    try:
+        tab = json.loads(p.read_text())
+    except Exception:
+        return None
+    for name, rec in tab.items():
+        base = name.split("<")[0].replace("_rows", "").replace("_blk", "")
+        if base == kernel or name.split("<")[0] == kernel:
+            return float(rec["dram_traffic_B_per_launch"])
+    return None
+
+
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -347,7 +364,7 @@ def run_b200(args):
             avg_ms = top["ms"] / max(top["launches"], 1)
             ach = top["bytes_per_launch"] / (avg_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "share_of_step": top["ms"] / tot_ms,
+                    "traffic": ncu_traffic(top["name"]), "peak_source": peak_src, "share_of_step": top["ms"] / tot_ms,
                     "algorithmic_bytes_per_launch": top["bytes_per_launch"], "avg_launch_ms": avg_ms}
         # whole-step view against the SURVEY 8d model: 4 B * N_int * (28 + 13 (kP + kC)) per env per solver step
         nint = 384 * 192

@@ -10,7 +10,7 @@ from collections import OrderedDict
 
 def short(name):
     n = name.split("(")[0]
-    n = n.replace("rlfc::<unnamed>::", "").replace("void ", "")
+    n = n.replace("rlfc::<unnamed>::", "").replace("void ", "").replace("unnamed>::", "")
     return n
 
 
