@@ -117,6 +117,7 @@ k_advdif(const float* __restrict__ srcx, const float* __restrict__ srcy, const f
     const float uoy = 0.5f * (xcm1 + xc);
     fyw = uoy * face_value(uoy, ya, yb, yc, yd, ip, in_);
   }
+#pragma unroll 4
   for (int i = ia; i <= ib; i++) {
     const float xe = ldx(i + 2), ye = ldy(i + 2);
     float u0xv, u0yv;
