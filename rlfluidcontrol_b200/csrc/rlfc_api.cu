@@ -517,6 +517,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   sp.mg_tol = g.mg_tol;
   sp.use_rows = 1;
   if (const char* ev = std::getenv("RLFC_SMOOTHER")) sp.use_rows = std::string(ev) != "strip";
+  const bool force_wave = std::getenv("RLFC_SMOOTHER") && std::string(std::getenv("RLFC_SMOOTHER")) == "wave";
   sp.nlevels = (int)g.levels.size();
   sp.resolution = cfg->resolution; sp.substeps = cfg->substeps; sp.mg_max_iters = cfg->mg_max_iters;
   sp.init_time = cfg->init_time; sp.episode_time = cfg->episode_time;
@@ -548,7 +549,8 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     {  // pre-skewed coefficient tables for the strip smoother (layout: solver.h SkewLevel)
       const int ni = H.n - 2, mj = H.m - 2;
       const int ns = (mj + 31) / 32, Tsk = 16 /*kSkewPad*/ + ni + 64 /*kSkewTail*/;
-      if (ns > 8) return bail(fail(RLFC_EGRID, "grids wider than 256 cells are not supported by the strip smoother yet"));
+      if (ns > 8 && !sp.use_rows) return bail(fail(RLFC_EGRID, "grids wider than 256 cells are not supported by the strip smoother"));
+      if (ns <= 8) {
       std::vector<float4> A((size_t)ns * Tsk * 32, make_float4(0.f, 0.f, 0.f, 0.f));
       std::vector<float2> nd((size_t)ns * Tsk * 32, make_float2(0.f, 0.f));
       for (int k = 0; k < ns; k++)
@@ -564,12 +566,17 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
       TRY(upload_vec(E, A, &L.sk.A));
       TRY(upload_vec(E, nd, &L.sk.nd));
       if (l >= 1) sp.coarse_strips = std::max(sp.coarse_strips, ns);
+      }
     }
     {  // pre-skewed coefficient table for the row-pipelined smoother (layout: solver.h RowTab)
       const int ni = H.n - 2, mj = H.m - 2;
       const int C = (mj + 31) / 32, K = (3 * C + 1 + 3) / 4, nl = (mj + C - 1) / C;
       const int front = 10 /*kTabFront*/, entries = front + ni + nl + 10 /*kStageLag*/ + 5 /*kPF*/ + 6;
-      if (C > 8) return bail(fail(RLFC_EGRID, "grids wider than 256 cells are not supported by the smoother yet"));
+      // levels too wide for the row pipeline (more than 8 columns per lane on level 0, 4 on coarse levels) are smoothed by
+      // the wavefront fallback (smooth_wave.cuh); RLFC_SMOOTHER=wave forces it everywhere (tests)
+      L.wave = (C > (l == 0 ? 8 : 4)) || force_wave;
+      L.rt.C = C; L.rt.K = K; L.rt.entries = 0; L.rt.copies = 1; L.rt.T = nullptr;
+      if (!L.wave) {
       std::vector<float4> T((size_t)entries * K * 32, make_float4(0.f, 0.f, 0.f, 0.f));
       std::vector<float> f(4 * K);
       for (int e = 0; e < entries; e++)
@@ -603,11 +610,14 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
       for (int c = 0; c < copies; c++) Trep.insert(Trep.end(), T.begin(), T.end());
       L.rt.C = C; L.rt.K = K; L.rt.entries = entries; L.rt.copies = copies;
       TRY(upload_vec(E, Trep, &L.rt.T));
+      }
     }
     TRY(E->dmalloc(&L.r, L.stride * B));
     TRY(E->dmalloc(&L.x, L.stride * B));
     TRY(E->dmalloc(&L.d, L.stride * B));
     L.r2 = nullptr;
+    L.w = nullptr;
+    if (l == 0 && L.wave) TRY(E->dmalloc(&L.w, L.stride * B));
   }
   // body band: faces where the BDIM blend is not the identity (del != 1, del1 != 0, or a control
   // cylinder's velocity kernel is non-zero)
@@ -672,7 +682,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   TRY(E->dmalloc(&E->pB, S));
   {
     const int C0 = sp.lev[0].rt.C, mj0 = g.m - 2;
-    sp.rsk_stride = (size_t)round_up((int)rows_skew_floats(C0, g.n - 2, (mj0 + C0 - 1) / C0), 32);
+    sp.rsk_stride = sp.lev[0].wave ? 32 : (size_t)round_up((int)rows_skew_floats(C0, g.n - 2, (mj0 + C0 - 1) / C0), 32);
     TRY(E->dmalloc(&sp.rsk, sp.rsk_stride * B));
   }
 #undef TRY
@@ -696,6 +706,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     for (int l = 0; l < v.nlevels; l++) {
       const size_t o = (size_t)e0 * v.lev[l].stride;
       v.lev[l].r += o; v.lev[l].x += o; v.lev[l].d += o;
+      if (v.lev[l].w) v.lev[l].w += o;
     }
     v.band_tmp += (size_t)e0 * (v.nband_x + v.nband_y);
     v.rsk += (size_t)e0 * v.rsk_stride;

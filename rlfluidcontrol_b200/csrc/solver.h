@@ -43,6 +43,8 @@ struct DevLevel {
   size_t stride;            // per-env stride (floats) of r/x/d at this level
   const float *lx, *ly, *inv, *diag;   // static, pitched
   float *r, *r2, *x, *d;    // per-env batch arrays (level 0: x = p; r2 = ping-pong residual)
+  float *w;                 // level 0, wavefront smoother only: scratch for the Gauss-Seidel iterate
+  int wave;                 // 1 = this level is smoothed by the wavefront fallback (smooth_wave.cuh)
 };
 
 struct BandFace {           // a face where the BDIM blend differs from the identity

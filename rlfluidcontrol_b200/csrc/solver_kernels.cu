@@ -22,6 +22,7 @@
 #include "solver.h"
 #include "smooth_strip.cuh"
 #include "smooth_rows.cuh"
+#include "smooth_wave.cuh"
 
 namespace rlfc {
 namespace {
@@ -810,7 +811,9 @@ k_mg_coarse_rows(const __grid_constant__ SolverParams q) {
   }
   {
     const DevLevel& L = q.lev[last];
-    rows_dispatch<1>(L, L.r + (size_t)e * L.stride, L.x + (size_t)e * L.stride, smem_raw);
+    const size_t eo = (size_t)e * L.stride;
+    if (L.wave) wave_smooth<1>(L, L.r + eo, L.x + eo, L.d + eo, nullptr, 4);     // L.d is unused on the coarsest level
+    else rows_dispatch<1>(L, L.r + eo, L.x + eo, smem_raw);
     TICK("smooth", last);
   }
   for (int l = last - 1; l >= 1; l--) {
@@ -822,7 +825,8 @@ k_mg_coarse_rows(const __grid_constant__ SolverParams q) {
     coarse_up_pass(L, C, r, x, C.x + (size_t)e * C.stride);
     __syncthreads();
     TICK("up", l);
-    rows_dispatch<2>(L, r, x, smem_raw);
+    if (L.wave) wave_smooth<2>(L, r, x, L.r + eo, nullptr, 4);   // the level's restricted residual is dead after the down pass
+    else rows_dispatch<2>(L, r, x, smem_raw);
     TICK("smooth", l);
   }
 #undef TICK
@@ -856,6 +860,28 @@ k_smooth0_rows(const __grid_constant__ SolverParams q, int which) {
     p[IDX(n - 1, 0)] += gbot[0]; p[IDX(n - 1, m - 1)] += gbot[mj - 1];
   }
   // r.r: fixed-order reduction (lanes by shuffle tree, then warps in order)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rr += __shfl_down_sync(0xffffffffu, rr, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = rr;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += wsum[w];
+    const int it = ++q.sc.iters[2 * e + which];
+    if ((float)s < q.mg_tol || it >= q.mg_max_iters) q.sc.active[e] = 0;
+    else atomicExch(q.sc.any_active, 1);
+  }
+}
+
+// level-0 smooth(4) + increment + r.r + loop test with the wavefront fallback (grids wider than 256 cells)
+__global__ void __launch_bounds__(1024)
+k_smooth0_wave(const __grid_constant__ SolverParams q, const float* r_in_all, float* r_out_all, int which) {
+  const DevLevel& L = q.lev[0];
+  __shared__ double wsum[32];
+  const int e = blockIdx.x;
+  if (!q.sc.active[e]) return;
+  const size_t eo = (size_t)e * L.stride;
+  double rr = wave_smooth<3>(L, r_in_all + eo, L.x + eo, L.w + eo, r_out_all + eo, 4);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) rr += __shfl_down_sync(0xffffffffu, rr, o);
   if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = rr;
@@ -1206,7 +1232,8 @@ static size_t smooth0_smem(const SolverParams& q) {
 // opt-in shared-memory sizes; called once per handle, outside any stream capture
 static size_t coarse_rows_smem(const SolverParams& q) {
   size_t s = 0;
-  for (int l = 1; l < q.nlevels; l++) s = max(s, rows_smem_bytes(min(q.lev[l].rt.C, 4), q.lev[l].P, false));
+  for (int l = 1; l < q.nlevels; l++)
+    if (!q.lev[l].wave) s = max(s, rows_smem_bytes(min(q.lev[l].rt.C, 4), q.lev[l].P, false));
   return s;
 }
 static size_t smooth0_rows_smem(const SolverParams& q) {
@@ -1219,8 +1246,11 @@ static cudaError_t set_smooth0_rows_attr(const SolverParams& q) {
 }
 
 int configure_kernels(const SolverParams& q) {
-  cudaError_t e1 = cudaFuncSetAttribute(k_mg_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)strip_smem(q.coarse_strips));
-  cudaError_t e2 = cudaFuncSetAttribute(k_smooth0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smooth0_smem(q));
+  cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+  if (!q.use_rows) {
+    e1 = cudaFuncSetAttribute(k_mg_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)strip_smem(q.coarse_strips));
+    e2 = cudaFuncSetAttribute(k_smooth0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smooth0_smem(q));
+  }
   if (q.fast_bc) {
     if (cudaFuncSetAttribute(k_bc2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc2_smem(q)) != cudaSuccess ||
         cudaFuncSetAttribute(k_bc2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc2_smem(q)) != cudaSuccess ||
@@ -1229,7 +1259,7 @@ int configure_kernels(const SolverParams& q) {
   }
   cudaError_t e3 = cudaFuncSetAttribute(k_mg_coarse_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coarse_rows_smem(q));
   cudaError_t e4 = cudaSuccess;
-  switch (q.lev[0].rt.C) {
+  if (!q.lev[0].wave) switch (q.lev[0].rt.C) {
     case 1: e4 = set_smooth0_rows_attr<1>(q); break;
     case 2: e4 = set_smooth0_rows_attr<2>(q); break;
     case 3: e4 = set_smooth0_rows_attr<3>(q); break;
@@ -1254,19 +1284,23 @@ int launch_mg_coarse(const SolverParams& q, cudaStream_t st) {
 
 int launch_mg_up0(const SolverParams& q, float* r, cudaStream_t st) {
   dim3 blk(32, 8);
-  if (q.use_rows) k_mg_up0_blk<<<grid2d(q.lev[1].m - 2, q.lev[1].n - 2, q.B, blk), blk, 0, st>>>(q, r);
+  if (q.use_rows && !q.lev[0].wave) k_mg_up0_blk<<<grid2d(q.lev[1].m - 2, q.lev[1].n - 2, q.B, blk), blk, 0, st>>>(q, r);
   else k_mg_up0<false><<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, r);
   return 1;
 }
 
 int launch_unskew_r(const SolverParams& q, float* r, cudaStream_t st) {
-  if (!q.use_rows) return 0;
+  if (!q.use_rows || q.lev[0].wave) return 0;
   dim3 blk(32, 8);
   k_unskew_r<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, r);
   return 1;
 }
 
 int launch_smooth0(const SolverParams& q, const float* r_in, float* r_out, int which, cudaStream_t st) {
+  if (q.use_rows && q.lev[0].wave) {
+    k_smooth0_wave<<<q.B, 1024, 0, st>>>(q, r_in, r_out, which);
+    return 1;
+  }
   if (q.use_rows) {
     const size_t sm = smooth0_rows_smem(q);
     switch (q.lev[0].rt.C) {

@@ -164,10 +164,10 @@ def test_other_grids(rlfc, oracle, resolution, xl, yl):
             assert_same(a, b, nm)
 
 
-@pytest.mark.parametrize("envvar,value", [("RLFC_SMOOTHER", "strip"), ("RLFC_NO_GRAPH", "1"), ("RLFC_GROUPS", "3"),
-                                          ("RLFC_FAST_BC", "0")])
+@pytest.mark.parametrize("envvar,value", [("RLFC_SMOOTHER", "strip"), ("RLFC_SMOOTHER", "wave"), ("RLFC_NO_GRAPH", "1"),
+                                          ("RLFC_GROUPS", "3"), ("RLFC_FAST_BC", "0")])
 def test_alternative_execution_paths(rlfc, oracle, init_state, monkeypatch, envvar, value):
-    """The strip smoother, eager launches, odd env-group splits and the literal setBC kernels are different
+    """The strip smoother, the wavefront fallback smoother, eager launches, odd env-group splits and the literal setBC kernels are different
     schedules of the same arithmetic: all must reproduce the oracle bit for bit."""
     monkeypatch.setenv(envvar, value)
     ref = make_oracle(oracle, init_state)
@@ -181,4 +181,26 @@ def test_alternative_execution_paths(rlfc, oracle, init_state, monkeypatch, envv
             ref.update2()
             assert_same(f[3], np.array(ref.force(), np.float32), f"force step {k}")
         for nm, a, b in zip(("ux", "uy", "p"), env.get_fields(3), ref.get_state()):
+            assert_same(a, b, nm)
+
+
+@pytest.mark.parametrize("resolution,dims", [(64, (1026, 514)), (128, (2050, 1026))])
+def test_wide_grid(rlfc, oracle, resolution, dims):
+    """Single-domain-style grids wider than the row pipeline's 256 columns: BASELINE config 3 (2048x1024, SURVEY 8d:
+    resolution 128, t_step = 0.18/128 so dt stays 0.18 grid units) and its half-scale version.  The wide levels fall
+    back to the wavefront smoother, setBC to the literal kernels.  Impulsive start, a non-zero action, every float
+    equal to the oracle's."""
+    kw = dict(resolution=resolution, x_lengths=16, y_lengths=8)
+    t_step = np.float32(0.18) / np.float32(resolution)
+    ref = oracle.OracleEnv(literal=False, resolution=resolution, xLengths=16, yLengths=8, tStep=float(t_step))
+    ref.set_xi(0.5, -0.5)
+    act = np.array([[0.5, -0.5]], np.float32)
+    with rlfc.AFCCylinderBatch(1, init_state=None, t_step=float(t_step), **kw) as env:
+        assert (env.n, env.m) == (ref.n, ref.m) == dims
+        for k in range(2):
+            f = env.update2(act if k == 0 else None)
+            ref.update2()
+            assert_same(f[0], np.array(ref.force(), np.float32), f"force step {k}")
+            assert tuple(env.mg_iters()[0]) == ref.mg_iters()
+        for nm, a, b in zip(("ux", "uy", "p"), env.get_fields(0), ref.get_state()):
             assert_same(a, b, nm)
