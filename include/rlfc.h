@@ -102,6 +102,10 @@ int  rlfc_env_substep(rlfc_env *env, const float *actions, float *force, float *
 int  rlfc_env_get_fields(rlfc_env *env, int e, float *ux, float *uy, float *p);
 int  rlfc_env_set_fields(rlfc_env *env, int e, const float *ux, const float *uy, const float *p);
 
+/* Field.sum() of every environment's pressure field (Field.pde:311-318: serial float accumulation over the
+   interior, i-major): sums[n_envs].  Runs the same device path the projection uses (VectorField.pde:136). */
+int  rlfc_env_field_sum(rlfc_env *env, float *sums);
+
 /* Text checkpoint of one environment in the BDIM.write format (readable by BDIM.resume). */
 int  rlfc_env_save_bdim(rlfc_env *env, int e, const char *path);
 int  rlfc_env_load_bdim(rlfc_env *env, int e, const char *path);

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <cstddef>
+#include <cstdint>
 
 namespace rlfc {
 
@@ -98,6 +99,10 @@ struct SolverParams {
   const ForcePt *force_pts; int nforce;
   const SamplePt *probe_pts; int nprobe;
   int rr_blocks;            // number of per-env partial sums written by the increment kernel
+  // Field.sum as segment summaries (exact_sum.cuh); xs_slots == nullptr selects the plain serial chain (k_psum)
+  double *xs_ctot;          // [B][xs_nchunks] double-precision chunk totals
+  unsigned *xs_slots;       // [B][xs_nseg][16] segment summaries
+  int xs_nseg, xs_nchunks;
   EnvScalars sc;
 };
 

@@ -23,6 +23,7 @@
 #include "smooth_strip.cuh"
 #include "smooth_rows.cuh"
 #include "smooth_wave.cuh"
+#include "exact_sum.cuh"
 
 namespace rlfc {
 namespace {
@@ -945,6 +946,8 @@ k_psum(const __grid_constant__ SolverParams q) {
   if (lane == 0) q.sc.psum[e] = s;
 }
 
+#include "exact_sum_kernels.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // projection tail (VectorField.pde:136-139): p += -sum/N on all cells; dp = grad p with its setBC
 // (dp.x[1][*] = dp.y[*][1] = 0); u += c * (dp * -1) on the interior.  u.setBC follows in k_bc.
@@ -1322,8 +1325,15 @@ int launch_smooth0(const SolverParams& q, const float* r_in, float* r_out, int w
 }
 
 int launch_psum(const SolverParams& q, cudaStream_t st) {
-  k_psum<<<q.B, 32, 0, st>>>(q);
-  return 1;
+  if (!q.xs_slots) {                    // RLFC_PSUM=serial: the plain dependent-add chain, one warp per environment
+    k_psum<<<q.B, 32, 0, st>>>(q);
+    return 1;
+  }
+  const dim3 grid(q.xs_nchunks, q.B);
+  k_xsum_totals<<<grid, kXsThreads, 0, st>>>(q);
+  k_xsum_tables<<<grid, kXsThreads, 0, st>>>(q);
+  k_xsum_chain<<<q.B, 32, 0, st>>>(q);
+  return 3;
 }
 
 int launch_project_u(const SolverParams& q, float* ux, float* uy, cudaStream_t st) {

@@ -70,6 +70,7 @@ def load_library():
     L.rlfc_env_dims.argtypes = [vp, ip, ip, ip]
     L.rlfc_env_get_time.argtypes = [vp, fp]
     L.rlfc_env_get_mg_iters.argtypes = [vp, ip]
+    L.rlfc_env_field_sum.argtypes = [vp, fp]
     L.rlfc_env_get_static.argtypes = [vp, C.c_char_p, C.c_int, fp, ip, ip]
     L.rlfc_geometry_static.argtypes = [C.POINTER(Config), C.c_char_p, C.c_int, fp, ip, ip, ip]
     L.rlfc_env_num_levels.argtypes = [vp]
@@ -205,6 +206,12 @@ class AFCCylinderBatch:
         it = np.empty((self.n_envs, 2), np.int32)
         self._check(self._L.rlfc_env_get_mg_iters(self._h, it.ctypes.data_as(C.POINTER(C.c_int))), "rlfc_env_get_mg_iters")
         return it
+
+    def field_sum(self):
+        """Field.sum() of every env's pressure field (Field.pde:311-318), evaluated on the device."""
+        s = np.empty(self.n_envs, np.float32)
+        self._check(self._L.rlfc_env_field_sum(self._h, _fp(s)), "rlfc_env_field_sum")
+        return s
 
     @property
     def num_levels(self):

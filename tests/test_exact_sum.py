@@ -1,0 +1,126 @@
+"""Field.sum (Field.pde:311-318) re-phrased as parallel segment summaries (rlfluidcontrol_b200/csrc/exact_sum.cuh).
+
+CPU part: the host/device core of the summaries is compiled for the host (tests/xsum_host.cpp) and must reproduce the
+plain serial float loop BIT FOR BIT on arbitrary data, including wrong predictions of the accumulator.
+GPU part: rlfc_env_field_sum (the kernels the projection uses) against the oracle's Field.sum on adversarial fields."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+HERE = Path(__file__).resolve().parent
+LIB = HERE / "_build" / "libxsum_host.so"
+FP = C.POINTER(C.c_float)
+
+
+@pytest.fixture(scope="module")
+def xs():
+    src = HERE / "xsum_host.cpp"
+    hdr = HERE.parent / "rlfluidcontrol_b200" / "csrc" / "exact_sum.cuh"
+    if not LIB.exists() or LIB.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime):
+        LIB.parent.mkdir(exist_ok=True)
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-o", str(LIB), str(src)],
+                       check=True)
+    L = C.CDLL(str(LIB))
+    L.xs_serial.restype = C.c_float
+    L.xs_serial.argtypes = [FP, C.c_long]
+    L.xs_parallel.restype = C.c_float
+    L.xs_parallel.argtypes = [FP, C.c_long, C.c_double, C.POINTER(C.c_long)]
+    return L
+
+
+def both(L, a, noise=0.0):
+    a = np.ascontiguousarray(a, np.float32)
+    st = (C.c_long * 4)()
+    s = np.float32(L.xs_serial(a.ctypes.data_as(FP), a.size))
+    p = np.float32(L.xs_parallel(a.ctypes.data_as(FP), a.size, noise, st))
+    same = s.tobytes() == p.tobytes() or (np.isnan(s) and np.isnan(p))
+    return same, s, p, list(st)
+
+
+def adversarial(kind, n, rng):
+    """Families of addends that stress one aspect each of the integer model."""
+    if kind == 0:
+        return rng.standard_normal(n)
+    if kind == 1:
+        return rng.standard_normal(n) + 0.3                                  # drifting accumulator: binade changes
+    if kind == 2:
+        return rng.standard_normal(n) * 10.0 ** rng.integers(-20, 20, n)      # wild magnitudes
+    if kind == 3:
+        return np.round(rng.standard_normal(n) * 8) / 8                       # few significand bits: exact ties
+    if kind == 4:
+        return np.where(rng.random(n) < 0.3, 0.0, rng.standard_normal(n)) - 0.5   # zeros, negative accumulator
+    if kind == 5:
+        return rng.integers(-3, 4, n) * 2.0 ** rng.integers(-30, 3, n)        # powers of two: ties and exact sums
+    if kind == 6:
+        return np.abs(rng.standard_normal(n)) * 2.0 ** rng.integers(-140, -100, n)   # denormal range
+    if kind == 7:
+        return rng.standard_normal(n) + 100 * np.sin(np.arange(n) / 50.0)     # oscillating accumulator: sign changes
+    if kind == 8:                                                             # accumulator parked on a power of two
+        a = rng.standard_normal(n) * 1e-3
+        a[0] = 1024.0
+        return a
+    if kind == 9:                                                             # half-ulp addends against a big accumulator
+        a = np.full(n, 2.0 ** -14)
+        a[0] = 512.0
+        a[rng.integers(1, max(2, n), n // 7)] *= -1
+        return a
+    a = rng.standard_normal(n)                                                # Inf / NaN somewhere
+    a[rng.integers(0, n)] = [np.inf, -np.inf, np.nan][int(rng.integers(0, 3))]
+    return a
+
+
+def test_matches_serial_loop_on_adversarial_data(xs):
+    rng = np.random.default_rng(20261017)
+    rejected = 0
+    for trial in range(1100):
+        n = int(rng.integers(1, 6000))
+        a = adversarial(trial % 11, n, rng)
+        for noise in (0.0, 1e-4, 0.3):        # relative error injected into the predicted accumulator
+            same, s, p, st = both(xs, a, noise)
+            assert same, (trial, trial % 11, n, noise, s, p, st)
+            rejected += st[3]
+    assert rejected > 0, "the validity check of the summaries was never exercised"
+
+
+def test_pressure_fields_of_the_oracle(xs, oracle, init_state):
+    """Real data: Field.sum of the pressure after each of 12 solver steps; nearly all segments are summarised."""
+    env = oracle.OracleEnv(literal=False)
+    env.set_state(init_state["ux"], init_state["uy"], init_state["p"])
+    env.set_xi(0.5, -0.3)
+    for k in range(12):
+        _, _, p = env.get_state()
+        a = p[1:-1, 1:-1].ravel()
+        same, s, par, st = both(xs, a)
+        assert same and s == np.float32(oracle.Field(p.shape[0], p.shape[1], values=p).sum())
+        assert st[2] + st[3] < 0.05 * sum(st[:3]), st
+        env.update2()
+
+
+def test_large_array(xs):
+    rng = np.random.default_rng(7)
+    a = rng.standard_normal(2048 * 1024) * 0.5 + 0.01
+    same, s, p, st = both(xs, a)
+    assert same, (s, p, st)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resolution,xl,yl", [(24, 16, 8), (12, 8, 4), (12, 7, 3)])
+def test_device_field_sum(rlfc, oracle, resolution, xl, yl):
+    """rlfc_env_field_sum on adversarial pressure fields == the oracle's Field.sum, bit for bit (also with the plain
+    serial chain, RLFC_PSUM=serial, through test_alternative_execution_paths)."""
+    rng = np.random.default_rng(5)
+    B = 11
+    with rlfc.AFCCylinderBatch(B, init_state=None, resolution=resolution, x_lengths=xl, y_lengths=yl) as env:
+        n, m = env.n, env.m
+        fields = []
+        for e in range(B):
+            p = adversarial(e % 11, n * m, rng).astype(np.float32).reshape(n, m)
+            fields.append(p)
+            env.set_fields(e, None, None, p)
+        got = env.field_sum()
+        for e in range(B):
+            want = np.float32(oracle.Field(n, m, values=fields[e]).sum())
+            assert got[e].tobytes() == want.tobytes() or (np.isnan(got[e]) and np.isnan(want)), (e, got[e], want)

@@ -165,9 +165,10 @@ def test_other_grids(rlfc, oracle, resolution, xl, yl):
 
 
 @pytest.mark.parametrize("envvar,value", [("RLFC_SMOOTHER", "strip"), ("RLFC_SMOOTHER", "wave"), ("RLFC_NO_GRAPH", "1"),
-                                          ("RLFC_GROUPS", "3"), ("RLFC_FAST_BC", "0")])
+                                          ("RLFC_GROUPS", "3"), ("RLFC_FAST_BC", "0"), ("RLFC_PSUM", "serial")])
 def test_alternative_execution_paths(rlfc, oracle, init_state, monkeypatch, envvar, value):
-    """The strip smoother, the wavefront fallback smoother, eager launches, odd env-group splits and the literal setBC kernels are different
+    """The strip smoother, the wavefront fallback smoother, eager launches, odd env-group splits, the literal setBC kernels and the plain
+    serial Field.sum chain are different
     schedules of the same arithmetic: all must reproduce the oracle bit for bit."""
     monkeypatch.setenv(envvar, value)
     ref = make_oracle(oracle, init_state)
