@@ -68,48 +68,49 @@ struct Table {
   int32_t D0, D1, lo0, hi0, lo1, hi1;
 };
 
-// Summarise the additions a[k0 .. k1) for an accumulator with sign/exponent `key`.  `get(k)` returns element k.
-// Returns false when some addend cannot be modelled (Inf/NaN, or an addend at least as large as the
-// accumulator's binade: the sum necessarily leaves the binade).
-template <typename Get>
-XS_HD bool build_table(Get get, int k0, int k1, uint32_t key, Table& T) {
-  if (k1 <= k0) {
-    T.key = kAnyKey; T.D0 = T.D1 = 0; T.lo0 = T.lo1 = INT32_MIN; T.hi0 = T.hi1 = INT32_MAX;
-    return true;
+// Running summary of a run of additions for an accumulator with sign/exponent `key`.
+// The integer increment of one addition is read off the FPU instead of being assembled from shifts:  with
+// R = 1.5 * 2^e (significand 0xC00000, made odd when the modelled significand is odd) and b = the addend with
+// the accumulator's sign factored out,  fl(R + b) - R  is exactly  u * (+-(Q + r))  as long as R + b stays
+// inside the binade -- guaranteed for |b| < 2^(e-2) -- because the rounding of R + b sees the same fraction
+// and the same significand parity as the real accumulator.  In the same binade the difference of the two bit
+// patterns IS that integer.  Larger addends (within a factor 8 of the accumulator) are not modelled.
+struct Run {
+  uint32_t key, sgnmask, Rb, lim;
+  int32_t P0, P1, mn0, mn1, mx0, mx1;
+  bool good, empty;
+  XS_HD void start(uint32_t key_) {
+    key = key_;
+    const uint32_t es = key & 255u;
+    sgnmask = (key >> 8) << 31;
+    Rb = (es << 23) | 0x400000u;
+    lim = (es - 2u) << 23;                         // |addend| must be below 2^(e-2)
+    P0 = P1 = 0; mn0 = mn1 = INT32_MAX; mx0 = mx1 = INT32_MIN;
+    good = true; empty = true;
   }
-  const uint32_t sgn = key >> 8, es = key & 255u;
-  int32_t P0 = 0, P1 = 0, mn0 = INT32_MAX, mn1 = INT32_MAX, mx0 = INT32_MIN, mx1 = INT32_MIN;
-  uint32_t c0 = 0, c1 = 1;                      // parity of the significand under the two start hypotheses
-  bool good = true;
-  for (int k = k0; k < k1; k++) {
-    const uint32_t ab = f2u(get(k));
-    const bool neg = (((ab >> 31) ^ sgn) & 1u) != 0;      // sign of the addend relative to the accumulator
-    uint32_t ea = (ab >> 23) & 255u, M = ab & 0x7fffffu;
-    if (ea == 255u) good = false;
-    if (ea) M |= 0x800000u; else ea = 1;                    // denormal / zero: exponent -126, no hidden bit
-    const int sh = (int)es - (int)ea;
-    if (sh < 1) { good = false; continue; }
-    uint32_t Q, gt, tie;                                     // a/u = Q + rem/2^sh; gt: rem > half, tie: rem == half
-    if (sh > 24) { Q = 0; gt = 0; tie = 0; }
-    else {
-      Q = M >> sh;
-      const uint32_t rem = M & ((1u << sh) - 1u), half = 1u << (sh - 1);
-      gt = rem > half; tie = rem == half;
-    }
-    const uint32_t r0 = gt | (tie & (c0 ^ Q)), r1 = gt | (tie & (c1 ^ Q));
-    const int32_t i0 = (int32_t)(Q + (r0 & 1u)), i1 = (int32_t)(Q + (r1 & 1u));
-    P0 += neg ? -i0 : i0;
-    P1 += neg ? -i1 : i1;
-    c0 ^= (uint32_t)i0; c1 ^= (uint32_t)i1;                 // only bit 0 is used
+  XS_HD void add(float a) {
+    const uint32_t ab = f2u(a);
+    good = good && (ab & 0x7fffffffu) < lim;       // also rejects Inf / NaN
+    const float b = u2f(ab ^ sgnmask);
+    const uint32_t r0 = Rb | ((uint32_t)P0 & 1u), r1 = Rb | (((uint32_t)P1 & 1u) ^ 1u);
+    P0 += (int32_t)(f2u(u2f(r0) + b) - r0);
+    P1 += (int32_t)(f2u(u2f(r1) + b) - r1);
     mn0 = P0 < mn0 ? P0 : mn0; mx0 = P0 > mx0 ? P0 : mx0;
     mn1 = P1 < mn1 ? P1 : mn1; mx1 = P1 > mx1 ? P1 : mx1;
+    empty = false;
   }
-  T.key = key; T.D0 = P0; T.D1 = P1;
-  // every significand after an addition must stay in [2^23 + 1, 2^24 - 1] (header comment)
-  T.lo0 = (int32_t)0x800001 - mn0; T.hi0 = (int32_t)0xffffff - mx0;
-  T.lo1 = (int32_t)0x800001 - mn1; T.hi1 = (int32_t)0xffffff - mx1;
-  return good;
-}
+  // words [key, D0, D1, lo0, hi0, lo1, hi1]; every significand after an addition must stay in
+  // [2^23 + 1, 2^24 - 1] (header comment)
+  XS_HD void store(uint32_t* w) const {
+    if (empty) {
+      w[0] = kAnyKey; w[1] = w[2] = 0; w[3] = w[5] = (uint32_t)INT32_MIN; w[4] = w[6] = (uint32_t)INT32_MAX;
+      return;
+    }
+    w[0] = key; w[1] = (uint32_t)P0; w[2] = (uint32_t)P1;
+    w[3] = (uint32_t)((int32_t)0x800001 - mn0); w[4] = (uint32_t)((int32_t)0xffffff - mx0);
+    w[5] = (uint32_t)((int32_t)0x800001 - mn1); w[6] = (uint32_t)((int32_t)0xffffff - mx1);
+  }
+};
 
 // Apply a table to the accumulator bits; clears `ok` when the table does not provably apply.
 XS_HD uint32_t apply_table(uint32_t bits, uint32_t key, int32_t D0, int32_t D1, int32_t lo0, int32_t hi0, int32_t lo1,
@@ -123,45 +124,41 @@ XS_HD uint32_t apply_table(uint32_t bits, uint32_t key, int32_t D0, int32_t D1, 
 }
 
 // Summary of one segment of cnt <= kSeg additions, given the predicted accumulator before its first addition.
-// slot[kSlotWords]: see the constants above.
+// slot[kSlotWords]: see the constants above.  One pass: the prediction is carried forward as a float chain
+// (what the real accumulator would do from the predicted start); an addition across which the prediction
+// changes sign or binade (or before which it has no usable key) cannot be part of a table -- with at most one
+// such addition the segment is  table | float addition | table, with more it is left to the serial pass.
 template <typename Get>
-XS_HD void build_segment(Get get, int cnt, double pred, uint32_t* slot) {
-  // States 0..cnt = predicted accumulator before element k.  Element k cannot be part of a table when the
-  // prediction changes sign or binade across it (or has no usable key before it): with at most one such
-  // element the segment is  table [0,kx) | float addition of a[kx] | table (kx,cnt).
-  const uint32_t key_first = key_of((float)pred);
-  uint32_t key_prev = key_first, key_after = key_first;
-  int ncross = 0, kx = 0;
+XS_HD void build_segment(Get get, int cnt, double pred_start, uint32_t* slot) {
+  float pred = (float)pred_start;
+  uint32_t key_prev = key_of(pred);
+  Run run;
+  run.start(key_prev);
+  int ncross = 0;
+  bool good = true;
+  for (int w = 0; w < kSlotWords; w++) slot[w] = 0;
   for (int k = 0; k < cnt; k++) {
-    pred += (double)get(k);
-    const uint32_t kn = key_of((float)pred);
-    if (kn != key_prev || !key_ok(key_prev)) { ncross++; kx = k; key_after = kn; }
+    const float a = get(k);
+    pred = pred + a;
+    const uint32_t kn = key_of(pred);
+    if (kn != key_prev || !key_ok(key_prev)) {
+      if (ncross == 0) {                 // close the first table, keep this addition as it is, open the second
+        good = run.good || run.empty;
+        run.store(slot + 1);
+        slot[8] = f2u(a);
+        run.start(kn);
+        if (!key_ok(kn)) run.good = false;          // only acceptable if nothing follows (checked through `empty`)
+      }
+      ncross++;
+    } else {
+      run.add(a);
+    }
     key_prev = kn;
   }
-  for (int w = 0; w < kSlotWords; w++) slot[w] = 0;
-  Table A, B;
-  bool good = ncross <= 1;
-  if (good && ncross == 0) {
-    good = build_table(get, 0, cnt, key_first, A);
-    if (good) {
-      slot[0] = kOne;
-      slot[1] = A.key; slot[2] = (uint32_t)A.D0; slot[3] = (uint32_t)A.D1; slot[4] = (uint32_t)A.lo0;
-      slot[5] = (uint32_t)A.hi0; slot[6] = (uint32_t)A.lo1; slot[7] = (uint32_t)A.hi1;
-      return;
-    }
-  } else if (good) {
-    good = build_table(get, 0, kx, key_first, A) && build_table(get, kx + 1, cnt, key_after, B);
-    if (good) {
-      slot[0] = kSplit;
-      slot[1] = A.key; slot[2] = (uint32_t)A.D0; slot[3] = (uint32_t)A.D1; slot[4] = (uint32_t)A.lo0;
-      slot[5] = (uint32_t)A.hi0; slot[6] = (uint32_t)A.lo1; slot[7] = (uint32_t)A.hi1;
-      slot[8] = f2u(get(kx));
-      slot[9] = B.key; slot[10] = (uint32_t)B.D0; slot[11] = (uint32_t)B.D1; slot[12] = (uint32_t)B.lo0;
-      slot[13] = (uint32_t)B.hi0; slot[14] = (uint32_t)B.lo1; slot[15] = (uint32_t)B.hi1;
-      return;
-    }
-  }
-  slot[0] = kSerial;
+  good = good && ncross <= 1 && (run.good || run.empty);
+  if (!good) { slot[0] = kSerial; return; }
+  if (ncross == 0) { slot[0] = kOne; run.store(slot + 1); }
+  else { slot[0] = kSplit; run.store(slot + 9); }
 }
 
 // Advance the accumulator over one summarised segment.  Returns true when the summary applied; false = the

@@ -77,8 +77,10 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
   const long long left = N - g * xsum::kSeg;
   const int cnt = left >= xsum::kSeg ? xsum::kSeg : (left > 0 ? (int)left : 0);
   const float* seg = buf + t * kXsPad;
-  double ssum = 0.0;
-  for (int k = 0; k < cnt; k++) ssum += (double)seg[k];
+  float fsum = 0.f;                                               // a prediction only: float precision is plenty
+#pragma unroll 8
+  for (int k = 0; k < xsum::kSeg; k++) fsum += seg[k];            // (tail elements are stored as +0)
+  const double ssum = (double)fsum;
   // exclusive scan of the segment sums over the CTA
   double incl = ssum;
 #pragma unroll
@@ -100,11 +102,15 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
   }
 }
 
-constexpr int kXsSlotPad = 20;    // words per slot in shared memory (conflict-free 16-byte stores)
-
+// Serial pass.  One warp per environment; lane L holds summary 32 b + L of batch b in registers.  Summaries of
+// type kOne only need  bits += (bits & 1) ? D1 : D0  on the critical path (about two dependent integer
+// operations), so the warp first runs that chain over a stretch of slots -- every lane keeps the accumulator
+// its own slot started from -- and then all lanes check their slot's validity condition at once.  Anything else
+// (a split summary, a serial one, a summary whose condition fails) is an "event" handled on its own before the
+// chain resumes behind it.
 __global__ void __launch_bounds__(32)
 k_xsum_chain(const __grid_constant__ SolverParams q) {
-  __shared__ __align__(16) uint32_t sbuf[2][32 * kXsSlotPad];
+  __shared__ __align__(16) uint2 sD[2][40];                       // (D0, D1 - D0) of the batch, broadcast to the chain
   const int e = blockIdx.x, lane = threadIdx.x;
   const int len = q.m - 2, P = q.P;
   const long long N = (long long)(q.n - 2) * len;
@@ -122,32 +128,60 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
       nxt[1] = nxt[2] = nxt[3] = make_uint4(0u, 0u, 0u, 0u);
     }
   };
+  // genuine serial additions of segment g from accumulator `bits` (warp-uniform)
+  auto serial = [&](uint32_t bits, long long g) {
+    const long long K0 = g * xsum::kSeg, left = N - K0;
+    const int cnt = left >= xsum::kSeg ? xsum::kSeg : (left > 0 ? (int)left : 0);
+    float v = 0.f;
+    if (lane < cnt) {
+      const long long K = K0 + lane;
+      v = p[(size_t)(1 + (int)(K / len)) * P + 1 + (int)(K % len)];
+    }
+    float s = xsum::u2f(bits);
+    for (int u = 0; u < cnt; u++) s += __shfl_sync(0xffffffffu, v, u);
+    return xsum::f2u(s);
+  };
   const int nb = (nseg + 31) / 32;
   fetch(0);
   uint32_t bits = 0u;                                             // s = +0.f
   for (int b = 0; b < nb; b++) {
-    uint32_t* sb = sbuf[b & 1];
+    uint32_t w[16];
 #pragma unroll
-    for (int w = 0; w < 4; w++) *reinterpret_cast<uint4*>(sb + lane * kXsSlotPad + 4 * w) = nxt[w];
-    __syncwarp();
+    for (int k = 0; k < 4; k++) { w[4 * k] = nxt[k].x; w[4 * k + 1] = nxt[k].y; w[4 * k + 2] = nxt[k].z; w[4 * k + 3] = nxt[k].w; }
     if (b + 1 < nb) fetch(b + 1);                                 // in flight during the chain
-#pragma unroll 4
-    for (int k = 0; k < 32; k++) {                                // every lane replays the same chain
-      const uint32_t* slot = sb + k * kXsSlotPad;
-      if (!xsum::apply_segment(bits, slot)) {
-        // genuine serial additions of this segment (warp-uniform branch)
-        const long long K0 = ((long long)b * 32 + k) * xsum::kSeg;
-        const long long left = N - K0;
-        const int cnt = left >= xsum::kSeg ? xsum::kSeg : (left > 0 ? (int)left : 0);
-        float v = 0.f;
-        if (lane < cnt) {
-          const long long K = K0 + lane;
-          v = p[(size_t)(1 + (int)(K / len)) * P + 1 + (int)(K % len)];
-        }
-        float s = xsum::u2f(bits);
-        for (int u = 0; u < cnt; u++) s += __shfl_sync(0xffffffffu, v, u);
-        bits = xsum::f2u(s);
+    uint2* sd = sD[b & 1];
+    const bool plain = w[0] == xsum::kOne;
+    sd[lane] = (plain && w[1] != xsum::kAnyKey) ? make_uint2(w[2], w[3] - w[2]) : make_uint2(0u, 0u);
+    const uint32_t special = __ballot_sync(0xffffffffu, !plain);
+    __syncwarp();
+    int cur = 0;
+    while (cur < 32) {
+      const uint32_t rest = special >> cur;
+      const int f = rest ? cur + __ffs(rest) - 1 : 32;            // next slot that is not a plain table
+      uint32_t acc = bits, mine = bits;
+      for (int k0 = cur; k0 < f; k0 += 4) {
+        const uint2 d0 = sd[k0], d1 = sd[k0 + 1], d2 = sd[k0 + 2], d3 = sd[k0 + 3];
+        mine = (lane == k0) ? acc : mine;
+        acc = (acc + d0.x) + (acc & 1u) * d0.y;
+        if (k0 + 1 < f) { mine = (lane == k0 + 1) ? acc : mine; acc = (acc + d1.x) + (acc & 1u) * d1.y; }
+        if (k0 + 2 < f) { mine = (lane == k0 + 2) ? acc : mine; acc = (acc + d2.x) + (acc & 1u) * d2.y; }
+        if (k0 + 3 < f) { mine = (lane == k0 + 3) ? acc : mine; acc = (acc + d3.x) + (acc & 1u) * d3.y; }
       }
+      // every lane of the stretch checks that its table really applied to the accumulator it started from
+      bool ok = true;
+      if (lane >= cur && lane < f) xsum::apply_table(mine, w[1], (int32_t)w[2], (int32_t)w[3], (int32_t)w[4], (int32_t)w[5],
+                                                     (int32_t)w[6], (int32_t)w[7], ok);
+      const uint32_t bad = __ballot_sync(0xffffffffu, !ok);
+      int ev;                                                     // slot to handle on its own (32 = none)
+      if (bad) { ev = __ffs(bad) - 1; bits = __shfl_sync(0xffffffffu, mine, ev); }
+      else { ev = f; bits = acc; }
+      if (ev < 32) {
+        uint32_t sw[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) sw[k] = __shfl_sync(0xffffffffu, w[k], ev);
+        if (bad || !xsum::apply_segment(bits, sw)) bits = serial(bits, (long long)b * 32 + ev);
+      }
+      cur = ev + 1;
     }
     __syncwarp();
   }
