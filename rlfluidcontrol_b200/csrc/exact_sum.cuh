@@ -161,6 +161,50 @@ XS_HD void build_segment(Get get, int cnt, double pred_start, uint32_t* slot) {
   else { slot[0] = kSplit; run.store(slot + 9); }
 }
 
+// ---- composition of tables (used to summarise a whole stretch of plain segments in one table) ----
+// A table half (one start parity) that can never apply is normalised to D = 0, lo = kNever, hi = -kNever, so
+// that composing it further cannot overflow or turn it valid again.
+constexpr int32_t kNever = 0x40000000;
+XS_HD void normalise_half(int32_t& D, int32_t& lo, int32_t& hi) {
+  // a table that applies moves the significand by less than 2^24; lo > hi is the empty interval
+  if (lo > hi || D >= (int32_t)0x1000000 || D <= -(int32_t)0x1000000) { D = 0; lo = kNever; hi = -kNever; }
+}
+// w = [key, D0, D1, lo0, hi0, lo1, hi1]
+XS_HD void normalise_table(uint32_t* w) {
+  if (w[0] == kAnyKey) return;
+  int32_t D0 = (int32_t)w[1], D1 = (int32_t)w[2], lo0 = (int32_t)w[3], hi0 = (int32_t)w[4], lo1 = (int32_t)w[5],
+          hi1 = (int32_t)w[6];
+  normalise_half(D0, lo0, hi0);
+  normalise_half(D1, lo1, hi1);
+  w[1] = (uint32_t)D0; w[2] = (uint32_t)D1; w[3] = (uint32_t)lo0; w[4] = (uint32_t)hi0; w[5] = (uint32_t)lo1; w[6] = (uint32_t)hi1;
+}
+// one start parity of (f then g): the half of g that follows is chosen by the parity f leaves behind
+XS_HD void compose_half(bool same, int32_t fD, int32_t flo, int32_t fhi, int32_t gD0, int32_t gD1, int32_t glo0, int32_t ghi0,
+                        int32_t glo1, int32_t ghi1, int32_t& D, int32_t& lo, int32_t& hi) {
+  const bool odd = (fD & 1) != 0;
+  const int32_t gD = odd ? gD1 : gD0, glo = odd ? glo1 : glo0, ghi = odd ? ghi1 : ghi0;
+  const bool dead = !same || flo == kNever || glo == kNever;
+  const int32_t l2 = glo - fD, u2 = ghi - fD;
+  D = fD + gD;
+  lo = flo > l2 ? flo : l2;
+  hi = fhi < u2 ? fhi : u2;
+  if (dead) { lo = kNever; hi = -kNever; }
+  normalise_half(D, lo, hi);
+}
+// g <- (f then g): the additions of f followed by those of g.  Both normalised; the result is normalised.
+XS_HD void compose_tables(const uint32_t* f, uint32_t* g) {
+  if (f[0] == kAnyKey) return;
+  if (g[0] == kAnyKey) { for (int k = 0; k < 7; k++) g[k] = f[k]; return; }
+  const bool same = f[0] == g[0];                    // a table only follows another inside the same binade
+  const int32_t gD0 = (int32_t)g[1], gD1 = (int32_t)g[2], glo0 = (int32_t)g[3], ghi0 = (int32_t)g[4], glo1 = (int32_t)g[5],
+                ghi1 = (int32_t)g[6];
+  int32_t D0, lo0, hi0, D1, lo1, hi1;
+  compose_half(same, (int32_t)f[1], (int32_t)f[3], (int32_t)f[4], gD0, gD1, glo0, ghi0, glo1, ghi1, D0, lo0, hi0);
+  compose_half(same, (int32_t)f[2], (int32_t)f[5], (int32_t)f[6], gD1, gD0, glo1, ghi1, glo0, ghi0, D1, lo1, hi1);
+  g[0] = f[0];
+  g[1] = (uint32_t)D0; g[2] = (uint32_t)D1; g[3] = (uint32_t)lo0; g[4] = (uint32_t)hi0; g[5] = (uint32_t)lo1; g[6] = (uint32_t)hi1;
+}
+
 // Advance the accumulator over one summarised segment.  Returns true when the summary applied; false = the
 // caller must redo the segment serially from `bits` (which is left untouched in that case).
 XS_HD bool apply_segment(uint32_t& bits, const uint32_t* slot) {

@@ -32,7 +32,7 @@ k_xsum_totals(const __grid_constant__ SolverParams q) {
   const float* p = q.lev[0].x + (size_t)e * q.stride;
   double s = 0.0;
   XsCursor cur(base + t, len, q.P);
-#pragma unroll 4
+#pragma unroll 16
   for (int u = 0; u < xsum::kSeg; u++) {
     if (base + t + (long long)u * kXsThreads < N) s += (double)p[cur.off()];
     cur.advance(kXsThreads);
@@ -59,7 +59,7 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
   const float* p = q.lev[0].x + (size_t)e * q.stride;
   {
     XsCursor cur(base + t, len, q.P);
-#pragma unroll 4
+#pragma unroll 8
     for (int u = 0; u < xsum::kSeg; u++) {
       const int kl = t + u * kXsThreads;                          // local index: segment kl / 32, element kl % 32
       buf[(kl >> 5) * kXsPad + (kl & 31)] = (base + kl < N) ? p[cur.off()] : 0.f;
@@ -93,31 +93,72 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
   double pred = base_pred;
   for (int w = 0; w < warp; w++) pred += wsum[w];
   pred += incl - ssum;
+  uint32_t slot[xsum::kSlotWords];
   if (cnt > 0) {
-    uint32_t slot[xsum::kSlotWords];
     xsum::build_segment([&](int k) { return seg[k]; }, cnt, pred, slot);
+  } else {                                                        // past the end: an empty table
+#pragma unroll
+    for (int w = 0; w < xsum::kSlotWords; w++) slot[w] = 0u;
+    slot[0] = xsum::kOne; slot[1] = xsum::kAnyKey;
+  }
+  // Stretch tables: inside the warp (= one batch of 32 slots of the serial pass), every plain slot also gets the
+  // composition of all plain tables from the start of its stretch up to itself (words 8..14, free in a plain
+  // slot), so the serial pass crosses a whole stretch with one table.  Kogge-Stone scan, segmented at the
+  // non-plain slots.
+  {
+    const bool plain = slot[0] == xsum::kOne;
+    if (plain) xsum::normalise_table(slot + 1);
+    const uint32_t pm = __ballot_sync(0xffffffffu, plain);
+    // plain slots directly below this lane: distance to the start of the stretch
+    const uint32_t below = ~pm & ((1u << lane) - 1u);
+    const int start = below ? 32 - __clz(below) : 0;
+    const int dist = lane - start;
+    uint32_t acc[7];
+#pragma unroll
+    for (int w = 0; w < 7; w++) acc[w] = slot[1 + w];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t prev[7];
+#pragma unroll
+      for (int w = 0; w < 7; w++) prev[w] = __shfl_up_sync(0xffffffffu, acc[w], o);
+      if (plain && dist >= o) xsum::compose_tables(prev, acc);
+    }
+    if (plain) {
+#pragma unroll
+      for (int w = 0; w < 7; w++) slot[8 + w] = acc[w];
+    }
+  }
+  if (g < q.xs_nseg) {
     uint4* out = reinterpret_cast<uint4*>(q.xs_slots + ((size_t)e * q.xs_nseg + g) * xsum::kSlotWords);
 #pragma unroll
     for (int w = 0; w < 4; w++) out[w] = make_uint4(slot[4 * w], slot[4 * w + 1], slot[4 * w + 2], slot[4 * w + 3]);
   }
 }
 
-// Serial pass.  One warp per environment; lane L holds summary 32 b + L of batch b in registers.  Summaries of
-// type kOne only need  bits += (bits & 1) ? D1 : D0  on the critical path (about two dependent integer
-// operations), so the warp first runs that chain over a stretch of slots -- every lane keeps the accumulator
-// its own slot started from -- and then all lanes check their slot's validity condition at once.  Anything else
-// (a split summary, a serial one, a summary whose condition fails) is an "event" handled on its own before the
-// chain resumes behind it.
+// Serial pass.  One warp per environment; lane L holds summary 32 b + L of batch b (registers + a shared-memory
+// copy for broadcast reads).  A stretch of plain slots is crossed with the stretch table of its last slot; a
+// slot that is not plain (split / serial) is an event handled on its own.  If a stretch table does not apply,
+// the stretch is walked slot by slot (chain of  bits += (bits & 1) ? D1 : D0,  then all lanes check their own
+// slot's condition at once) and the first slot whose own table fails is redone as 32 float additions.
+constexpr int kXsSlotPad = 20;    // words per slot in shared memory (conflict-free 16-byte stores)
+constexpr int kXsRawPf = 4;       // serial slots per batch whose elements are prefetched
+
 __global__ void __launch_bounds__(32)
 k_xsum_chain(const __grid_constant__ SolverParams q) {
-  __shared__ __align__(16) uint2 sD[2][40];                       // (D0, D1 - D0) of the batch, broadcast to the chain
+  __shared__ __align__(16) uint32_t sbuf[2][32 * kXsSlotPad];
   const int e = blockIdx.x, lane = threadIdx.x;
-  const int len = q.m - 2, P = q.P;
-  const long long N = (long long)(q.n - 2) * len;
+  const unsigned len = (unsigned)(q.m - 2), P = (unsigned)q.P;
+  const unsigned N = (unsigned)(q.n - 2) * len;                   // rlfc_env_create rejects grids beyond 2^31 cells
   const int nseg = q.xs_nseg;
   const float* p = q.lev[0].x + (size_t)e * q.stride;
   const uint4* slots = reinterpret_cast<const uint4*>(q.xs_slots + (size_t)e * nseg * xsum::kSlotWords);
+  auto element = [&](unsigned g) {                                 // this lane's element of segment g (0 past the end)
+    const unsigned K = g * xsum::kSeg + lane;
+    return K < N ? p[(size_t)(1u + K / len) * P + 1u + K % len] : 0.f;
+  };
   uint4 nxt[4];
+  float rawn[kXsRawPf];
+  uint32_t sern = 0u;
   auto fetch = [&](int b) {
     const int g = b * 32 + lane;
     if (g < nseg) {
@@ -128,60 +169,111 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
       nxt[1] = nxt[2] = nxt[3] = make_uint4(0u, 0u, 0u, 0u);
     }
   };
-  // genuine serial additions of segment g from accumulator `bits` (warp-uniform)
-  auto serial = [&](uint32_t bits, long long g) {
-    const long long K0 = g * xsum::kSeg, left = N - K0;
-    const int cnt = left >= xsum::kSeg ? xsum::kSeg : (left > 0 ? (int)left : 0);
-    float v = 0.f;
-    if (lane < cnt) {
-      const long long K = K0 + lane;
-      v = p[(size_t)(1 + (int)(K / len)) * P + 1 + (int)(K % len)];
+  // elements of the first kXsRawPf serial slots of batch b (known once its summaries have arrived)
+  auto fetch_raw = [&](int b, uint32_t sermask) {
+#pragma unroll
+    for (int i = 0; i < kXsRawPf; i++) {
+      rawn[i] = 0.f;
+      if (sermask) {
+        const int k = __ffs(sermask) - 1;
+        sermask &= sermask - 1u;
+        rawn[i] = element((unsigned)(b * 32 + k));
+      }
     }
+  };
+  // genuine serial additions of one segment (warp-uniform): lane u holds element u in v
+  auto serial = [&](uint32_t bits, float v, int cnt) {
+    float el[xsum::kSeg];
+#pragma unroll
+    for (int u = 0; u < xsum::kSeg; u++) el[u] = __shfl_sync(0xffffffffu, v, u);
     float s = xsum::u2f(bits);
-    for (int u = 0; u < cnt; u++) s += __shfl_sync(0xffffffffu, v, u);
+#pragma unroll
+    for (int u = 0; u < xsum::kSeg; u++) s = (u < cnt) ? s + el[u] : s;
     return xsum::f2u(s);
   };
   const int nb = (nseg + 31) / 32;
   fetch(0);
+  sern = __ballot_sync(0xffffffffu, nxt[0].x == xsum::kSerial);
+  fetch_raw(0, sern);
   uint32_t bits = 0u;                                             // s = +0.f
   for (int b = 0; b < nb; b++) {
-    uint32_t w[16];
+    uint32_t w[8];                                                // own plain table (event slots are re-read from smem)
+    w[0] = nxt[0].x; w[1] = nxt[0].y; w[2] = nxt[0].z; w[3] = nxt[0].w;
+    w[4] = nxt[1].x; w[5] = nxt[1].y; w[6] = nxt[1].z; w[7] = nxt[1].w;
+    uint32_t* sb = sbuf[b & 1];
 #pragma unroll
-    for (int k = 0; k < 4; k++) { w[4 * k] = nxt[k].x; w[4 * k + 1] = nxt[k].y; w[4 * k + 2] = nxt[k].z; w[4 * k + 3] = nxt[k].w; }
-    if (b + 1 < nb) fetch(b + 1);                                 // in flight during the chain
-    uint2* sd = sD[b & 1];
+    for (int k = 0; k < 4; k++) *reinterpret_cast<uint4*>(sb + lane * kXsSlotPad + 4 * k) = nxt[k];
+    float raw[kXsRawPf];
+#pragma unroll
+    for (int i = 0; i < kXsRawPf; i++) raw[i] = rawn[i];
+    const uint32_t sermask = sern;
     const bool plain = w[0] == xsum::kOne;
-    sd[lane] = (plain && w[1] != xsum::kAnyKey) ? make_uint2(w[2], w[3] - w[2]) : make_uint2(0u, 0u);
     const uint32_t special = __ballot_sync(0xffffffffu, !plain);
     __syncwarp();
+    if (b + 1 < nb) {                                             // next batch in flight during this one
+      fetch(b + 1);
+      sern = __ballot_sync(0xffffffffu, nxt[0].x == xsum::kSerial);
+      fetch_raw(b + 1, sern);
+    }
+    auto redo = [&](int k) {                                      // slot k of this batch as 32 float additions
+      const unsigned g = (unsigned)(b * 32 + k);
+      const unsigned K0 = g * xsum::kSeg;
+      const int cnt = K0 >= N ? 0 : (N - K0 >= (unsigned)xsum::kSeg ? xsum::kSeg : (int)(N - K0));
+      const int idx = __popc(sermask & ((1u << k) - 1u));
+      float v;
+      if (((sermask >> k) & 1u) && idx < kXsRawPf) {
+        v = raw[0];
+#pragma unroll
+        for (int i = 1; i < kXsRawPf; i++) v = (idx == i) ? raw[i] : v;
+      } else {
+        v = element(g);
+      }
+      bits = serial(bits, v, cnt);
+    };
     int cur = 0;
+    bool fresh = true;                                            // cur is the first slot of its stretch
     while (cur < 32) {
       const uint32_t rest = special >> cur;
       const int f = rest ? cur + __ffs(rest) - 1 : 32;            // next slot that is not a plain table
-      uint32_t acc = bits, mine = bits;
-      for (int k0 = cur; k0 < f; k0 += 4) {
-        const uint2 d0 = sd[k0], d1 = sd[k0 + 1], d2 = sd[k0 + 2], d3 = sd[k0 + 3];
-        mine = (lane == k0) ? acc : mine;
-        acc = (acc + d0.x) + (acc & 1u) * d0.y;
-        if (k0 + 1 < f) { mine = (lane == k0 + 1) ? acc : mine; acc = (acc + d1.x) + (acc & 1u) * d1.y; }
-        if (k0 + 2 < f) { mine = (lane == k0 + 2) ? acc : mine; acc = (acc + d2.x) + (acc & 1u) * d2.y; }
-        if (k0 + 3 < f) { mine = (lane == k0 + 3) ? acc : mine; acc = (acc + d3.x) + (acc & 1u) * d3.y; }
+      if (f > cur) {
+        bool crossed = false;
+        if (fresh) {                                              // the whole stretch in one table
+          const uint4 t0 = *reinterpret_cast<const uint4*>(sb + (f - 1) * kXsSlotPad + 8);
+          const uint4 t1 = *reinterpret_cast<const uint4*>(sb + (f - 1) * kXsSlotPad + 12);
+          bool ok = true;
+          const uint32_t nb_ = xsum::apply_table(bits, t0.x, (int32_t)t0.y, (int32_t)t0.z, (int32_t)t0.w, (int32_t)t1.x,
+                                                 (int32_t)t1.y, (int32_t)t1.z, ok);
+          if (ok) { bits = nb_; crossed = true; }
+        }
+        if (!crossed) {                                           // slot by slot
+          uint32_t acc = bits, mine = bits;
+          for (int k0 = cur; k0 < f; k0++) {
+            const uint2 d = *reinterpret_cast<const uint2*>(sb + k0 * kXsSlotPad + 2);   // (D0, D1); 0, 0 for an empty table
+            mine = (lane == k0) ? acc : mine;
+            acc += (acc & 1u) ? d.y : d.x;
+          }
+          bool ok = true;
+          if (lane >= cur && lane < f)
+            xsum::apply_table(mine, w[1], (int32_t)w[2], (int32_t)w[3], (int32_t)w[4], (int32_t)w[5], (int32_t)w[6],
+                              (int32_t)w[7], ok);
+          const uint32_t bad = __ballot_sync(0xffffffffu, !ok);
+          if (bad) {
+            const int g = __ffs(bad) - 1;
+            bits = __shfl_sync(0xffffffffu, mine, g);
+            redo(g);
+            cur = g + 1;
+            fresh = false;
+            continue;
+          }
+          bits = acc;
+        }
       }
-      // every lane of the stretch checks that its table really applied to the accumulator it started from
-      bool ok = true;
-      if (lane >= cur && lane < f) xsum::apply_table(mine, w[1], (int32_t)w[2], (int32_t)w[3], (int32_t)w[4], (int32_t)w[5],
-                                                     (int32_t)w[6], (int32_t)w[7], ok);
-      const uint32_t bad = __ballot_sync(0xffffffffu, !ok);
-      int ev;                                                     // slot to handle on its own (32 = none)
-      if (bad) { ev = __ffs(bad) - 1; bits = __shfl_sync(0xffffffffu, mine, ev); }
-      else { ev = f; bits = acc; }
-      if (ev < 32) {
-        uint32_t sw[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) sw[k] = __shfl_sync(0xffffffffu, w[k], ev);
-        if (bad || !xsum::apply_segment(bits, sw)) bits = serial(bits, (long long)b * 32 + ev);
+      if (f < 32) {                                               // the event slot
+        const uint32_t* sw = sb + f * kXsSlotPad;
+        if (!xsum::apply_segment(bits, sw)) redo(f);
       }
-      cur = ev + 1;
+      cur = f + 1;
+      fresh = true;
     }
     __syncwarp();
   }

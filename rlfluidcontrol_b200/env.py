@@ -7,12 +7,14 @@ clientCFD.draw() drives it (clientCFD.pde:35-55).  All numerics run in librlfc.s
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
-_LIB_PATH = _PKG / "librlfc.so"
+# RLFC_LIBRARY selects another build of the same library (e.g. an instrumented one made by tools/); never a fallback
+_LIB_PATH = Path(os.environ["RLFC_LIBRARY"]).resolve() if os.environ.get("RLFC_LIBRARY") else _PKG / "librlfc.so"
 NUM_PROBES = 32
 
 

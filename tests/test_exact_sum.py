@@ -33,7 +33,7 @@ def xs():
 
 def both(L, a, noise=0.0):
     a = np.ascontiguousarray(a, np.float32)
-    st = (C.c_long * 4)()
+    st = (C.c_long * 6)()
     s = np.float32(L.xs_serial(a.ctypes.data_as(FP), a.size))
     p = np.float32(L.xs_parallel(a.ctypes.data_as(FP), a.size, noise, st))
     same = s.tobytes() == p.tobytes() or (np.isnan(s) and np.isnan(p))
@@ -74,7 +74,7 @@ def adversarial(kind, n, rng):
 
 def test_matches_serial_loop_on_adversarial_data(xs):
     rng = np.random.default_rng(20261017)
-    rejected = 0
+    rejected = crossed = walked = 0
     for trial in range(1100):
         n = int(rng.integers(1, 6000))
         a = adversarial(trial % 11, n, rng)
@@ -82,7 +82,10 @@ def test_matches_serial_loop_on_adversarial_data(xs):
             same, s, p, st = both(xs, a, noise)
             assert same, (trial, trial % 11, n, noise, s, p, st)
             rejected += st[3]
+            crossed += st[4]
+            walked += st[5]
     assert rejected > 0, "the validity check of the summaries was never exercised"
+    assert crossed > 0 and walked > 0, "stretch tables / the slot-by-slot walk were never exercised"
 
 
 def test_pressure_fields_of_the_oracle(xs, oracle, init_state):
