@@ -13,15 +13,46 @@ constexpr int kXsThreads = 256;
 constexpr int kXsChunk = kXsThreads * xsum::kSeg;       // additions per CTA
 constexpr int kXsPad = xsum::kSeg + 1;                  // shared-memory stride of a segment (bank-conflict free)
 
-// serial index K (i-major over the interior) -> offset in the pitched array
+// serial index K (i-major over the interior) -> offset in the pitched array.  advance() is branch-free when a
+// row is at least half a CTA wide (WIDE: at most two row ends per stride of kXsThreads elements), so that the
+// loads of an unrolled loop are not separated by control flow.
+template <bool WIDE>
 struct XsCursor {
   int i, j, len, P;
   __device__ __forceinline__ XsCursor(long long K, int len_, int P_) : len(len_), P(P_) {
-    i = 1 + (int)(K / len_); j = 1 + (int)(K % len_);
+    const unsigned k = (unsigned)K;                               // rlfc_env_create rejects grids beyond 2^31 cells
+    i = 1 + (int)(k / (unsigned)len_); j = 1 + (int)(k % (unsigned)len_);
   }
   __device__ __forceinline__ size_t off() const { return (size_t)i * P + j; }
-  __device__ __forceinline__ void advance(int d) { j += d; while (j > len) { j -= len; i++; } }
+  __device__ __forceinline__ void advance() {
+    j += kXsThreads;
+    if (WIDE) {
+      const bool a = j > len; j -= a ? len : 0; i += a;
+      const bool b = j > len; j -= b ? len : 0; i += b;
+    } else {
+      while (j > len) { j -= len; i++; }
+    }
+  }
 };
+
+template <bool WIDE>
+__device__ __forceinline__ double xs_chunk_total(const SolverParams& q, const float* p, long long base, long long N, int t) {
+  double s = 0.0;
+  XsCursor<WIDE> cur(base + t, q.m - 2, q.P);
+  const unsigned left = (unsigned)(N - base);                     // elements of this chunk and beyond (N > base)
+#pragma unroll 1
+  for (int h = 0; h < xsum::kSeg; h += 8) {                       // 8 independent loads in flight per thread
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      v[u] = ((unsigned)(t + (h + u) * kXsThreads) < left) ? p[cur.off()] : 0.f;
+      cur.advance();
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) s += (double)v[u];
+  }
+  return s;
+}
 
 __global__ void __launch_bounds__(kXsThreads)
 k_xsum_totals(const __grid_constant__ SolverParams q) {
@@ -30,13 +61,7 @@ k_xsum_totals(const __grid_constant__ SolverParams q) {
   const int len = q.m - 2;
   const long long N = (long long)(q.n - 2) * len, base = (long long)c * kXsChunk;
   const float* p = q.lev[0].x + (size_t)e * q.stride;
-  double s = 0.0;
-  XsCursor cur(base + t, len, q.P);
-#pragma unroll 16
-  for (int u = 0; u < xsum::kSeg; u++) {
-    if (base + t + (long long)u * kXsThreads < N) s += (double)p[cur.off()];
-    cur.advance(kXsThreads);
-  }
+  double s = (2 * len >= kXsThreads) ? xs_chunk_total<true>(q, p, base, N, t) : xs_chunk_total<false>(q, p, base, N, t);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
   if ((t & 31) == 0) wsum[t >> 5] = s;
@@ -45,6 +70,17 @@ k_xsum_totals(const __grid_constant__ SolverParams q) {
     double tot = 0.0;
     for (int w = 0; w < kXsThreads / 32; w++) tot += wsum[w];
     q.xs_ctot[(size_t)e * q.xs_nchunks + c] = tot;
+  }
+}
+
+template <bool WIDE>
+__device__ __forceinline__ void xs_fill(const SolverParams& q, const float* p, long long base, long long N, int t, float* buf) {
+  XsCursor<WIDE> cur(base + t, q.m - 2, q.P);
+#pragma unroll 8
+  for (int u = 0; u < xsum::kSeg; u++) {
+    const int kl = t + u * kXsThreads;                            // local index: segment kl / 32, element kl % 32
+    buf[(kl >> 5) * kXsPad + (kl & 31)] = (base + kl < N) ? p[cur.off()] : 0.f;
+    cur.advance();
   }
 }
 
@@ -57,15 +93,8 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
   const int len = q.m - 2;
   const long long N = (long long)(q.n - 2) * len, base = (long long)c * kXsChunk;
   const float* p = q.lev[0].x + (size_t)e * q.stride;
-  {
-    XsCursor cur(base + t, len, q.P);
-#pragma unroll 8
-    for (int u = 0; u < xsum::kSeg; u++) {
-      const int kl = t + u * kXsThreads;                          // local index: segment kl / 32, element kl % 32
-      buf[(kl >> 5) * kXsPad + (kl & 31)] = (base + kl < N) ? p[cur.off()] : 0.f;
-      cur.advance(kXsThreads);
-    }
-  }
+  if (2 * len >= kXsThreads) xs_fill<true>(q, p, base, N, t, buf);
+  else xs_fill<false>(q, p, base, N, t, buf);
   if (t == 0) {
     double b = 0.0;
     const double* ct = q.xs_ctot + (size_t)e * q.xs_nchunks;
@@ -140,12 +169,16 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
 // slot that is not plain (split / serial) is an event handled on its own.  If a stretch table does not apply,
 // the stretch is walked slot by slot (chain of  bits += (bits & 1) ? D1 : D0,  then all lanes check their own
 // slot's condition at once) and the first slot whose own table fails is redone as 32 float additions.
-constexpr int kXsSlotPad = 20;    // words per slot in shared memory (conflict-free 16-byte stores)
+constexpr int kXsRing = 4;        // batches of summaries in the shared-memory ring (cp.async, 3 batches ahead)
 constexpr int kXsRawPf = 4;       // serial slots per batch whose elements are prefetched
+
+__device__ __forceinline__ void xs_cp16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
 
 __global__ void __launch_bounds__(32)
 k_xsum_chain(const __grid_constant__ SolverParams q) {
-  __shared__ __align__(16) uint32_t sbuf[2][32 * kXsSlotPad];
+  __shared__ __align__(16) uint32_t ring[kXsRing][32 * xsum::kSlotWords];
   const int e = blockIdx.x, lane = threadIdx.x;
   const unsigned len = (unsigned)(q.m - 2), P = (unsigned)q.P;
   const unsigned N = (unsigned)(q.n - 2) * len;                   // rlfc_env_create rejects grids beyond 2^31 cells
@@ -156,30 +189,18 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
     const unsigned K = g * xsum::kSeg + lane;
     return K < N ? p[(size_t)(1u + K / len) * P + 1u + K % len] : 0.f;
   };
-  uint4 nxt[4];
-  float rawn[kXsRawPf];
-  uint32_t sern = 0u;
+  const int nb = (nseg + 31) / 32;
+  // batch b -> ring slot b % kXsRing; every lane copies its own summary (one commit group per batch, also when empty)
   auto fetch = [&](int b) {
-    const int g = b * 32 + lane;
-    if (g < nseg) {
+    if (b < nb) {
+      uint32_t* dst = ring[b % kXsRing] + lane * xsum::kSlotWords;
+      const int g = b * 32 + lane;
+      if (g < nseg) {                                             // (lanes past the last summary are never looked at)
 #pragma unroll
-      for (int w = 0; w < 4; w++) nxt[w] = slots[(size_t)g * 4 + w];
-    } else {                                                      // past the end: an empty table
-      nxt[0] = make_uint4(xsum::kOne, xsum::kAnyKey, 0u, 0u);
-      nxt[1] = nxt[2] = nxt[3] = make_uint4(0u, 0u, 0u, 0u);
-    }
-  };
-  // elements of the first kXsRawPf serial slots of batch b (known once its summaries have arrived)
-  auto fetch_raw = [&](int b, uint32_t sermask) {
-#pragma unroll
-    for (int i = 0; i < kXsRawPf; i++) {
-      rawn[i] = 0.f;
-      if (sermask) {
-        const int k = __ffs(sermask) - 1;
-        sermask &= sermask - 1u;
-        rawn[i] = element((unsigned)(b * 32 + k));
+        for (int w = 0; w < 4; w++) xs_cp16(dst + 4 * w, slots + (size_t)g * 4 + w);
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
   // genuine serial additions of one segment (warp-uniform): lane u holds element u in v
   auto serial = [&](uint32_t bits, float v, int cnt) {
@@ -191,29 +212,43 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
     for (int u = 0; u < xsum::kSeg; u++) s = (u < cnt) ? s + el[u] : s;
     return xsum::f2u(s);
   };
-  const int nb = (nseg + 31) / 32;
-  fetch(0);
-  sern = __ballot_sync(0xffffffffu, nxt[0].x == xsum::kSerial);
-  fetch_raw(0, sern);
+  fetch(0); fetch(1); fetch(2);
+  float rawn[kXsRawPf];                                           // elements of the next batch's first serial slots
+  uint32_t sern = 0u;
+#pragma unroll
+  for (int i = 0; i < kXsRawPf; i++) rawn[i] = 0.f;
   uint32_t bits = 0u;                                             // s = +0.f
   for (int b = 0; b < nb; b++) {
-    uint32_t w[8];                                                // own plain table (event slots are re-read from smem)
-    w[0] = nxt[0].x; w[1] = nxt[0].y; w[2] = nxt[0].z; w[3] = nxt[0].w;
-    w[4] = nxt[1].x; w[5] = nxt[1].y; w[6] = nxt[1].z; w[7] = nxt[1].w;
-    uint32_t* sb = sbuf[b & 1];
-#pragma unroll
-    for (int k = 0; k < 4; k++) *reinterpret_cast<uint4*>(sb + lane * kXsSlotPad + 4 * k) = nxt[k];
+    fetch(b + 3);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");          // batches <= b + 1 have landed
+    __syncwarp();
+    const uint32_t* sb = ring[b % kXsRing];
+    uint32_t w[8];                                                // own table (event slots are read from the ring)
+    {
+      const uint4 a0 = *reinterpret_cast<const uint4*>(sb + lane * xsum::kSlotWords);
+      const uint4 a1 = *reinterpret_cast<const uint4*>(sb + lane * xsum::kSlotWords + 4);
+      w[0] = a0.x; w[1] = a0.y; w[2] = a0.z; w[3] = a0.w; w[4] = a1.x; w[5] = a1.y; w[6] = a1.z; w[7] = a1.w;
+    }
+    const int ns = min(32, nseg - b * 32);                        // summaries in this batch
+    const bool plain = w[0] == xsum::kOne;
+    const uint32_t special = __ballot_sync(0xffffffffu, !plain || lane >= ns);
     float raw[kXsRawPf];
 #pragma unroll
     for (int i = 0; i < kXsRawPf; i++) raw[i] = rawn[i];
-    const uint32_t sermask = sern;
-    const bool plain = w[0] == xsum::kOne;
-    const uint32_t special = __ballot_sync(0xffffffffu, !plain);
-    __syncwarp();
-    if (b + 1 < nb) {                                             // next batch in flight during this one
-      fetch(b + 1);
-      sern = __ballot_sync(0xffffffffu, nxt[0].x == xsum::kSerial);
-      fetch_raw(b + 1, sern);
+    const uint32_t sermask = (b == 0) ? 0u : sern;                // batch 0 has no prefetch: its serial slots load on demand
+    if (b + 1 < nb) {                                             // elements of the next batch's serial slots, used one batch later
+      sern = __ballot_sync(0xffffffffu, (b + 1) * 32 + lane < nseg &&
+                                            ring[(b + 1) % kXsRing][lane * xsum::kSlotWords] == xsum::kSerial);
+      uint32_t m = sern;
+#pragma unroll
+      for (int i = 0; i < kXsRawPf; i++) {
+        rawn[i] = 0.f;
+        if (m) {
+          const int k = __ffs(m) - 1;
+          m &= m - 1u;
+          rawn[i] = element((unsigned)((b + 1) * 32 + k));
+        }
+      }
     }
     auto redo = [&](int k) {                                      // slot k of this batch as 32 float additions
       const unsigned g = (unsigned)(b * 32 + k);
@@ -232,14 +267,14 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
     };
     int cur = 0;
     bool fresh = true;                                            // cur is the first slot of its stretch
-    while (cur < 32) {
+    while (cur < ns) {
       const uint32_t rest = special >> cur;
-      const int f = rest ? cur + __ffs(rest) - 1 : 32;            // next slot that is not a plain table
+      const int f = rest ? cur + __ffs(rest) - 1 : 32;            // next slot that is not a plain table (or the batch end)
       if (f > cur) {
         bool crossed = false;
         if (fresh) {                                              // the whole stretch in one table
-          const uint4 t0 = *reinterpret_cast<const uint4*>(sb + (f - 1) * kXsSlotPad + 8);
-          const uint4 t1 = *reinterpret_cast<const uint4*>(sb + (f - 1) * kXsSlotPad + 12);
+          const uint4 t0 = *reinterpret_cast<const uint4*>(sb + (f - 1) * xsum::kSlotWords + 8);
+          const uint4 t1 = *reinterpret_cast<const uint4*>(sb + (f - 1) * xsum::kSlotWords + 12);
           bool ok = true;
           const uint32_t nb_ = xsum::apply_table(bits, t0.x, (int32_t)t0.y, (int32_t)t0.z, (int32_t)t0.w, (int32_t)t1.x,
                                                  (int32_t)t1.y, (int32_t)t1.z, ok);
@@ -248,7 +283,7 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
         if (!crossed) {                                           // slot by slot
           uint32_t acc = bits, mine = bits;
           for (int k0 = cur; k0 < f; k0++) {
-            const uint2 d = *reinterpret_cast<const uint2*>(sb + k0 * kXsSlotPad + 2);   // (D0, D1); 0, 0 for an empty table
+            const uint2 d = *reinterpret_cast<const uint2*>(sb + k0 * xsum::kSlotWords + 2);   // (D0, D1); 0, 0 for an empty table
             mine = (lane == k0) ? acc : mine;
             acc += (acc & 1u) ? d.y : d.x;
           }
@@ -268,14 +303,14 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
           bits = acc;
         }
       }
-      if (f < 32) {                                               // the event slot
-        const uint32_t* sw = sb + f * kXsSlotPad;
-        if (!xsum::apply_segment(bits, sw)) redo(f);
+      if (f < ns) {                                               // the event slot
+        if (!xsum::apply_segment(bits, sb + f * xsum::kSlotWords)) redo(f);
       }
       cur = f + 1;
       fresh = true;
     }
     __syncwarp();
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (lane == 0) q.sc.psum[e] = xsum::u2f(bits);
 }

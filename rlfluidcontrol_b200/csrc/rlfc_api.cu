@@ -469,6 +469,8 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   *out = nullptr;
   if (cfg->n_envs < 1) return fail(RLFC_EINVAL, "n_envs must be >= 1");
   if (!cfg->exact) return fail(RLFC_EINVAL, "only exact mode is implemented");
+  if ((long long)cfg->resolution * cfg->x_lengths * cfg->resolution * cfg->y_lengths >= (1ll << 31))
+    return fail(RLFC_EINVAL, "grid too large (the kernels index cells with 32 bits)");
   if (cfg->substeps < 1 || cfg->mg_max_iters < 1) return fail(RLFC_EINVAL, "substeps and mg_max_iters must be >= 1");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
