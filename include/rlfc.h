@@ -105,6 +105,11 @@ int  rlfc_env_set_fields(rlfc_env *env, int e, const float *ux, const float *uy,
 /* Field.sum() of every environment's pressure field (Field.pde:311-318: serial float accumulation over the
    interior, i-major): sums[n_envs].  Runs the same device path the projection uses (VectorField.pde:136). */
 int  rlfc_env_field_sum(rlfc_env *env, float *sums);
+/* Counters of the last Field.sum evaluation of every environment (the projection's or rlfc_env_field_sum's),
+   stats[n_envs][8]: [0] batches (32 segment summaries) crossed by their condensed record, [1] batches walked
+   summary by summary, [2] record entries applied, [3] segments redone as 32 float additions; [4..7] reserved.
+   All zero with RLFC_PSUM=serial. */
+int  rlfc_env_field_sum_stats(rlfc_env *env, int *stats);
 
 /* Text checkpoint of one environment in the BDIM.write format (readable by BDIM.resume). */
 int  rlfc_env_save_bdim(rlfc_env *env, int e, const char *path);

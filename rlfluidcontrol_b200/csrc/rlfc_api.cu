@@ -684,10 +684,13 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     const long long N = (long long)(g.n - 2) * (g.m - 2);
     sp.xs_nseg = (int)((N + 31) / 32);
     sp.xs_nchunks = (sp.xs_nseg + 255) / 256;
-    sp.xs_ctot = nullptr; sp.xs_slots = nullptr;
+    sp.xs_nbatches = (sp.xs_nseg + 31) / 32;
+    sp.xs_ctot = nullptr; sp.xs_slots = nullptr; sp.xs_recs = nullptr;
+    TRY(E->dmalloc(&sp.xs_stats, (size_t)8 * B));
     if (!(ev && std::strcmp(ev, "serial") == 0)) {
       TRY(E->dmalloc(&sp.xs_ctot, (size_t)sp.xs_nchunks * B));
       TRY(E->dmalloc(&sp.xs_slots, (size_t)sp.xs_nseg * 16 * B));
+      TRY(E->dmalloc(&sp.xs_recs, (size_t)sp.xs_nbatches * 64 * B));
     }
   }
   TRY(E->dmalloc(&sp.sc.any_active, n_groups));
@@ -727,7 +730,11 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     v.sc.xi += 2 * e0; v.sc.t += e0; v.sc.force += 2 * e0; v.sc.probes += (size_t)e0 * RLFC_NUM_PROBES;
     v.sc.callLearn += e0; v.sc.Cd += e0; v.sc.Cl += e0; v.sc.obs += 2 * e0; v.sc.active += e0; v.sc.iters += 2 * e0;
     v.sc.psum += e0; v.sc.any_active += g;
-    if (v.xs_slots) { v.xs_ctot += (size_t)e0 * v.xs_nchunks; v.xs_slots += (size_t)e0 * v.xs_nseg * 16; }
+    if (v.xs_slots) {
+      v.xs_ctot += (size_t)e0 * v.xs_nchunks; v.xs_slots += (size_t)e0 * v.xs_nseg * 16;
+      v.xs_recs += (size_t)e0 * v.xs_nbatches * 64;
+    }
+    v.xs_stats += 8 * e0;
     const size_t o = (size_t)e0 * sp.stride;
     G.uAx = E->uAx + o; G.uAy = E->uAy + o; G.uBx = E->uBx + o; G.uBy = E->uBy + o; G.uCx = E->uCx + o; G.uCy = E->uCy + o;
     G.spB = G.sp;
@@ -919,6 +926,14 @@ int rlfc_env_field_sum(rlfc_env* E, float* sums) {
   E->launches += launch_psum(E->whole.sp, E->stream);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(sums, E->sp.sc.psum, E->sp.B * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaStreamSynchronize(E->stream));
+  return RLFC_OK;
+}
+
+int rlfc_env_field_sum_stats(rlfc_env* E, int* stats) {
+  if (!E || !stats) return fail(RLFC_EINVAL, "null argument");
+  CU(cudaSetDevice(E->device));
+  CU(cudaMemcpyAsync(stats, E->sp.xs_stats, (size_t)8 * E->sp.B * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
   CU(cudaStreamSynchronize(E->stream));
   return RLFC_OK;
 }

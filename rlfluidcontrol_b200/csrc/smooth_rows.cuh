@@ -45,7 +45,10 @@ namespace rlfc {
 
 constexpr int kRowsWarps = 8;
 constexpr int kRowsThreads = 32 * kRowsWarps;
-constexpr int kPF = 5;             // cp.async groups (steps) in flight
+#ifndef RLFC_KPF
+#define RLFC_KPF 5
+#endif
+constexpr int kPF = RLFC_KPF;      // bulk-copy groups (steps) in flight; at most 5 with 16 coefficient slots
 constexpr int kCoefShift = 4;
 constexpr int kCoefSlots = 1 << kCoefShift;     // coefficient-entry ring: entries t-10 .. t+kPF live at step t
 constexpr int kRSlots = 16;        // step-indexed ring of this lane's r values (stage 0 -> sweeps, increment)

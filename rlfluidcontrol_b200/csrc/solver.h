@@ -102,7 +102,9 @@ struct SolverParams {
   // Field.sum as segment summaries (exact_sum.cuh); xs_slots == nullptr selects the plain serial chain (k_psum)
   double *xs_ctot;          // [B][xs_nchunks] double-precision chunk totals
   unsigned *xs_slots;       // [B][xs_nseg][16] segment summaries
-  int xs_nseg, xs_nchunks;
+  unsigned *xs_recs;        // [B][xs_nbatches][64] batch records (32 summaries condensed)
+  int xs_nseg, xs_nchunks, xs_nbatches;
+  int *xs_stats;            // [B][8] counters of the last serial pass (rlfc_env_field_sum_stats)
   EnvScalars sc;
 };
 

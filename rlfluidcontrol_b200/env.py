@@ -73,6 +73,7 @@ def load_library():
     L.rlfc_env_get_time.argtypes = [vp, fp]
     L.rlfc_env_get_mg_iters.argtypes = [vp, ip]
     L.rlfc_env_field_sum.argtypes = [vp, fp]
+    L.rlfc_env_field_sum_stats.argtypes = [vp, ip]
     L.rlfc_env_get_static.argtypes = [vp, C.c_char_p, C.c_int, fp, ip, ip]
     L.rlfc_geometry_static.argtypes = [C.POINTER(Config), C.c_char_p, C.c_int, fp, ip, ip, ip]
     L.rlfc_env_num_levels.argtypes = [vp]
@@ -214,6 +215,12 @@ class AFCCylinderBatch:
         s = np.empty(self.n_envs, np.float32)
         self._check(self._L.rlfc_env_field_sum(self._h, _fp(s)), "rlfc_env_field_sum")
         return s
+
+    def field_sum_stats(self):
+        """Counters of the last Field.sum evaluation per env (see rlfc_env_field_sum_stats)."""
+        st = np.zeros((self.n_envs, 8), np.int32)
+        self._check(self._L.rlfc_env_field_sum_stats(self._h, st.ctypes.data_as(C.POINTER(C.c_int))), "rlfc_env_field_sum_stats")
+        return st
 
     @property
     def num_levels(self):

@@ -19,7 +19,7 @@ float xs_serial(const float* a, long n) {
 }
 
 // stats[0..2] = segments summarised as one table / split / serial, stats[3] = summaries rejected by the serial pass,
-// stats[4] = stretches crossed with one composed table, stats[5] = stretches walked slot by slot.
+// stats[4] = batches crossed by their record, stats[5] = batches walked summary by summary.
 // pred_noise perturbs the predicted accumulator (relative) to exercise wrong predictions.
 float xs_parallel(const float* a, long n, double pred_noise, long* stats) {
   const long nseg = (n + kSeg - 1) / kSeg;
@@ -45,54 +45,70 @@ float xs_parallel(const float* a, long n, double pred_noise, long* stats) {
     bits = f2u(s);
   };
   uint32_t bits = 0;   // s = +0.f
-  // batches of 32 slots, exactly as k_xsum_tables / k_xsum_chain organise them
+  // batches of 32 summaries, exactly as k_xsum_tables / k_xsum_chain organise them: a record of entries
+  // "table, then one float addition" per batch; any entry that does not apply -> the batch is walked summary by summary
+  const uint32_t ident[7] = {kAnyKey, 0u, 0u, (uint32_t)INT32_MIN, (uint32_t)INT32_MAX, (uint32_t)INT32_MIN, (uint32_t)INT32_MAX};
   for (long b0 = 0; b0 < nseg; b0 += 32) {
     uint32_t w[32][kSlotWords];
-    bool plain[32];
     for (int k = 0; k < 32; k++) {
       if (b0 + k < nseg) std::memcpy(w[k], &slots[(size_t)(b0 + k) * kSlotWords], sizeof(w[k]));
       else { std::memset(w[k], 0, sizeof(w[k])); w[k][0] = kOne; w[k][1] = kAnyKey; }
       stats[w[k][0]] += (b0 + k < nseg);
-      plain[k] = w[k][0] == kOne;
-      if (plain[k]) {                    // stretch table in words 8..14 (sequential composition; the device scans a tree)
-        normalise_table(w[k] + 1);
-        std::memcpy(w[k] + 8, w[k] + 1, 7 * sizeof(uint32_t));
-        if (k > 0 && plain[k - 1]) compose_tables(w[k - 1] + 8, w[k] + 8);
+      normalise_table(w[k] + 1);
+      if (w[k][0] == kSplit) normalise_table(w[k] + 9);
+    }
+    // record (sequential composition; the device scans a tree)
+    struct Entry { uint32_t t[7]; float raw; int serial_slot; };
+    std::vector<Entry> rec;
+    uint32_t C[7];
+    std::memcpy(C, ident, sizeof(C));
+    for (int k = 0; k < 32; k++) {
+      if (w[k][0] == kOne) {
+        uint32_t g[7]; std::memcpy(g, w[k] + 1, sizeof(g));
+        compose_tables(C, g); std::memcpy(C, g, sizeof(C));
+      } else {
+        Entry en; en.serial_slot = -1; en.raw = -0.f;
+        if (w[k][0] == kSplit) {
+          uint32_t g[7]; std::memcpy(g, w[k] + 1, sizeof(g));
+          compose_tables(C, g); std::memcpy(en.t, g, sizeof(g));
+          en.raw = u2f(w[k][8]);
+          std::memcpy(C, w[k] + 9, sizeof(C));
+        } else {
+          std::memcpy(en.t, C, sizeof(C));
+          en.serial_slot = k;
+          std::memcpy(C, ident, sizeof(C));
+        }
+        rec.push_back(en);
       }
     }
-    int cur = 0;
-    bool fresh = true;
-    while (cur < 32) {
-      int f = cur;
-      while (f < 32 && plain[f]) f++;
-      if (f > cur) {
-        bool crossed = false;
-        if (fresh) {
-          const uint32_t* t = w[f - 1] + 8;
+    { Entry en; std::memcpy(en.t, C, sizeof(C)); en.raw = -0.f; en.serial_slot = -1; rec.push_back(en); }
+    bool walk = rec.size() > 7;
+    if (!walk) {
+      const uint32_t start = bits;
+      bool ok = true;
+      for (const Entry& en : rec) {
+        bits = apply_table(bits, en.t[0], (int32_t)en.t[1], (int32_t)en.t[2], (int32_t)en.t[3], (int32_t)en.t[4], (int32_t)en.t[5],
+                           (int32_t)en.t[6], ok);
+        volatile float sv = u2f(bits); sv = sv + en.raw; bits = f2u(sv);
+        if (en.serial_slot >= 0) redo(bits, b0 + en.serial_slot);
+      }
+      if (ok) stats[4]++;
+      else { bits = start; walk = true; }
+    }
+    if (walk) {
+      stats[5]++;
+      for (int k = 0; k < 32; k++) {
+        if (w[k][0] == kOne) {
+          const uint32_t* t = w[k] + 1;
           bool ok = true;
           const uint32_t nb = apply_table(bits, t[0], (int32_t)t[1], (int32_t)t[2], (int32_t)t[3], (int32_t)t[4], (int32_t)t[5],
                                           (int32_t)t[6], ok);
-          if (ok) { bits = nb; crossed = true; stats[4]++; }
-        }
-        if (!crossed) {
-          stats[5]++;
-          int g = cur;
-          for (; g < f; g++) {
-            const uint32_t* t = w[g] + 1;
-            bool ok = true;
-            const uint32_t nb = apply_table(bits, t[0], (int32_t)t[1], (int32_t)t[2], (int32_t)t[3], (int32_t)t[4], (int32_t)t[5],
-                                            (int32_t)t[6], ok);
-            if (!ok) break;
-            bits = nb;
-          }
-          if (g < f) { stats[3]++; redo(bits, b0 + g); cur = g + 1; fresh = false; continue; }
+          if (ok) bits = nb; else { stats[3]++; redo(bits, b0 + k); }
+        } else if (!apply_segment(bits, w[k])) {
+          if (w[k][0] != kSerial) stats[3]++;
+          redo(bits, b0 + k);
         }
       }
-      if (f < 32) {
-        if (!apply_segment(bits, w[f])) { if (w[f][0] != kSerial) stats[3]++; redo(bits, b0 + f); }
-      }
-      cur = f + 1;
-      fresh = true;
     }
   }
   return u2f(bits);
