@@ -36,9 +36,11 @@ namespace rlfc {
 namespace xsum {
 
 constexpr int kSeg = 32;                 // additions per segment summary
-constexpr int kSlotWords = 16;           // summary size: [type | table (7) | raw float | table (7)]
+constexpr int kSlotWords = 20;           // summary: [type | table (7) | 3 floats | table (7) | 2 unused]
+constexpr int kSlotRaw = 8, kSlotB = 11; // word offsets of the float additions and of the second table
+constexpr uint32_t kNegZero = 0x80000000u;   // s + -0.f == s for every s: the "no addition" float
 constexpr uint32_t kOne = 0;             // one table covers the whole segment
-constexpr uint32_t kSplit = 1;           // table, one genuine float addition (the binade/sign change), table
+constexpr uint32_t kSplit = 1;           // table, three genuine float additions (around the binade/sign change), table
 constexpr uint32_t kSerial = 2;          // no summary: the serial pass adds the segment's elements one by one
 constexpr uint32_t kAnyKey = 0xffffffffu;   // table of an empty run: applies to any accumulator, changes nothing
 
@@ -125,40 +127,61 @@ XS_HD uint32_t apply_table(uint32_t bits, uint32_t key, int32_t D0, int32_t D1, 
 
 // Summary of one segment of cnt <= kSeg additions, given the predicted accumulator before its first addition.
 // slot[kSlotWords]: see the constants above.  One pass: the prediction is carried forward as a float chain
-// (what the real accumulator would do from the predicted start); an addition across which the prediction
-// changes sign or binade (or before which it has no usable key) cannot be part of a table -- with at most one
-// such addition the segment is  table | float addition | table, with more it is left to the serial pass.
+// (what the real accumulator would do from the predicted start).  The addition across which the prediction
+// changes sign or binade (or before which it has no usable key) cannot be part of a table; it is kept as a
+// genuine float addition TOGETHER WITH ITS TWO NEIGHBOURS, because the real accumulator differs from the
+// prediction by a few ulps and may change binade one addition earlier or later.  With one such place the
+// segment is  table | 3 float additions | table;  with more it is left to the serial pass.
 template <typename Get>
 XS_HD void build_segment(Get get, int cnt, double pred_start, uint32_t* slot) {
   float pred = (float)pred_start;
   uint32_t key_prev = key_of(pred);
   Run run;
   run.start(key_prev);
-  int ncross = 0;
-  bool good = true;
+  int state = 0;                         // 0: first table, 1: the addition after the change is due, 2: second table
+  bool good = true, pending = false, serial = false;
+  float pend = 0.f;                      // the last addition, not yet committed to the first table
   for (int w = 0; w < kSlotWords; w++) slot[w] = 0;
+  slot[kSlotRaw] = slot[kSlotRaw + 1] = slot[kSlotRaw + 2] = kNegZero;
   for (int k = 0; k < cnt; k++) {
     const float a = get(k);
     pred = pred + a;
     const uint32_t kn = key_of(pred);
-    if (kn != key_prev || !key_ok(key_prev)) {
-      if (ncross == 0) {                 // close the first table, keep this addition as it is, open the second
+    const bool change = kn != key_prev || !key_ok(key_prev);
+    if (state == 0) {
+      if (change) {
         good = run.good || run.empty;
         run.store(slot + 1);
-        slot[8] = f2u(a);
-        run.start(kn);
-        if (!key_ok(kn)) run.good = false;          // only acceptable if nothing follows (checked through `empty`)
+        slot[kSlotRaw] = pending ? f2u(pend) : kNegZero;
+        slot[kSlotRaw + 1] = f2u(a);
+        pending = false;
+        state = 1;
+      } else {
+        if (pending) run.add(pend);
+        pend = a; pending = true;
       }
-      ncross++;
+    } else if (state == 1) {             // a genuine addition whatever it does; the second table starts behind it
+      slot[kSlotRaw + 2] = f2u(a);
+      run.start(kn);
+      if (!key_ok(kn)) run.good = false; // only acceptable if nothing follows (checked through `empty`)
+      state = 2;
     } else {
-      run.add(a);
+      if (change) serial = true; else run.add(a);
     }
     key_prev = kn;
   }
-  good = good && ncross <= 1 && (run.good || run.empty);
+  if (state == 0) {
+    if (pending) run.add(pend);
+    if (!run.good) { slot[0] = kSerial; return; }
+    slot[0] = kOne;
+    run.store(slot + 1);
+    return;
+  }
+  if (state == 1) { run.start(key_prev); run.good = true; }     // nothing behind the change: empty second table
+  good = good && !serial && (run.good || run.empty);
   if (!good) { slot[0] = kSerial; return; }
-  if (ncross == 0) { slot[0] = kOne; run.store(slot + 1); }
-  else { slot[0] = kSplit; run.store(slot + 9); }
+  slot[0] = kSplit;
+  run.store(slot + kSlotB);
 }
 
 // ---- composition of tables (used to summarise a whole stretch of plain segments in one table) ----
@@ -213,9 +236,9 @@ XS_HD bool apply_segment(uint32_t& bits, const uint32_t* slot) {
   uint32_t b = apply_table(bits, slot[1], (int32_t)slot[2], (int32_t)slot[3], (int32_t)slot[4], (int32_t)slot[5],
                            (int32_t)slot[6], (int32_t)slot[7], ok);
   if (slot[0] == kSplit) {
-    b = f2u(u2f(b) + u2f(slot[8]));
-    b = apply_table(b, slot[9], (int32_t)slot[10], (int32_t)slot[11], (int32_t)slot[12], (int32_t)slot[13],
-                    (int32_t)slot[14], (int32_t)slot[15], ok);
+    b = f2u(((u2f(b) + u2f(slot[kSlotRaw])) + u2f(slot[kSlotRaw + 1])) + u2f(slot[kSlotRaw + 2]));
+    b = apply_table(b, slot[kSlotB], (int32_t)slot[kSlotB + 1], (int32_t)slot[kSlotB + 2], (int32_t)slot[kSlotB + 3],
+                    (int32_t)slot[kSlotB + 4], (int32_t)slot[kSlotB + 5], (int32_t)slot[kSlotB + 6], ok);
   }
   if (ok) bits = b;
   return ok;

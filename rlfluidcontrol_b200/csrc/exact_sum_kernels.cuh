@@ -1,7 +1,7 @@
 // exact_sum_kernels.cuh -- Field.sum (Field.pde:311-318) as three kernels around exact_sum.cuh:
-//   k_xsum_totals  double-precision sum of every chunk (kXsChunk additions) of every environment
 //   k_xsum_tables  one thread per segment of 32 additions: predicted accumulator before the segment (chunk
-//                  totals + block scan), then the segment summary (exact_sum.cuh) -> 64 B slot
+//                  totals handed from CTA to CTA + block scan), then the segment summary (exact_sum.cuh) -> 64 B
+//                  slot, and per warp a condensed batch record
 //   k_xsum_chain   one warp per environment walks the slots with the true accumulator; a segment whose summary
 //                  does not provably apply is redone as 32 genuine float additions
 // The result is bit-identical to the serial loop for any input (tests/test_exact_sum.py, tests/test_gpu_parity.py).
@@ -12,8 +12,9 @@
 constexpr int kXsThreads = 256;
 constexpr int kXsChunk = kXsThreads * xsum::kSeg;       // additions per CTA
 constexpr int kXsPad = xsum::kSeg + 1;                  // shared-memory stride of a segment (bank-conflict free)
-constexpr int kXsRecWords = 64;                         // batch record: 8 header words + kXsRecEntries entries of 8 words
-constexpr int kXsRecEntries = 7;
+constexpr int kXsEntWords = 12;                         // record entry: table (7), three float additions, 2 unused
+constexpr int kXsRecEntries = 15;
+constexpr int kXsRecWords = 8 + kXsRecEntries * kXsEntWords + 4;   // batch record: 8 header words + entries (192 words)
 
 // serial index K (i-major over the interior) -> offset in the pitched array.  advance() is branch-free when a
 // row is at least half a CTA wide (WIDE: at most two row ends per stride of kXsThreads elements), so that the
@@ -38,44 +39,6 @@ struct XsCursor {
 };
 
 template <bool WIDE>
-__device__ __forceinline__ double xs_chunk_total(const SolverParams& q, const float* p, long long base, long long N, int t) {
-  double s = 0.0;
-  XsCursor<WIDE> cur(base + t, q.m - 2, q.P);
-  const unsigned left = (unsigned)(N - base);                     // elements of this chunk and beyond (N > base)
-#pragma unroll 1
-  for (int h = 0; h < xsum::kSeg; h += 8) {                       // 8 independent loads in flight per thread
-    float v[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      v[u] = ((unsigned)(t + (h + u) * kXsThreads) < left) ? p[cur.off()] : 0.f;
-      cur.advance();
-    }
-#pragma unroll
-    for (int u = 0; u < 8; u++) s += (double)v[u];
-  }
-  return s;
-}
-
-__global__ void __launch_bounds__(kXsThreads)
-k_xsum_totals(const __grid_constant__ SolverParams q) {
-  __shared__ double wsum[kXsThreads / 32];
-  const int c = blockIdx.x, e = blockIdx.y, t = threadIdx.x;
-  const int len = q.m - 2;
-  const long long N = (long long)(q.n - 2) * len, base = (long long)c * kXsChunk;
-  const float* p = q.lev[0].x + (size_t)e * q.stride;
-  double s = (2 * len >= kXsThreads) ? xs_chunk_total<true>(q, p, base, N, t) : xs_chunk_total<false>(q, p, base, N, t);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-  if ((t & 31) == 0) wsum[t >> 5] = s;
-  __syncthreads();
-  if (t == 0) {
-    double tot = 0.0;
-    for (int w = 0; w < kXsThreads / 32; w++) tot += wsum[w];
-    q.xs_ctot[(size_t)e * q.xs_nchunks + c] = tot;
-  }
-}
-
-template <bool WIDE>
 __device__ __forceinline__ void xs_fill(const SolverParams& q, const float* p, long long base, long long N, int t, float* buf) {
   XsCursor<WIDE> cur(base + t, q.m - 2, q.P);
 #pragma unroll 8
@@ -91,18 +54,13 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
   __shared__ float buf[kXsThreads * kXsPad];
   __shared__ double wsum[kXsThreads / 32];
   __shared__ double base_pred;
+  __shared__ double wpart[kXsThreads / 32];
   const int c = blockIdx.x, e = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int len = q.m - 2;
   const long long N = (long long)(q.n - 2) * len, base = (long long)c * kXsChunk;
   const float* p = q.lev[0].x + (size_t)e * q.stride;
   if (2 * len >= kXsThreads) xs_fill<true>(q, p, base, N, t, buf);
   else xs_fill<false>(q, p, base, N, t, buf);
-  if (t == 0) {
-    double b = 0.0;
-    const double* ct = q.xs_ctot + (size_t)e * q.xs_nchunks;
-    for (int k = 0; k < c; k++) b += ct[k];
-    base_pred = b;
-  }
   __syncthreads();
   const long long g = (long long)c * kXsThreads + t;              // this thread's segment
   const long long left = N - g * xsum::kSeg;
@@ -120,6 +78,39 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
     if (lane >= o) incl += v;
   }
   if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  {
+    // Chunk totals travel between the CTAs of one environment through global memory (single pass, "look-back"):
+    // publish this chunk's total, then wait for the totals of the chunks before it.  CTAs are dispatched in
+    // blockIdx order (chunk index fastest), so the CTAs waited for are already running; the wait is bounded
+    // all the same -- the total only feeds the PREDICTION, a wrong one merely sends segments to the serial path.
+    const unsigned ep = q.xs_epoch[e] + 1u;                       // k_xsum_chain bumps the epoch after every pass
+    volatile double* ct = q.xs_ctot + (size_t)e * q.xs_nchunks;
+    volatile unsigned* cf = q.xs_cflag + (size_t)e * q.xs_nchunks;
+    if (t == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < kXsThreads / 32; w++) tot += wsum[w];
+      ct[c] = tot;
+      __threadfence();
+      cf[c] = ep;
+    }
+    double part = 0.0;
+    for (int k = t; k < c; k += kXsThreads) {
+      int spins = 0;
+      while (cf[k] != ep && ++spins < (1 << 20)) {}
+      __threadfence();
+      part += ct[k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+    if (lane == 0) wpart[warp] = part;
+    __syncthreads();
+    if (t == 0) {
+      double bsum = 0.0;
+      for (int w = 0; w < kXsThreads / 32; w++) bsum += wpart[w];
+      base_pred = bsum;
+    }
+  }
   __syncthreads();
   double pred = base_pred;
   for (int w = 0; w < warp; w++) pred += wsum[w];
@@ -145,11 +136,11 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
     uint32_t X[7], acc[7];
     const uint32_t ident[7] = {xsum::kAnyKey, 0u, 0u, (uint32_t)INT32_MIN, (uint32_t)INT32_MAX, (uint32_t)INT32_MIN, (uint32_t)INT32_MAX};
     xsum::normalise_table(slot + 1);
-    if (type == xsum::kSplit) xsum::normalise_table(slot + 9);
+    if (type == xsum::kSplit) xsum::normalise_table(slot + xsum::kSlotB);
 #pragma unroll
     for (int w = 0; w < 7; w++) {
       X[w] = (type == xsum::kSerial) ? ident[w] : slot[1 + w];
-      acc[w] = (type == xsum::kOne) ? slot[1 + w] : (type == xsum::kSplit ? slot[9 + w] : ident[w]);
+      acc[w] = (type == xsum::kOne) ? slot[1 + w] : (type == xsum::kSplit ? slot[xsum::kSlotB + w] : ident[w]);
     }
     const uint32_t headmask = __ballot_sync(0xffffffffu, head);
     const uint32_t upto = headmask & ((2u << lane) - 1u);         // heads at or below this lane
@@ -177,15 +168,19 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
       if (lane == 0)
         *reinterpret_cast<uint4*>(rec) = make_uint4(count <= kXsRecEntries ? (uint32_t)count : 0xffffffffu, serbits, headmask, 0u);
       if (count <= kXsRecEntries) {
+        const uint32_t nz = xsum::kNegZero;                        // serial heads and the last entry add nothing
         if (head) {
-          uint4* ent = reinterpret_cast<uint4*>(rec + 8 + 8 * idx);
+          const bool sp = type == xsum::kSplit;
+          uint4* ent = reinterpret_cast<uint4*>(rec + 8 + kXsEntWords * idx);
           ent[0] = make_uint4(X[0], X[1], X[2], X[3]);
-          ent[1] = make_uint4(X[4], X[5], X[6], type == xsum::kSplit ? slot[8] : 0x80000000u);   // -0.f: s + -0 == s
+          ent[1] = make_uint4(X[4], X[5], X[6], sp ? slot[xsum::kSlotRaw] : nz);
+          ent[2] = make_uint4(sp ? slot[xsum::kSlotRaw + 1] : nz, sp ? slot[xsum::kSlotRaw + 2] : nz, 0u, 0u);
         }
         if (lane == 31) {
-          uint4* ent = reinterpret_cast<uint4*>(rec + 8 + 8 * (count - 1));
+          uint4* ent = reinterpret_cast<uint4*>(rec + 8 + kXsEntWords * (count - 1));
           ent[0] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-          ent[1] = make_uint4(acc[4], acc[5], acc[6], 0x80000000u);
+          ent[1] = make_uint4(acc[4], acc[5], acc[6], nz);
+          ent[2] = make_uint4(nz, nz, 0u, 0u);
         }
       }
     }
@@ -193,7 +188,7 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
   if (g < q.xs_nseg) {
     uint4* out = reinterpret_cast<uint4*>(q.xs_slots + ((size_t)e * q.xs_nseg + g) * xsum::kSlotWords);
 #pragma unroll
-    for (int w = 0; w < 4; w++) out[w] = make_uint4(slot[4 * w], slot[4 * w + 1], slot[4 * w + 2], slot[4 * w + 3]);
+    for (int w = 0; w < xsum::kSlotWords / 4; w++) out[w] = make_uint4(slot[4 * w], slot[4 * w + 1], slot[4 * w + 2], slot[4 * w + 3]);
   }
 }
 
@@ -202,7 +197,7 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
 // of a batch does not provably apply (or the batch has too many heads for a record), the batch is redone from
 // its start summary by summary (walk): chain of  bits += (bits & 1) ? D1 : D0  over the plain summaries, every
 // lane checks its own summary's condition, the first one that fails is redone as 32 float additions.
-constexpr int kXsRing = 4;        // batch records in the shared-memory ring (cp.async, 3 batches ahead)
+constexpr int kXsGroup = 8;       // batch records per cp.async group; the ring holds two groups
 constexpr int kXsRawPf = 4;       // serial segments per batch whose elements are prefetched
 
 __device__ __forceinline__ void xs_cp16(void* smem, const void* gmem) {
@@ -211,7 +206,7 @@ __device__ __forceinline__ void xs_cp16(void* smem, const void* gmem) {
 
 __global__ void __launch_bounds__(32)
 k_xsum_chain(const __grid_constant__ SolverParams q) {
-  __shared__ __align__(16) uint32_t ring[kXsRing][kXsRecWords];
+  __shared__ __align__(16) uint32_t ring[2 * kXsGroup][kXsRecWords];
   const int e = blockIdx.x, lane = threadIdx.x;
   const unsigned len = (unsigned)(q.m - 2), P = (unsigned)q.P;
   const unsigned N = (unsigned)(q.n - 2) * len;                   // rlfc_env_create rejects grids beyond 2^31 cells
@@ -223,13 +218,22 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
     const unsigned K = g * xsum::kSeg + lane;
     return K < N ? p[(size_t)(1u + K / len) * P + 1u + K % len] : 0.f;
   };
-  auto fetch = [&](int b) {                                       // one commit group per batch, also when empty
-    if (b < nb && lane < kXsRecWords / 4) xs_cp16(ring[b % kXsRing] + 4 * lane, recs + (size_t)b * kXsRecWords + 4 * lane);
+  auto fetch = [&](int grp) {                                     // records of batches grp*kXsGroup ..; one commit group
+    const int b0 = grp * kXsGroup, n16 = min(kXsGroup, nb - b0) * (kXsRecWords / 4);   // 16-byte pieces (contiguous records)
+    uint32_t* dst = ring[b0 % (2 * kXsGroup)];
+    const uint32_t* src = recs + (size_t)b0 * kXsRecWords;
+    for (int k = lane; k < n16; k += 32) xs_cp16(dst + 4 * k, src + 4 * k);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   // xs_stats[e][0..3]: batches crossed by their record / walked summary by summary, record entries applied,
   // segments redone as float additions
   int st_rec = 0, st_walk = 0, st_ent = 0, st_redo = 0;
+#ifdef RLFC_XS_TIMING           // cycles: [4] batch set-up + prefetch, [5] record entries, [6] serial segments, [7] walks
+  long long tk = clock64(), tacc[4] = {0, 0, 0, 0};
+#define XS_TICK(i) do { const long long n_ = clock64(); tacc[i] += n_ - tk; tk = n_; } while (0)
+#else
+#define XS_TICK(i)
+#endif
   uint32_t bits = 0u;                                             // s = +0.f
   // 32 genuine additions of segment g; lane u holds element u in v
   auto redo = [&](unsigned g, float v) {
@@ -247,19 +251,21 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
   // batch b summary by summary, from the accumulator in `bits`
   auto walk = [&](int b) {
     st_walk++;
-    uint32_t w[16];
+    constexpr int kQ = xsum::kSlotWords / 4;
+    uint32_t w[xsum::kSlotWords];
     {
       const int g = b * 32 + lane;
-      uint4 v4[4];
+      uint4 v4[kQ];
       if (g < nseg) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) v4[k] = slots[(size_t)g * 4 + k];
+        for (int k = 0; k < kQ; k++) v4[k] = slots[(size_t)g * kQ + k];
       } else {                                                    // past the end: an empty table
         v4[0] = make_uint4(xsum::kOne, xsum::kAnyKey, 0u, 0u);
-        v4[1] = v4[2] = v4[3] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int k = 1; k < kQ; k++) v4[k] = make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
-      for (int k = 0; k < 4; k++) { w[4 * k] = v4[k].x; w[4 * k + 1] = v4[k].y; w[4 * k + 2] = v4[k].z; w[4 * k + 3] = v4[k].w; }
+      for (int k = 0; k < kQ; k++) { w[4 * k] = v4[k].x; w[4 * k + 1] = v4[k].y; w[4 * k + 2] = v4[k].z; w[4 * k + 3] = v4[k].w; }
     }
     const uint32_t special = __ballot_sync(0xffffffffu, w[0] != xsum::kOne);
     int cur = 0;
@@ -280,72 +286,91 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
       if (bad) { ev = __ffs(bad) - 1; bits = __shfl_sync(0xffffffffu, mine, ev); }
       else { ev = f; bits = acc; }
       if (ev < 32) {
-        uint32_t sw[16];
+        uint32_t sw[xsum::kSlotWords];
 #pragma unroll
-        for (int k = 0; k < 16; k++) sw[k] = __shfl_sync(0xffffffffu, w[k], ev);
+        for (int k = 0; k < xsum::kSlotWords; k++) sw[k] = __shfl_sync(0xffffffffu, w[k], ev);
         if (bad || !xsum::apply_segment(bits, sw)) redo((unsigned)(b * 32 + ev), element((unsigned)(b * 32 + ev)));
       }
       cur = ev + 1;
     }
   };
-  fetch(0); fetch(1); fetch(2);
+  const int ngrp = (nb + kXsGroup - 1) / kXsGroup;
+  fetch(0);
   float rawn[kXsRawPf];                                           // elements of the next batch's first serial segments
 #pragma unroll
   for (int i = 0; i < kXsRawPf; i++) rawn[i] = 0.f;
+  bool have_raw = false;
   for (int b = 0; b < nb; b++) {
-    fetch(b + 3);
-    asm volatile("cp.async.wait_group 2;" ::: "memory");          // records <= b + 1 have landed
-    __syncwarp();
-    const uint32_t* rec = ring[b % kXsRing];
+    if (b % kXsGroup == 0) {                                      // group boundary: next group in flight, this one landed
+      const int grp = b / kXsGroup;
+      __syncwarp();
+      if (grp + 1 < ngrp) { fetch(grp + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+    }
+    const uint32_t* rec = ring[b % (2 * kXsGroup)];
     const uint4 hdr = *reinterpret_cast<const uint4*>(rec);       // count, serial entries, head summaries
     float raw[kXsRawPf];
 #pragma unroll
     for (int i = 0; i < kXsRawPf; i++) raw[i] = rawn[i];
-    if (b + 1 < nb) {                                             // elements of the next batch's serial segments
-      const uint4 nh = *reinterpret_cast<const uint4*>(ring[(b + 1) % kXsRing]);
+    const bool raw_ok = have_raw;
+    have_raw = false;
+    if ((b + 1) % kXsGroup != 0 && b + 1 < nb) {                  // elements of the next batch's serial segments (same group)
+      const uint4 nh = *reinterpret_cast<const uint4*>(ring[(b + 1) % (2 * kXsGroup)]);
       uint32_t m = nh.x == 0xffffffffu ? 0u : nh.y;
+      if (m) {
+        have_raw = true;
 #pragma unroll
-      for (int i = 0; i < kXsRawPf; i++) {
-        rawn[i] = 0.f;
-        if (m) {
-          const int ent = __ffs(m) - 1;
-          m &= m - 1u;
-          rawn[i] = element((unsigned)((b + 1) * 32) + __fns(nh.z, 0u, ent + 1));
+        for (int i = 0; i < kXsRawPf; i++) {
+          rawn[i] = 0.f;
+          if (m) {
+            const int ent = __ffs(m) - 1;
+            m &= m - 1u;
+            rawn[i] = element((unsigned)((b + 1) * 32) + __fns(nh.z, 0u, ent + 1));
+          }
         }
       }
     }
-    if (hdr.x == 0xffffffffu) { walk(b); continue; }
+    XS_TICK(0);
+    if (hdr.x == 0xffffffffu) { walk(b); XS_TICK(3); continue; }
     const uint32_t start = bits;
     const int st_redo0 = st_redo;
     bool ok = true;
     const int count = (int)hdr.x;
     for (int i = 0; i < count; i++) {
-      const uint4 t0 = *reinterpret_cast<const uint4*>(rec + 8 + 8 * i);
-      const uint4 t1 = *reinterpret_cast<const uint4*>(rec + 12 + 8 * i);
+      const uint4 t0 = *reinterpret_cast<const uint4*>(rec + 8 + kXsEntWords * i);
+      const uint4 t1 = *reinterpret_cast<const uint4*>(rec + 12 + kXsEntWords * i);
+      const uint2 t2 = *reinterpret_cast<const uint2*>(rec + 16 + kXsEntWords * i);
       bits = xsum::apply_table(bits, t0.x, (int32_t)t0.y, (int32_t)t0.z, (int32_t)t0.w, (int32_t)t1.x, (int32_t)t1.y,
                                (int32_t)t1.z, ok);
-      bits = xsum::f2u(xsum::u2f(bits) + xsum::u2f(t1.w));
+      bits = xsum::f2u(((xsum::u2f(bits) + xsum::u2f(t1.w)) + xsum::u2f(t2.x)) + xsum::u2f(t2.y));
+      XS_TICK(1);
       if ((hdr.y >> i) & 1u) {                                    // the entry ends at a serial segment
         const unsigned g = (unsigned)(b * 32) + __fns(hdr.z, 0u, i + 1);
         const int si = __popc(hdr.y & ((1u << i) - 1u));
         float v;
-        if (b > 0 && si < kXsRawPf) {
+        if (raw_ok && si < kXsRawPf) {
           v = raw[0];
 #pragma unroll
           for (int k = 1; k < kXsRawPf; k++) v = (si == k) ? raw[k] : v;
         } else {
-          v = element(g);                                         // (batch 0 has no prefetch)
+          v = element(g);                                         // (no prefetch across group boundaries)
         }
         redo(g, v);
+        XS_TICK(2);
       }
     }
     if (ok) { st_rec++; st_ent += count; }
-    else { bits = start; st_redo = st_redo0; walk(b); }
+    else { bits = start; st_redo = st_redo0; walk(b); XS_TICK(3); }
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (lane == 0) {
     q.sc.psum[e] = xsum::u2f(bits);
+    q.xs_epoch[e] += 1u;                                          // next pass: fresh chunk-total flags
     int* st = q.xs_stats + 8 * e;
     st[0] = st_rec; st[1] = st_walk; st[2] = st_ent; st[3] = st_redo;
+#ifdef RLFC_XS_TIMING
+    for (int k = 0; k < 4; k++) st[4 + k] = (int)tacc[k];
+#endif
   }
+#undef XS_TICK
 }

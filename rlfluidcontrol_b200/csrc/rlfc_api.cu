@@ -689,8 +689,10 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     TRY(E->dmalloc(&sp.xs_stats, (size_t)8 * B));
     if (!(ev && std::strcmp(ev, "serial") == 0)) {
       TRY(E->dmalloc(&sp.xs_ctot, (size_t)sp.xs_nchunks * B));
-      TRY(E->dmalloc(&sp.xs_slots, (size_t)sp.xs_nseg * 16 * B));
-      TRY(E->dmalloc(&sp.xs_recs, (size_t)sp.xs_nbatches * 64 * B));
+      TRY(E->dmalloc(&sp.xs_cflag, (size_t)sp.xs_nchunks * B));
+      TRY(E->dmalloc(&sp.xs_epoch, (size_t)B));
+      TRY(E->dmalloc(&sp.xs_slots, (size_t)sp.xs_nseg * 20 * B));
+      TRY(E->dmalloc(&sp.xs_recs, (size_t)sp.xs_nbatches * 192 * B));
     }
   }
   TRY(E->dmalloc(&sp.sc.any_active, n_groups));
@@ -731,8 +733,9 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     v.sc.callLearn += e0; v.sc.Cd += e0; v.sc.Cl += e0; v.sc.obs += 2 * e0; v.sc.active += e0; v.sc.iters += 2 * e0;
     v.sc.psum += e0; v.sc.any_active += g;
     if (v.xs_slots) {
-      v.xs_ctot += (size_t)e0 * v.xs_nchunks; v.xs_slots += (size_t)e0 * v.xs_nseg * 16;
-      v.xs_recs += (size_t)e0 * v.xs_nbatches * 64;
+      v.xs_ctot += (size_t)e0 * v.xs_nchunks; v.xs_slots += (size_t)e0 * v.xs_nseg * 20;
+      v.xs_cflag += (size_t)e0 * v.xs_nchunks; v.xs_epoch += e0;
+      v.xs_recs += (size_t)e0 * v.xs_nbatches * 192;
     }
     v.xs_stats += 8 * e0;
     const size_t o = (size_t)e0 * sp.stride;

@@ -1330,10 +1330,9 @@ int launch_psum(const SolverParams& q, cudaStream_t st) {
     return 1;
   }
   const dim3 grid(q.xs_nchunks, q.B);
-  k_xsum_totals<<<grid, kXsThreads, 0, st>>>(q);
   k_xsum_tables<<<grid, kXsThreads, 0, st>>>(q);
   k_xsum_chain<<<q.B, 32, 0, st>>>(q);
-  return 3;
+  return 2;
 }
 
 int launch_project_u(const SolverParams& q, float* ux, float* uy, cudaStream_t st) {

@@ -55,10 +55,10 @@ float xs_parallel(const float* a, long n, double pred_noise, long* stats) {
       else { std::memset(w[k], 0, sizeof(w[k])); w[k][0] = kOne; w[k][1] = kAnyKey; }
       stats[w[k][0]] += (b0 + k < nseg);
       normalise_table(w[k] + 1);
-      if (w[k][0] == kSplit) normalise_table(w[k] + 9);
+      if (w[k][0] == kSplit) normalise_table(w[k] + kSlotB);
     }
     // record (sequential composition; the device scans a tree)
-    struct Entry { uint32_t t[7]; float raw; int serial_slot; };
+    struct Entry { uint32_t t[7]; float raw[3]; int serial_slot; };
     std::vector<Entry> rec;
     uint32_t C[7];
     std::memcpy(C, ident, sizeof(C));
@@ -67,12 +67,12 @@ float xs_parallel(const float* a, long n, double pred_noise, long* stats) {
         uint32_t g[7]; std::memcpy(g, w[k] + 1, sizeof(g));
         compose_tables(C, g); std::memcpy(C, g, sizeof(C));
       } else {
-        Entry en; en.serial_slot = -1; en.raw = -0.f;
+        Entry en; en.serial_slot = -1; en.raw[0] = en.raw[1] = en.raw[2] = -0.f;
         if (w[k][0] == kSplit) {
           uint32_t g[7]; std::memcpy(g, w[k] + 1, sizeof(g));
           compose_tables(C, g); std::memcpy(en.t, g, sizeof(g));
-          en.raw = u2f(w[k][8]);
-          std::memcpy(C, w[k] + 9, sizeof(C));
+          for (int r = 0; r < 3; r++) en.raw[r] = u2f(w[k][kSlotRaw + r]);
+          std::memcpy(C, w[k] + kSlotB, sizeof(C));
         } else {
           std::memcpy(en.t, C, sizeof(C));
           en.serial_slot = k;
@@ -81,15 +81,15 @@ float xs_parallel(const float* a, long n, double pred_noise, long* stats) {
         rec.push_back(en);
       }
     }
-    { Entry en; std::memcpy(en.t, C, sizeof(C)); en.raw = -0.f; en.serial_slot = -1; rec.push_back(en); }
-    bool walk = rec.size() > 7;
+    { Entry en; std::memcpy(en.t, C, sizeof(C)); en.raw[0] = en.raw[1] = en.raw[2] = -0.f; en.serial_slot = -1; rec.push_back(en); }
+    bool walk = rec.size() > 15;
     if (!walk) {
       const uint32_t start = bits;
       bool ok = true;
       for (const Entry& en : rec) {
         bits = apply_table(bits, en.t[0], (int32_t)en.t[1], (int32_t)en.t[2], (int32_t)en.t[3], (int32_t)en.t[4], (int32_t)en.t[5],
                            (int32_t)en.t[6], ok);
-        volatile float sv = u2f(bits); sv = sv + en.raw; bits = f2u(sv);
+        volatile float sv = u2f(bits); sv = sv + en.raw[0]; sv = sv + en.raw[1]; sv = sv + en.raw[2]; bits = f2u(sv);
         if (en.serial_slot >= 0) redo(bits, b0 + en.serial_slot);
       }
       if (ok) stats[4]++;
