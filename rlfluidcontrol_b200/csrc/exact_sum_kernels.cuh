@@ -159,22 +159,26 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
       if (lane == 0) cprev[w] = ident[w];
     }
     xsum::compose_tables(cprev, X);                               // X = E_k on head lanes
-    const int idx = __popc(headmask & ((1u << lane) - 1u));       // entry index of a head lane
-    const int count = __popc(headmask) + 1;
-    const uint32_t serbits = __reduce_or_sync(0xffffffffu, type == xsum::kSerial ? (1u << idx) : 0u);
+    // a run of consecutive serial summaries is ONE entry: the table before it, then `run` whole segments
+    const uint32_t sermask = __ballot_sync(0xffffffffu, type == xsum::kSerial);
+    const bool absorbed = type == xsum::kSerial && lane > 0 && ((sermask >> (lane - 1)) & 1u);
+    const uint32_t emitmask = __ballot_sync(0xffffffffu, head && !absorbed);
+    const int idx = __popc(emitmask & ((1u << lane) - 1u));       // entry index of an emitting head lane
+    const int count = __popc(emitmask) + 1;
+    const int run = type == xsum::kSerial ? __ffs(~(sermask >> lane)) - 1 : 0;   // serial summaries from this lane on
     const long long batch = (long long)c * (kXsThreads / 32) + warp;
     if (batch < q.xs_nbatches) {
       uint32_t* rec = q.xs_recs + ((size_t)e * q.xs_nbatches + batch) * kXsRecWords;
       if (lane == 0)
-        *reinterpret_cast<uint4*>(rec) = make_uint4(count <= kXsRecEntries ? (uint32_t)count : 0xffffffffu, serbits, headmask, 0u);
+        *reinterpret_cast<uint4*>(rec) = make_uint4(count <= kXsRecEntries ? (uint32_t)count : 0xffffffffu, sermask, 0u, 0u);
       if (count <= kXsRecEntries) {
         const uint32_t nz = xsum::kNegZero;                        // serial heads and the last entry add nothing
-        if (head) {
+        if (head && !absorbed) {
           const bool sp = type == xsum::kSplit;
           uint4* ent = reinterpret_cast<uint4*>(rec + 8 + kXsEntWords * idx);
           ent[0] = make_uint4(X[0], X[1], X[2], X[3]);
           ent[1] = make_uint4(X[4], X[5], X[6], sp ? slot[xsum::kSlotRaw] : nz);
-          ent[2] = make_uint4(sp ? slot[xsum::kSlotRaw + 1] : nz, sp ? slot[xsum::kSlotRaw + 2] : nz, 0u, 0u);
+          ent[2] = make_uint4(sp ? slot[xsum::kSlotRaw + 1] : nz, sp ? slot[xsum::kSlotRaw + 2] : nz, (uint32_t)run, (uint32_t)lane);
         }
         if (lane == 31) {
           uint4* ent = reinterpret_cast<uint4*>(rec + 8 + kXsEntWords * (count - 1));
@@ -185,18 +189,12 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
       }
     }
   }
-  if (g < q.xs_nseg) {
-    uint4* out = reinterpret_cast<uint4*>(q.xs_slots + ((size_t)e * q.xs_nseg + g) * xsum::kSlotWords);
-#pragma unroll
-    for (int w = 0; w < xsum::kSlotWords / 4; w++) out[w] = make_uint4(slot[4 * w], slot[4 * w + 1], slot[4 * w + 2], slot[4 * w + 3]);
-  }
 }
 
-// Serial pass.  One warp per environment walks the batch records: per entry one table application (checked) and
-// one float addition, plus the 32 genuine additions of a serial segment where an entry says so.  If any entry
-// of a batch does not provably apply (or the batch has too many heads for a record), the batch is redone from
-// its start summary by summary (walk): chain of  bits += (bits & 1) ? D1 : D0  over the plain summaries, every
-// lane checks its own summary's condition, the first one that fails is redone as 32 float additions.
+// Serial pass.  One warp per environment walks the batch records: per entry one table application (checked),
+// three float additions, and the genuine additions of a run of serial segments where the entry says so.  If any
+// entry of a batch does not provably apply (or the batch has too many heads for a record), the whole batch is
+// redone from its start as 1024 genuine float additions.
 constexpr int kXsGroup = 8;       // batch records per cp.async group; the ring holds two groups
 constexpr int kXsRawPf = 4;       // serial segments per batch whose elements are prefetched
 
@@ -212,7 +210,6 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
   const unsigned N = (unsigned)(q.n - 2) * len;                   // rlfc_env_create rejects grids beyond 2^31 cells
   const int nseg = q.xs_nseg, nb = q.xs_nbatches;
   const float* p = q.lev[0].x + (size_t)e * q.stride;
-  const uint4* slots = reinterpret_cast<const uint4*>(q.xs_slots + (size_t)e * nseg * xsum::kSlotWords);
   const uint32_t* recs = q.xs_recs + (size_t)e * nb * kXsRecWords;
   auto element = [&](unsigned g) {                                 // this lane's element of segment g (0 past the end)
     const unsigned K = g * xsum::kSeg + lane;
@@ -248,50 +245,15 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
     for (int u = 0; u < xsum::kSeg; u++) s = (u < cnt) ? s + el[u] : s;
     bits = xsum::f2u(s);
   };
-  // batch b summary by summary, from the accumulator in `bits`
-  auto walk = [&](int b) {
+  // batch b as genuine additions, from the accumulator in `bits`
+  auto redo_batch = [&](int b) {
     st_walk++;
-    constexpr int kQ = xsum::kSlotWords / 4;
-    uint32_t w[xsum::kSlotWords];
-    {
-      const int g = b * 32 + lane;
-      uint4 v4[kQ];
-      if (g < nseg) {
+    for (int k0 = 0; k0 < 32; k0 += 8) {                          // 8 segments' elements in flight
+      float v[8];
 #pragma unroll
-        for (int k = 0; k < kQ; k++) v4[k] = slots[(size_t)g * kQ + k];
-      } else {                                                    // past the end: an empty table
-        v4[0] = make_uint4(xsum::kOne, xsum::kAnyKey, 0u, 0u);
+      for (int k = 0; k < 8; k++) v[k] = element((unsigned)(b * 32 + k0 + k));
 #pragma unroll
-        for (int k = 1; k < kQ; k++) v4[k] = make_uint4(0u, 0u, 0u, 0u);
-      }
-#pragma unroll
-      for (int k = 0; k < kQ; k++) { w[4 * k] = v4[k].x; w[4 * k + 1] = v4[k].y; w[4 * k + 2] = v4[k].z; w[4 * k + 3] = v4[k].w; }
-    }
-    const uint32_t special = __ballot_sync(0xffffffffu, w[0] != xsum::kOne);
-    int cur = 0;
-    while (cur < 32) {
-      const uint32_t rest = special >> cur;
-      const int f = rest ? cur + __ffs(rest) - 1 : 32;            // next summary that is not a plain table
-      uint32_t acc = bits, mine = bits;
-      for (int k0 = cur; k0 < f; k0++) {
-        const uint32_t d0 = __shfl_sync(0xffffffffu, w[2], k0), d1 = __shfl_sync(0xffffffffu, w[3], k0);
-        mine = (lane == k0) ? acc : mine;
-        acc += (acc & 1u) ? d1 : d0;
-      }
-      bool ok = true;
-      if (lane >= cur && lane < f)
-        xsum::apply_table(mine, w[1], (int32_t)w[2], (int32_t)w[3], (int32_t)w[4], (int32_t)w[5], (int32_t)w[6], (int32_t)w[7], ok);
-      const uint32_t bad = __ballot_sync(0xffffffffu, !ok);
-      int ev;
-      if (bad) { ev = __ffs(bad) - 1; bits = __shfl_sync(0xffffffffu, mine, ev); }
-      else { ev = f; bits = acc; }
-      if (ev < 32) {
-        uint32_t sw[xsum::kSlotWords];
-#pragma unroll
-        for (int k = 0; k < xsum::kSlotWords; k++) sw[k] = __shfl_sync(0xffffffffu, w[k], ev);
-        if (bad || !xsum::apply_segment(bits, sw)) redo((unsigned)(b * 32 + ev), element((unsigned)(b * 32 + ev)));
-      }
-      cur = ev + 1;
+      for (int k = 0; k < 8; k++) redo((unsigned)(b * 32 + k0 + k), v[k]);
     }
   };
   const int ngrp = (nb + kXsGroup - 1) / kXsGroup;
@@ -324,15 +286,15 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
         for (int i = 0; i < kXsRawPf; i++) {
           rawn[i] = 0.f;
           if (m) {
-            const int ent = __ffs(m) - 1;
+            const int k = __ffs(m) - 1;
             m &= m - 1u;
-            rawn[i] = element((unsigned)((b + 1) * 32) + __fns(nh.z, 0u, ent + 1));
+            rawn[i] = element((unsigned)((b + 1) * 32 + k));
           }
         }
       }
     }
     XS_TICK(0);
-    if (hdr.x == 0xffffffffu) { walk(b); XS_TICK(3); continue; }
+    if (hdr.x == 0xffffffffu) { redo_batch(b); XS_TICK(3); continue; }
     const uint32_t start = bits;
     const int st_redo0 = st_redo;
     bool ok = true;
@@ -345,23 +307,25 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
                                (int32_t)t1.z, ok);
       bits = xsum::f2u(((xsum::u2f(bits) + xsum::u2f(t1.w)) + xsum::u2f(t2.x)) + xsum::u2f(t2.y));
       XS_TICK(1);
-      if ((hdr.y >> i) & 1u) {                                    // the entry ends at a serial segment
-        const unsigned g = (unsigned)(b * 32) + __fns(hdr.z, 0u, i + 1);
-        const int si = __popc(hdr.y & ((1u << i) - 1u));
+      const uint2 sr = *reinterpret_cast<const uint2*>(rec + 18 + kXsEntWords * i);   // serial run: length, first slot
+      for (int j = 0; j < (int)sr.x; j++) {
+        const int k = (int)sr.y + j;
+        const unsigned g = (unsigned)(b * 32 + k);
+        const int si = __popc(hdr.y & ((1u << k) - 1u));
         float v;
         if (raw_ok && si < kXsRawPf) {
           v = raw[0];
 #pragma unroll
-          for (int k = 1; k < kXsRawPf; k++) v = (si == k) ? raw[k] : v;
+          for (int r = 1; r < kXsRawPf; r++) v = (si == r) ? raw[r] : v;
         } else {
-          v = element(g);                                         // (no prefetch across group boundaries)
+          v = element(g);                                         // (no prefetch across group boundaries / beyond kXsRawPf)
         }
         redo(g, v);
-        XS_TICK(2);
       }
+      XS_TICK(2);
     }
     if (ok) { st_rec++; st_ent += count; }
-    else { bits = start; st_redo = st_redo0; walk(b); XS_TICK(3); }
+    else { bits = start; st_redo = st_redo0; redo_batch(b); XS_TICK(3); }
   }
   if (lane == 0) {
     q.sc.psum[e] = xsum::u2f(bits);

@@ -685,13 +685,12 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     sp.xs_nseg = (int)((N + 31) / 32);
     sp.xs_nchunks = (sp.xs_nseg + 255) / 256;
     sp.xs_nbatches = (sp.xs_nseg + 31) / 32;
-    sp.xs_ctot = nullptr; sp.xs_slots = nullptr; sp.xs_recs = nullptr;
+    sp.xs_ctot = nullptr; sp.xs_recs = nullptr;
     TRY(E->dmalloc(&sp.xs_stats, (size_t)8 * B));
     if (!(ev && std::strcmp(ev, "serial") == 0)) {
       TRY(E->dmalloc(&sp.xs_ctot, (size_t)sp.xs_nchunks * B));
       TRY(E->dmalloc(&sp.xs_cflag, (size_t)sp.xs_nchunks * B));
       TRY(E->dmalloc(&sp.xs_epoch, (size_t)B));
-      TRY(E->dmalloc(&sp.xs_slots, (size_t)sp.xs_nseg * 20 * B));
       TRY(E->dmalloc(&sp.xs_recs, (size_t)sp.xs_nbatches * 192 * B));
     }
   }
@@ -732,8 +731,8 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     v.sc.xi += 2 * e0; v.sc.t += e0; v.sc.force += 2 * e0; v.sc.probes += (size_t)e0 * RLFC_NUM_PROBES;
     v.sc.callLearn += e0; v.sc.Cd += e0; v.sc.Cl += e0; v.sc.obs += 2 * e0; v.sc.active += e0; v.sc.iters += 2 * e0;
     v.sc.psum += e0; v.sc.any_active += g;
-    if (v.xs_slots) {
-      v.xs_ctot += (size_t)e0 * v.xs_nchunks; v.xs_slots += (size_t)e0 * v.xs_nseg * 20;
+    if (v.xs_recs) {
+      v.xs_ctot += (size_t)e0 * v.xs_nchunks;
       v.xs_cflag += (size_t)e0 * v.xs_nchunks; v.xs_epoch += e0;
       v.xs_recs += (size_t)e0 * v.xs_nbatches * 192;
     }

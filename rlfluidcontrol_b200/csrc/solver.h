@@ -99,11 +99,10 @@ struct SolverParams {
   const ForcePt *force_pts; int nforce;
   const SamplePt *probe_pts; int nprobe;
   int rr_blocks;            // number of per-env partial sums written by the increment kernel
-  // Field.sum as segment summaries (exact_sum.cuh); xs_slots == nullptr selects the plain serial chain (k_psum)
+  // Field.sum as segment summaries (exact_sum.cuh); xs_recs == nullptr selects the plain serial chain (k_psum)
   double *xs_ctot;          // [B][xs_nchunks] chunk totals, valid when xs_cflag == xs_epoch + 1
   unsigned *xs_cflag;       // [B][xs_nchunks]
   unsigned *xs_epoch;       // [B] passes completed
-  unsigned *xs_slots;       // [B][xs_nseg][20] segment summaries
   unsigned *xs_recs;        // [B][xs_nbatches][192] batch records (32 summaries condensed)
   int xs_nseg, xs_nchunks, xs_nbatches;
   int *xs_stats;            // [B][8] counters of the last serial pass (rlfc_env_field_sum_stats)

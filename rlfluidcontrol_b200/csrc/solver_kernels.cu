@@ -1325,7 +1325,7 @@ int launch_smooth0(const SolverParams& q, const float* r_in, float* r_out, int w
 }
 
 int launch_psum(const SolverParams& q, cudaStream_t st) {
-  if (!q.xs_slots) {                    // RLFC_PSUM=serial: the plain dependent-add chain, one warp per environment
+  if (!q.xs_recs) {                     // RLFC_PSUM=serial: the plain dependent-add chain, one warp per environment
     k_psum<<<q.B, 32, 0, st>>>(q);
     return 1;
   }

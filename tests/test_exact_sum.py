@@ -85,7 +85,7 @@ def test_matches_serial_loop_on_adversarial_data(xs):
             crossed += st[4]
             walked += st[5]
     assert rejected > 0, "the validity check of the summaries was never exercised"
-    assert crossed > 0 and walked > 0, "stretch tables / the slot-by-slot walk were never exercised"
+    assert crossed > 0 and walked > 0, "batch records / the redo of a whole batch were never exercised"
 
 
 def test_pressure_fields_of_the_oracle(xs, oracle, init_state):
@@ -98,7 +98,7 @@ def test_pressure_fields_of_the_oracle(xs, oracle, init_state):
         a = p[1:-1, 1:-1].ravel()
         same, s, par, st = both(xs, a)
         assert same and s == np.float32(oracle.Field(p.shape[0], p.shape[1], values=p).sum())
-        assert st[2] + st[3] < 0.05 * sum(st[:3]), st
+        assert st[2] < 0.05 * sum(st[:3]) and st[5] <= 4, st
         env.update2()
 
 

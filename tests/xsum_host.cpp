@@ -18,8 +18,8 @@ float xs_serial(const float* a, long n) {
   return s;
 }
 
-// stats[0..2] = segments summarised as one table / split / serial, stats[3] = summaries rejected by the serial pass,
-// stats[4] = batches crossed by their record, stats[5] = batches walked summary by summary.
+// stats[0..2] = segments summarised as one table / split / serial, stats[3] = batch records rejected by the serial pass,
+// stats[4] = batches crossed by their record, stats[5] = batches redone as genuine additions.
 // pred_noise perturbs the predicted accumulator (relative) to exercise wrong predictions.
 float xs_parallel(const float* a, long n, double pred_noise, long* stats) {
   const long nseg = (n + kSeg - 1) / kSeg;
@@ -57,8 +57,8 @@ float xs_parallel(const float* a, long n, double pred_noise, long* stats) {
       normalise_table(w[k] + 1);
       if (w[k][0] == kSplit) normalise_table(w[k] + kSlotB);
     }
-    // record (sequential composition; the device scans a tree)
-    struct Entry { uint32_t t[7]; float raw[3]; int serial_slot; };
+    // record (sequential composition; the device scans a tree); a run of consecutive serial summaries is one entry
+    struct Entry { uint32_t t[7]; float raw[3]; int serial_slot, serial_run; };
     std::vector<Entry> rec;
     uint32_t C[7];
     std::memcpy(C, ident, sizeof(C));
@@ -66,49 +66,40 @@ float xs_parallel(const float* a, long n, double pred_noise, long* stats) {
       if (w[k][0] == kOne) {
         uint32_t g[7]; std::memcpy(g, w[k] + 1, sizeof(g));
         compose_tables(C, g); std::memcpy(C, g, sizeof(C));
+      } else if (w[k][0] == kSplit) {
+        Entry en; en.serial_slot = -1; en.serial_run = 0;
+        uint32_t g[7]; std::memcpy(g, w[k] + 1, sizeof(g));
+        compose_tables(C, g); std::memcpy(en.t, g, sizeof(g));
+        for (int r = 0; r < 3; r++) en.raw[r] = u2f(w[k][kSlotRaw + r]);
+        std::memcpy(C, w[k] + kSlotB, sizeof(C));
+        rec.push_back(en);
+      } else if (k > 0 && w[k - 1][0] == kSerial) {
+        rec.back().serial_run++;
       } else {
-        Entry en; en.serial_slot = -1; en.raw[0] = en.raw[1] = en.raw[2] = -0.f;
-        if (w[k][0] == kSplit) {
-          uint32_t g[7]; std::memcpy(g, w[k] + 1, sizeof(g));
-          compose_tables(C, g); std::memcpy(en.t, g, sizeof(g));
-          for (int r = 0; r < 3; r++) en.raw[r] = u2f(w[k][kSlotRaw + r]);
-          std::memcpy(C, w[k] + kSlotB, sizeof(C));
-        } else {
-          std::memcpy(en.t, C, sizeof(C));
-          en.serial_slot = k;
-          std::memcpy(C, ident, sizeof(C));
-        }
+        Entry en; en.raw[0] = en.raw[1] = en.raw[2] = -0.f;
+        std::memcpy(en.t, C, sizeof(C));
+        en.serial_slot = k; en.serial_run = 1;
+        std::memcpy(C, ident, sizeof(C));
         rec.push_back(en);
       }
     }
-    { Entry en; std::memcpy(en.t, C, sizeof(C)); en.raw[0] = en.raw[1] = en.raw[2] = -0.f; en.serial_slot = -1; rec.push_back(en); }
-    bool walk = rec.size() > 15;
-    if (!walk) {
+    { Entry en; std::memcpy(en.t, C, sizeof(C)); en.raw[0] = en.raw[1] = en.raw[2] = -0.f; en.serial_slot = -1; en.serial_run = 0; rec.push_back(en); }
+    bool redo_batch = rec.size() > 15;
+    if (!redo_batch) {
       const uint32_t start = bits;
       bool ok = true;
       for (const Entry& en : rec) {
         bits = apply_table(bits, en.t[0], (int32_t)en.t[1], (int32_t)en.t[2], (int32_t)en.t[3], (int32_t)en.t[4], (int32_t)en.t[5],
                            (int32_t)en.t[6], ok);
         volatile float sv = u2f(bits); sv = sv + en.raw[0]; sv = sv + en.raw[1]; sv = sv + en.raw[2]; bits = f2u(sv);
-        if (en.serial_slot >= 0) redo(bits, b0 + en.serial_slot);
+        for (int j = 0; j < en.serial_run; j++) redo(bits, b0 + en.serial_slot + j);
       }
       if (ok) stats[4]++;
-      else { bits = start; walk = true; }
+      else { bits = start; redo_batch = true; stats[3]++; }
     }
-    if (walk) {
+    if (redo_batch) {                    // the whole batch as genuine additions
       stats[5]++;
-      for (int k = 0; k < 32; k++) {
-        if (w[k][0] == kOne) {
-          const uint32_t* t = w[k] + 1;
-          bool ok = true;
-          const uint32_t nb = apply_table(bits, t[0], (int32_t)t[1], (int32_t)t[2], (int32_t)t[3], (int32_t)t[4], (int32_t)t[5],
-                                          (int32_t)t[6], ok);
-          if (ok) bits = nb; else { stats[3]++; redo(bits, b0 + k); }
-        } else if (!apply_segment(bits, w[k])) {
-          if (w[k][0] != kSerial) stats[3]++;
-          redo(bits, b0 + k);
-        }
-      }
+      for (int k = 0; k < 32; k++) redo(bits, b0 + k);
     }
   }
   return u2f(bits);

@@ -14,6 +14,6 @@ with R.AFCCylinderBatch(n_envs) as env:
     for k in range(3):
         env.update2(a if k == 0 else None)
     st = env.field_sum_stats()
-    print("mean over envs [batches by record, batches walked, entries applied, segments redone | cycles: setup, entries, serial segments, walks]:")
+    print("mean over envs [batches by record, batches redone, entries applied, segments redone | cycles: setup, entries, serial segments, walks]:")
     print(np.round(st.mean(axis=0), 1).tolist())
     print("max:", st.max(axis=0).tolist())
