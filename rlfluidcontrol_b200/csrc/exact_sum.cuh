@@ -148,25 +148,28 @@ XS_HD void build_segment(Get get, int cnt, double pred_start, uint32_t* slot) {
     pred = pred + a;
     const uint32_t kn = key_of(pred);
     const bool change = kn != key_prev || !key_ok(key_prev);
-    if (state == 0) {
-      if (change) {
+    // one call site for the table update (threads of a warp are in different states: keep them converged):
+    // state 0 commits the PREVIOUS addition once this one turned out not to be the change; state 2 commits this one
+    const bool commit = !change && (state == 0 ? pending : state == 2);
+    const float val = state == 0 ? pend : a;
+    if (commit) run.add(val);
+    if (state == 0 && !change) { pend = a; pending = true; }
+    if (change || state == 1) {          // rare
+      if (state == 0) {
         good = run.good || run.empty;
         run.store(slot + 1);
         slot[kSlotRaw] = pending ? f2u(pend) : kNegZero;
         slot[kSlotRaw + 1] = f2u(a);
         pending = false;
         state = 1;
+      } else if (state == 1) {           // a genuine addition whatever it does; the second table starts behind it
+        slot[kSlotRaw + 2] = f2u(a);
+        run.start(kn);
+        if (!key_ok(kn)) run.good = false;   // only acceptable if nothing follows (checked through `empty`)
+        state = 2;
       } else {
-        if (pending) run.add(pend);
-        pend = a; pending = true;
+        serial = true;
       }
-    } else if (state == 1) {             // a genuine addition whatever it does; the second table starts behind it
-      slot[kSlotRaw + 2] = f2u(a);
-      run.start(kn);
-      if (!key_ok(kn)) run.good = false; // only acceptable if nothing follows (checked through `empty`)
-      state = 2;
-    } else {
-      if (change) serial = true; else run.add(a);
     }
     key_prev = kn;
   }

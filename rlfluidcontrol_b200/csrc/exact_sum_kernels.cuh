@@ -55,7 +55,7 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
   __shared__ double wsum[kXsThreads / 32];
   __shared__ double base_pred;
   __shared__ double wpart[kXsThreads / 32];
-  const int c = blockIdx.x, e = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int e = blockIdx.x, c = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int len = q.m - 2;
   const long long N = (long long)(q.n - 2) * len, base = (long long)c * kXsChunk;
   const float* p = q.lev[0].x + (size_t)e * q.stride;
@@ -82,7 +82,8 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
   {
     // Chunk totals travel between the CTAs of one environment through global memory (single pass, "look-back"):
     // publish this chunk's total, then wait for the totals of the chunks before it.  CTAs are dispatched in
-    // blockIdx order (chunk index fastest), so the CTAs waited for are already running; the wait is bounded
+    // blockIdx order and the chunk index is the SLOW grid dimension, so the CTAs waited for started a whole row of
+    // environments earlier and have normally published already; the wait is bounded
     // all the same -- the total only feeds the PREDICTION, a wrong one merely sends segments to the serial path.
     const unsigned ep = q.xs_epoch[e] + 1u;                       // k_xsum_chain bumps the epoch after every pass
     volatile double* ct = q.xs_ctot + (size_t)e * q.xs_nchunks;

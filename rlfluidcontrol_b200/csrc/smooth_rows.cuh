@@ -228,7 +228,12 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
   }
   __syncthreads();
 
+#ifdef RLFC_ROWS_TIMING        // per-warp busy time between two step barriers (tools: which stage does a step wait for?)
+  long long busy_ = 0, tk_ = clock64();
+#define RLFC_STEP_SYNC() do { busy_ += clock64() - tk_; __syncthreads(); tk_ = clock64(); } while (0)
+#else
 #define RLFC_STEP_SYNC() __syncthreads()
+#endif
   double rr = 0.0;
   if (warp < 4) {
     // ------------------------------------------------------------------ sweep g = warp + 1, row t - L - 2g
@@ -435,6 +440,10 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
     for (int q = t_end + 2; q <= t_end + kPF; q++) mbar_wait(bars + ((q - 1) & (kCoefSlots - 1)), ((unsigned)(q - 1) >> kCoefShift) & 1u);
   }
 #undef RLFC_STEP_SYNC
+#ifdef RLFC_ROWS_TIMING
+  if (XMODE == 3 && blockIdx.x == 0 && lane == 0)
+    printf("rows level0 C=%d warp %d: busy %lld cycles over %d steps = %lld per step\n", C, warp, busy_, t_end, busy_ / t_end);
+#endif
   __syncthreads();
   if (threadIdx.x == 0)
     for (int k = 0; k < kCoefSlots; k++) mbar_inval(bars + k);

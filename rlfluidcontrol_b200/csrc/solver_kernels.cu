@@ -1329,7 +1329,7 @@ int launch_psum(const SolverParams& q, cudaStream_t st) {
     k_psum<<<q.B, 32, 0, st>>>(q);
     return 1;
   }
-  const dim3 grid(q.xs_nchunks, q.B);
+  const dim3 grid(q.B, q.xs_nchunks);     // chunk index slow: see the look-back in k_xsum_tables
   k_xsum_tables<<<grid, kXsThreads, 0, st>>>(q);
   k_xsum_chain<<<q.B, 32, 0, st>>>(q);
   return 2;
