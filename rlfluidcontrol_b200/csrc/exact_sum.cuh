@@ -80,7 +80,7 @@ struct Table {
 struct Run {
   uint32_t key, sgnmask, Rb, lim;
   int32_t P0, P1, mn0, mn1, mx0, mx1;
-  bool good, empty;
+  int good, empty;                       // (ints, not bools: the compiler packs bools into bytes and pays PRMTs for it)
   XS_HD void start(uint32_t key_) {
     key = key_;
     const uint32_t es = key & 255u;
@@ -88,18 +88,18 @@ struct Run {
     Rb = (es << 23) | 0x400000u;
     lim = (es - 2u) << 23;                         // |addend| must be below 2^(e-2)
     P0 = P1 = 0; mn0 = mn1 = INT32_MAX; mx0 = mx1 = INT32_MIN;
-    good = true; empty = true;
+    good = 1; empty = 1;
   }
   XS_HD void add(float a) {
     const uint32_t ab = f2u(a);
-    good = good && (ab & 0x7fffffffu) < lim;       // also rejects Inf / NaN
+    good &= (int)((ab & 0x7fffffffu) < lim);       // also rejects Inf / NaN
     const float b = u2f(ab ^ sgnmask);
     const uint32_t r0 = Rb | ((uint32_t)P0 & 1u), r1 = Rb | (((uint32_t)P1 & 1u) ^ 1u);
     P0 += (int32_t)(f2u(u2f(r0) + b) - r0);
     P1 += (int32_t)(f2u(u2f(r1) + b) - r1);
     mn0 = P0 < mn0 ? P0 : mn0; mx0 = P0 > mx0 ? P0 : mx0;
     mn1 = P1 < mn1 ? P1 : mn1; mx1 = P1 > mx1 ? P1 : mx1;
-    empty = false;
+    empty = 0;
   }
   // words [key, D0, D1, lo0, hi0, lo1, hi1]; every significand after an addition must stay in
   // [2^23 + 1, 2^24 - 1] (header comment)
@@ -139,7 +139,7 @@ XS_HD void build_segment(Get get, int cnt, double pred_start, uint32_t* slot) {
   Run run;
   run.start(key_prev);
   int state = 0;                         // 0: first table, 1: the addition after the change is due, 2: second table
-  bool good = true, pending = false, serial = false;
+  int good = 1, pending = 0, serial = 0;
   float pend = 0.f;                      // the last addition, not yet committed to the first table
   for (int w = 0; w < kSlotWords; w++) slot[w] = 0;
   slot[kSlotRaw] = slot[kSlotRaw + 1] = slot[kSlotRaw + 2] = kNegZero;
@@ -150,25 +150,25 @@ XS_HD void build_segment(Get get, int cnt, double pred_start, uint32_t* slot) {
     const bool change = kn != key_prev || !key_ok(key_prev);
     // one call site for the table update (threads of a warp are in different states: keep them converged):
     // state 0 commits the PREVIOUS addition once this one turned out not to be the change; state 2 commits this one
-    const bool commit = !change && (state == 0 ? pending : state == 2);
+    const bool commit = !change && (state == 0 ? pending != 0 : state == 2);
     const float val = state == 0 ? pend : a;
     if (commit) run.add(val);
-    if (state == 0 && !change) { pend = a; pending = true; }
+    if (state == 0 && !change) { pend = a; pending = 1; }
     if (change || state == 1) {          // rare
       if (state == 0) {
-        good = run.good || run.empty;
+        good = run.good | run.empty;
         run.store(slot + 1);
         slot[kSlotRaw] = pending ? f2u(pend) : kNegZero;
         slot[kSlotRaw + 1] = f2u(a);
-        pending = false;
+        pending = 0;
         state = 1;
       } else if (state == 1) {           // a genuine addition whatever it does; the second table starts behind it
         slot[kSlotRaw + 2] = f2u(a);
         run.start(kn);
-        if (!key_ok(kn)) run.good = false;   // only acceptable if nothing follows (checked through `empty`)
+        if (!key_ok(kn)) run.good = 0;       // only acceptable if nothing follows (checked through `empty`)
         state = 2;
       } else {
-        serial = true;
+        serial = 1;
       }
     }
     key_prev = kn;
@@ -180,8 +180,8 @@ XS_HD void build_segment(Get get, int cnt, double pred_start, uint32_t* slot) {
     run.store(slot + 1);
     return;
   }
-  if (state == 1) { run.start(key_prev); run.good = true; }     // nothing behind the change: empty second table
-  good = good && !serial && (run.good || run.empty);
+  if (state == 1) { run.start(key_prev); run.good = 1; }        // nothing behind the change: empty second table
+  good = good & (serial ^ 1) & (run.good | run.empty);
   if (!good) { slot[0] = kSerial; return; }
   slot[0] = kSplit;
   run.store(slot + kSlotB);
