@@ -671,7 +671,6 @@ k_mg_up0(const __grid_constant__ SolverParams q, float* __restrict__ r_all) {
 // xc[I][J]; their outward neighbours take the adjacent coarse cell's value, or -- at the domain edge, where
 // d.setBC copies the adjacent interior value (MG.pde:139-152) -- the cell's own.  x += d on the children and on the
 // ghost cells they border, r -= A d written to the smoother's skewed array.
-template <int C>                       // columns per lane of the level-0 row smoother (compile-time: the skewed index divides by it)
 __global__ void __launch_bounds__(256)
 k_mg_up0_blk(const __grid_constant__ SolverParams q, const float* __restrict__ r_all) {
   const int e = blockIdx.z;
@@ -692,7 +691,7 @@ k_mg_up0_blk(const __grid_constant__ SolverParams q, const float* __restrict__ r
   const float dWc = (I > 1) ? xc[(I - 1) * CPc + J] : dc, dEc = (I < nci) ? xc[(I + 1) * CPc + J] : dc;
   const float dSc = (J > 1) ? xc[I * CPc + J - 1] : dc, dNc = (J < ncj) ? xc[I * CPc + J + 1] : dc;
   const int i0 = 2 * I - 1, j0 = 2 * J - 1;
-  constexpr int CP = rows_CP(C);
+  const int C = L0.rt.C, CP = rows_CP(C);
   float xo[2][2], ro[2][2];
 #pragma unroll
   for (int a = 0; a < 2; a++)
@@ -1288,19 +1287,7 @@ int launch_mg_coarse(const SolverParams& q, cudaStream_t st) {
 
 int launch_mg_up0(const SolverParams& q, float* r, cudaStream_t st) {
   dim3 blk(32, 8);
-  if (q.use_rows && !q.lev[0].wave) {
-    const dim3 grid = grid2d(q.lev[1].m - 2, q.lev[1].n - 2, q.B, blk);
-    switch (q.lev[0].rt.C) {
-      case 1: k_mg_up0_blk<1><<<grid, blk, 0, st>>>(q, r); break;
-      case 2: k_mg_up0_blk<2><<<grid, blk, 0, st>>>(q, r); break;
-      case 3: k_mg_up0_blk<3><<<grid, blk, 0, st>>>(q, r); break;
-      case 4: k_mg_up0_blk<4><<<grid, blk, 0, st>>>(q, r); break;
-      case 5: k_mg_up0_blk<5><<<grid, blk, 0, st>>>(q, r); break;
-      case 6: k_mg_up0_blk<6><<<grid, blk, 0, st>>>(q, r); break;
-      case 7: k_mg_up0_blk<7><<<grid, blk, 0, st>>>(q, r); break;
-      default: k_mg_up0_blk<8><<<grid, blk, 0, st>>>(q, r); break;
-    }
-  }
+  if (q.use_rows && !q.lev[0].wave) k_mg_up0_blk<<<grid2d(q.lev[1].m - 2, q.lev[1].n - 2, q.B, blk), blk, 0, st>>>(q, r);
   else k_mg_up0<false><<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, r);
   return 1;
 }
