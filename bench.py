@@ -335,8 +335,9 @@ def run_b200(args):
         prof = []
         if rank == 0 and args.profile_steps > 0:
             env.set_profiling(True)
-            for _ in range(args.profile_steps):
-                dev_step(step_idx); step_idx += 1
+            for _ in range(args.profile_steps):   # rank 0 alone: no collective in here (the other ranks do not take part)
+                env.step_device(acts_dev[step_idx].data_ptr(), obs_dev.data_ptr(), rew_dev.data_ptr(), done_dev.data_ptr())
+                step_idx += 1
             torch.cuda.synchronize()
             prof = env.get_profile()
             env.set_profiling(False)
