@@ -140,41 +140,39 @@ XS_HD void build_segment(Get get, int cnt, double pred_start, uint32_t* slot) {
   run.start(key_prev);
   int state = 0;                         // 0: first table, 1: the addition after the change is due, 2: second table
   int good = 1, pending = 0, serial = 0;
-  float pend = 0.f;                      // the last addition, not yet committed to the first table
+  // additions enter a table one step late (`pend`), so that the one before a change can still be kept out of it
+  float pend = 0.f;
+  int force = key_ok(key_prev) ? 0 : 1;  // non-zero: the next addition takes the rare path whatever its key
   for (int w = 0; w < kSlotWords; w++) slot[w] = 0;
   slot[kSlotRaw] = slot[kSlotRaw + 1] = slot[kSlotRaw + 2] = kNegZero;
   for (int k = 0; k < cnt; k++) {
     const float a = get(k);
     pred = pred + a;
     const uint32_t kn = key_of(pred);
-    const bool change = kn != key_prev || !key_ok(key_prev);
-    // one call site for the table update (threads of a warp are in different states: keep them converged):
-    // state 0 commits the PREVIOUS addition once this one turned out not to be the change; state 2 commits this one
-    const bool commit = !change && (state == 0 ? pending != 0 : state == 2);
-    const float val = state == 0 ? pend : a;
-    if (commit) run.add(val);
-    if (state == 0 && !change) { pend = a; pending = 1; }
-    if (change || state == 1) {          // rare
-      if (state == 0) {
-        good = run.good | run.empty;
-        run.store(slot + 1);
-        slot[kSlotRaw] = pending ? f2u(pend) : kNegZero;
-        slot[kSlotRaw + 1] = f2u(a);
-        pending = 0;
-        state = 1;
-      } else if (state == 1) {           // a genuine addition whatever it does; the second table starts behind it
-        slot[kSlotRaw + 2] = f2u(a);
-        run.start(kn);
-        if (!key_ok(kn)) run.good = 0;       // only acceptable if nothing follows (checked through `empty`)
-        state = 2;
-      } else {
-        serial = 1;
-      }
+    if (kn == key_prev && !force) {      // common path (threads of a warp stay converged here)
+      if (pending) run.add(pend);
+      pend = a; pending = 1;
+      continue;
+    }
+    if (state == 0) {                    // the change: close the first table WITHOUT the previous addition
+      good = run.good | run.empty;
+      run.store(slot + 1);
+      slot[kSlotRaw] = pending ? f2u(pend) : kNegZero;
+      slot[kSlotRaw + 1] = f2u(a);
+      pending = 0;
+      state = 1; force = 1;
+    } else if (state == 1) {             // a genuine addition whatever it does; the second table starts behind it
+      slot[kSlotRaw + 2] = f2u(a);
+      run.start(kn);
+      if (!key_ok(kn)) run.good = 0;     // only acceptable if nothing follows (checked through `empty`)
+      state = 2; force = 0;
+    } else {
+      serial = 1;                        // a second change: left to the serial pass
     }
     key_prev = kn;
   }
+  if (pending) run.add(pend);
   if (state == 0) {
-    if (pending) run.add(pend);
     if (!run.good) { slot[0] = kSerial; return; }
     slot[0] = kOne;
     run.store(slot + 1);

@@ -20,32 +20,30 @@ constexpr int kXsRecWords = 8 + kXsRecEntries * kXsEntWords + 4;   // batch reco
 // row is at least half a CTA wide (WIDE: at most two row ends per stride of kXsThreads elements), so that the
 // loads of an unrolled loop are not separated by control flow.
 template <bool WIDE>
-struct XsCursor {
-  int i, j, len, P;
-  __device__ __forceinline__ XsCursor(long long K, int len_, int P_) : len(len_), P(P_) {
-    const unsigned k = (unsigned)K;                               // rlfc_env_create rejects grids beyond 2^31 cells
-    i = 1 + (int)(k / (unsigned)len_); j = 1 + (int)(k % (unsigned)len_);
-  }
-  __device__ __forceinline__ size_t off() const { return (size_t)i * P + j; }
-  __device__ __forceinline__ void advance() {
-    j += kXsThreads;
-    if (WIDE) {
-      const bool a = j > len; j -= a ? len : 0; i += a;
-      const bool b = j > len; j -= b ? len : 0; i += b;
-    } else {
-      while (j > len) { j -= len; i++; }
-    }
-  }
-};
-
-template <bool WIDE>
 __device__ __forceinline__ void xs_fill(const SolverParams& q, const float* p, long long base, long long N, int t, float* buf) {
-  XsCursor<WIDE> cur(base + t, q.m - 2, q.P);
+  // 32-bit incremental addressing (rlfc_env_create rejects grids beyond 2^31 cells): element K = base + t + 256 u
+  // sits at row 1 + K / len, column 1 + K % len; a stride of 256 elements passes at most two row ends when WIDE.
+  const int len = q.m - 2, P = q.P, skip = P - len;
+  const unsigned k0 = (unsigned)base + (unsigned)t;
+  int j = 1 + (int)(k0 % (unsigned)len);
+  int off = (1 + (int)(k0 / (unsigned)len)) * P + j;
+  const int left = (int)((N - base) < (long long)kXsChunk ? (N - base) : (long long)kXsChunk) - t;   // u*256 < left <=> in range
+  float* dst = buf + (t >> 5) * kXsPad + (t & 31);                // local index t + 256 u: segment (t >> 5) + 8 u
+  const float* ptr = p + off;                                     // running pointer: one 64-bit add per element
+  const unsigned uskip = (unsigned)skip;
+  asm volatile("" : "+l"(ptr), "+r"(j));                          // keep them in registers (no rematerialisation per load)
 #pragma unroll 8
   for (int u = 0; u < xsum::kSeg; u++) {
-    const int kl = t + u * kXsThreads;                            // local index: segment kl / 32, element kl % 32
-    buf[(kl >> 5) * kXsPad + (kl & 31)] = (base + kl < N) ? p[cur.off()] : 0.f;
-    cur.advance();
+    dst[u * (kXsThreads / 32) * kXsPad] = (u * kXsThreads < left) ? *ptr : 0.f;
+    j += kXsThreads;
+    unsigned inc = kXsThreads;
+    if (WIDE) {
+      const bool a = j > len; j -= a ? len : 0; inc += a ? uskip : 0u;
+      const bool b = j > len; j -= b ? len : 0; inc += b ? uskip : 0u;
+    } else {
+      while (j > len) { j -= len; inc += uskip; }
+    }
+    ptr += inc;
   }
 }
 
