@@ -210,9 +210,9 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
   const int nseg = q.xs_nseg, nb = q.xs_nbatches;
   const float* p = q.lev[0].x + (size_t)e * q.stride;
   const uint32_t* recs = q.xs_recs + (size_t)e * nb * kXsRecWords;
-  auto element = [&](unsigned g) {                                 // this lane's element of segment g (0 past the end)
-    const unsigned K = g * xsum::kSeg + lane;
-    return K < N ? p[(size_t)(1u + K / len) * P + 1u + K % len] : 0.f;
+  auto element = [&](unsigned g) {                                 // this lane's element of segment g (-0 past the end:
+    const unsigned K = g * xsum::kSeg + lane;                      //  s + -0.f == s for every s)
+    return K < N ? p[(size_t)(1u + K / len) * P + 1u + K % len] : -0.f;
   };
   auto fetch = [&](int grp) {                                     // records of batches grp*kXsGroup ..; one commit group
     const int b0 = grp * kXsGroup, n16 = min(kXsGroup, nb - b0) * (kXsRecWords / 4);   // 16-byte pieces (contiguous records)
@@ -232,27 +232,25 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
 #endif
   uint32_t bits = 0u;                                             // s = +0.f
   // 32 genuine additions of segment g; lane u holds element u in v
-  auto redo = [&](unsigned g, float v) {
+  auto redo = [&](float v) {
     st_redo++;
-    const unsigned K0 = g * xsum::kSeg;
-    const int cnt = K0 >= N ? 0 : (N - K0 >= (unsigned)xsum::kSeg ? xsum::kSeg : (int)(N - K0));
     float el[xsum::kSeg];
 #pragma unroll
     for (int u = 0; u < xsum::kSeg; u++) el[u] = __shfl_sync(0xffffffffu, v, u);
     float s = xsum::u2f(bits);
 #pragma unroll
-    for (int u = 0; u < xsum::kSeg; u++) s = (u < cnt) ? s + el[u] : s;
+    for (int u = 0; u < xsum::kSeg; u++) s += el[u];
     bits = xsum::f2u(s);
   };
-  // batch b as genuine additions, from the accumulator in `bits`
+  // batch b as genuine additions, from the accumulator in `bits` (one call site: the code stays small)
   auto redo_batch = [&](int b) {
     st_walk++;
-    for (int k0 = 0; k0 < 32; k0 += 8) {                          // 8 segments' elements in flight
-      float v[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++) v[k] = element((unsigned)(b * 32 + k0 + k));
-#pragma unroll
-      for (int k = 0; k < 8; k++) redo((unsigned)(b * 32 + k0 + k), v[k]);
+    float v = element((unsigned)(b * 32));
+#pragma unroll 1
+    for (int k = 0; k < 32; k++) {
+      const float vn = element((unsigned)(b * 32 + k + 1));       // next segment's elements in flight
+      redo(v);
+      v = vn;
     }
   };
   const int ngrp = (nb + kXsGroup - 1) / kXsGroup;
@@ -319,7 +317,7 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
         } else {
           v = element(g);                                         // (no prefetch across group boundaries / beyond kXsRawPf)
         }
-        redo(g, v);
+        redo(v);
       }
       XS_TICK(2);
     }
