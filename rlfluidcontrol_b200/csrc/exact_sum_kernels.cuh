@@ -201,9 +201,14 @@ __device__ __forceinline__ void xs_cp16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 
+__device__ __forceinline__ void xs_cp4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+
 __global__ void __launch_bounds__(32)
 k_xsum_chain(const __grid_constant__ SolverParams q) {
   __shared__ __align__(16) uint32_t ring[2 * kXsGroup][kXsRecWords];
+  __shared__ float stage[32][32];
   const int e = blockIdx.x, lane = threadIdx.x;
   const unsigned len = (unsigned)(q.m - 2), P = (unsigned)q.P;
   const unsigned N = (unsigned)(q.n - 2) * len;                   // rlfc_env_create rejects grids beyond 2^31 cells
@@ -242,16 +247,22 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
     for (int u = 0; u < xsum::kSeg; u++) s += el[u];
     bits = xsum::f2u(s);
   };
-  // batch b as genuine additions, from the accumulator in `bits` (one call site: the code stays small)
+  // batch b as genuine additions, from the accumulator in `bits`: all 1024 elements land in shared memory by
+  // cp.async (one memory round trip for the batch); rolled loops and one call site of redo keep the code small
   auto redo_batch = [&](int b) {
     st_walk++;
-    float v = element((unsigned)(b * 32));
+    __syncwarp();
 #pragma unroll 1
     for (int k = 0; k < 32; k++) {
-      const float vn = element((unsigned)(b * 32 + k + 1));       // next segment's elements in flight
-      redo(v);
-      v = vn;
+      const unsigned K = (unsigned)(b * 32 + k) * xsum::kSeg + lane;
+      if (K < N) xs_cp4(&stage[k][lane], p + (size_t)(1u + K / len) * P + 1u + K % len);
+      else stage[k][lane] = -0.f;
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");          // (also waits for the record group in flight: rare path)
+    __syncwarp();
+#pragma unroll 1
+    for (int k = 0; k < 32; k++) redo(stage[k][lane]);
   };
   const int ngrp = (nb + kXsGroup - 1) / kXsGroup;
   fetch(0);
