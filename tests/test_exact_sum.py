@@ -28,6 +28,8 @@ def xs():
     L.xs_serial.argtypes = [FP, C.c_long]
     L.xs_parallel.restype = C.c_float
     L.xs_parallel.argtypes = [FP, C.c_long, C.c_double, C.POINTER(C.c_long)]
+    L.xs_tree_vs_sequential.restype = C.c_long
+    L.xs_tree_vs_sequential.argtypes = [FP, C.c_long]
     return L
 
 
@@ -100,6 +102,17 @@ def test_pressure_fields_of_the_oracle(xs, oracle, init_state):
         assert same and s == np.float32(oracle.Field(p.shape[0], p.shape[1], values=p).sum())
         assert st[2] < 0.05 * sum(st[:3]) and st[5] <= 4, st
         env.update2()
+
+
+def test_record_scan_order_is_immaterial(xs, init_state):
+    """The kernel condenses 32 summaries with a tree of table compositions, the CPU model composes left to right:
+    every group table must come out bit-identical (composition incl. the dead-half normalisation is associative)."""
+    rng = np.random.default_rng(11)
+    arrays = [init_state["p"][1:-1, 1:-1].ravel()]
+    arrays += [adversarial(k % 11, int(rng.integers(40, 5000)), rng) for k in range(330)]
+    for a in arrays:
+        a = np.ascontiguousarray(a, np.float32)
+        assert xs.xs_tree_vs_sequential(a.ctypes.data_as(FP), a.size) == 0
 
 
 def test_large_array(xs):

@@ -104,4 +104,73 @@ float xs_parallel(const float* a, long n, double pred_noise, long* stats) {
   }
   return u2f(bits);
 }
+
+// The device condenses a batch with a Kogge-Stone scan of table compositions (k_xsum_tables); the serial model
+// above composes left to right.  Composition must be associative INCLUDING the normalisation of dead halves, or the
+// two would disagree.  Returns the number of batches whose group tables (C_k of every lane, E_k of every head)
+// differ between the two orders.
+long xs_tree_vs_sequential(const float* a, long n) {
+  const long nseg = (n + kSeg - 1) / kSeg;
+  std::vector<uint32_t> slots((size_t)nseg * kSlotWords);
+  double pred = 0;
+  for (long g = 0; g < nseg; g++) {
+    const float* seg = a + g * kSeg;
+    const int cnt = (int)((n - g * kSeg) < kSeg ? (n - g * kSeg) : kSeg);
+    build_segment([&](int k) { return seg[k]; }, cnt, pred, &slots[(size_t)g * kSlotWords]);
+    for (int k = 0; k < cnt; k++) pred += (double)seg[k];
+  }
+  const uint32_t ident[7] = {kAnyKey, 0u, 0u, (uint32_t)INT32_MIN, (uint32_t)INT32_MAX, (uint32_t)INT32_MIN, (uint32_t)INT32_MAX};
+  long differ = 0;
+  for (long b0 = 0; b0 < nseg; b0 += 32) {
+    uint32_t X[32][7], v[32][7], type[32];
+    for (int k = 0; k < 32; k++) {
+      uint32_t w[kSlotWords];
+      if (b0 + k < nseg) std::memcpy(w, &slots[(size_t)(b0 + k) * kSlotWords], sizeof(w));
+      else { std::memset(w, 0, sizeof(w)); w[0] = kOne; w[1] = kAnyKey; }
+      type[k] = w[0];
+      normalise_table(w + 1);
+      if (w[0] == kSplit) normalise_table(w + kSlotB);
+      for (int q = 0; q < 7; q++) {
+        X[k][q] = (w[0] == kSerial) ? ident[q] : w[1 + q];
+        v[k][q] = (w[0] == kOne) ? w[1 + q] : (w[0] == kSplit ? w[kSlotB + q] : ident[q]);
+      }
+    }
+    // sequential: C_k = head ? v_k : C_{k-1} o v_k ;  E_k = C_{k-1} o X_k
+    uint32_t Cs[32][7], Es[32][7];
+    for (int k = 0; k < 32; k++) {
+      uint32_t prev[7];
+      std::memcpy(prev, k ? Cs[k - 1] : ident, sizeof(prev));
+      std::memcpy(Cs[k], v[k], sizeof(prev));
+      if (type[k] == kOne) compose_tables(prev, Cs[k]);
+      std::memcpy(Es[k], X[k], sizeof(prev));
+      compose_tables(prev, Es[k]);
+    }
+    // tree, exactly as the kernel: dist = lane - (last head at or below the lane, else 0)
+    uint32_t acc[32][7];
+    std::memcpy(acc, v, sizeof(acc));
+    int dist[32];
+    for (int k = 0; k < 32; k++) {
+      int s0 = 0;
+      for (int j = 0; j <= k; j++) if (type[j] != kOne) s0 = j;
+      dist[k] = k - s0;
+    }
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t nxt[32][7];
+      std::memcpy(nxt, acc, sizeof(acc));
+      for (int k = 0; k < 32; k++)
+        if (k >= o && dist[k] >= o) compose_tables(acc[k - o], nxt[k]);
+      std::memcpy(acc, nxt, sizeof(acc));
+    }
+    bool same = true;
+    for (int k = 0; k < 32; k++) {
+      uint32_t E[7];
+      std::memcpy(E, X[k], sizeof(E));
+      compose_tables(k ? acc[k - 1] : ident, E);
+      same = same && std::memcmp(acc[k], Cs[k], sizeof(E)) == 0;
+      if (type[k] != kOne) same = same && std::memcmp(E, Es[k], sizeof(E)) == 0;
+    }
+    differ += !same;
+  }
+  return differ;
+}
 }
