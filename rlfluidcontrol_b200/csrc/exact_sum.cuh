@@ -13,14 +13,15 @@
 // which the integer model equals IEEE-754 addition) and the accumulator really has the sign and exponent the
 // table was built for.  Tables of different segments are built independently -- in parallel -- from a
 // PREDICTED accumulator (double-precision prefix sums of the data, accurate to ~1e-5 relative, far finer than
-// a binade); the one addition at which the predicted accumulator changes binade or sign is kept as a genuine
-// float addition between two tables.  A last, short serial pass walks the segment summaries with the true
-// accumulator, checks every table's validity condition, and recomputes any segment that fails (wrong
-// prediction, several binade changes, accumulator near zero, Inf/NaN) with the plain serial loop.  Nothing is
-// approximate: a table is only applied when it provably reproduces the serial additions bit for bit.
+// a binade); the addition at which the predicted accumulator changes binade or sign, and its two neighbours, are
+// kept as genuine float additions between two tables.  Tables compose (associatively), so a run of segments
+// condenses into one table.  A last, short serial pass walks the condensed summaries with the true accumulator,
+// checks every table's validity condition, and recomputes whatever fails (wrong prediction, several binade
+// changes, accumulator near zero, Inf/NaN) with the plain serial loop.  Nothing is approximate: a table is only
+// applied when it provably reproduces the serial additions bit for bit.
 //
-// This header holds the host/device core (segment summary + application); tests/test_exact_sum.py drives it
-// on the CPU against the serial loop, solver_kernels.cu wraps it in three kernels.
+// This header holds the host/device core (segment summary, composition, application); tests/test_exact_sum.py
+// drives it on the CPU against the serial loop (tests/xsum_host.cpp), exact_sum_kernels.cuh wraps it in two kernels.
 #pragma once
 #include <climits>
 #include <cstdint>
@@ -65,10 +66,7 @@ XS_HD float u2f(uint32_t u) {
 XS_HD uint32_t key_of(float v) { return f2u(v) >> 23; }
 XS_HD bool key_ok(uint32_t key) { const uint32_t e = key & 255u; return e >= 30u && e <= 254u; }
 
-struct Table {
-  uint32_t key;
-  int32_t D0, D1, lo0, hi0, lo1, hi1;
-};
+// A table is seven words: [key, D0, D1, lo0, hi0, lo1, hi1].
 
 // Running summary of a run of additions for an accumulator with sign/exponent `key`.
 // The integer increment of one addition is read off the FPU instead of being assembled from shifts:  with

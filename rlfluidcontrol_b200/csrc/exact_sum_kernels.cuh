@@ -1,9 +1,9 @@
-// exact_sum_kernels.cuh -- Field.sum (Field.pde:311-318) as three kernels around exact_sum.cuh:
-//   k_xsum_tables  one thread per segment of 32 additions: predicted accumulator before the segment (chunk
-//                  totals handed from CTA to CTA + block scan), then the segment summary (exact_sum.cuh) -> 64 B
-//                  slot, and per warp a condensed batch record
-//   k_xsum_chain   one warp per environment walks the slots with the true accumulator; a segment whose summary
-//                  does not provably apply is redone as 32 genuine float additions
+// exact_sum_kernels.cuh -- Field.sum (Field.pde:311-318) as two kernels around exact_sum.cuh:
+//   k_xsum_tables  one thread per segment of 32 additions: predicted accumulator before the segment (chunk totals
+//                  handed from CTA to CTA + block scan), then the segment summary (exact_sum.cuh); each warp condenses
+//                  its 32 summaries into a batch record of a few "table + float additions" entries
+//   k_xsum_chain   one warp per environment walks the batch records with the true accumulator; a batch whose record
+//                  does not provably apply is redone as genuine float additions
 // The result is bit-identical to the serial loop for any input (tests/test_exact_sum.py, tests/test_gpu_parity.py).
 // Included by solver_kernels.cu inside namespace rlfc::{anonymous}.
 #pragma once
@@ -16,9 +16,9 @@ constexpr int kXsEntWords = 12;                         // record entry: table (
 constexpr int kXsRecEntries = 15;
 constexpr int kXsRecWords = 8 + kXsRecEntries * kXsEntWords + 4;   // batch record: 8 header words + entries (192 words)
 
-// serial index K (i-major over the interior) -> offset in the pitched array.  advance() is branch-free when a
-// row is at least half a CTA wide (WIDE: at most two row ends per stride of kXsThreads elements), so that the
-// loads of an unrolled loop are not separated by control flow.
+// Chunk loader: serial index K (i-major over the interior) -> pitched array.  The pointer update is branch-free when
+// a row is at least half a CTA wide (WIDE: at most two row ends per stride of kXsThreads elements), so that the loads
+// of the unrolled loop are not separated by control flow.
 template <bool WIDE>
 __device__ __forceinline__ void xs_fill(const SolverParams& q, const float* p, long long base, long long N, int t, float* buf) {
   // 32-bit incremental addressing (rlfc_env_create rejects grids beyond 2^31 cells): element K = base + t + 256 u

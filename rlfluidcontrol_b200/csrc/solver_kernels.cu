@@ -25,6 +25,14 @@
 #include "smooth_wave.cuh"
 #include "exact_sum.cuh"
 
+#ifndef RLFC_DOWN_UNROLL
+#define RLFC_DOWN_UNROLL 2      // coarse down pass: blocks in flight per thread
+#endif
+#ifndef RLFC_UP_ROWS
+#define RLFC_UP_ROWS 4          // coarse up pass: rows in flight per warp
+#endif
+constexpr int kDownUnroll = RLFC_DOWN_UNROLL;
+
 namespace rlfc {
 namespace {
 
@@ -565,7 +573,7 @@ __device__ __forceinline__ void coarse_up_pass(const DevLevel& L, const DevLevel
   const float* __restrict__ lx = L.lx;
   const float* __restrict__ ly = L.ly;
   const float* __restrict__ diag = L.diag;
-  constexpr int U = 4;
+  constexpr int U = RLFC_UP_ROWS;
   for (int j = 1 + lane; j <= mj; j += 32) {
     const int cj = (j - 1) / 2 + 1, cjm = (max(j - 1, 1) - 1) / 2 + 1, cjp = (min(j + 1, mj) - 1) / 2 + 1;
     for (int i0 = 1 + warp; i0 <= ni; i0 += nw * U) {
@@ -607,7 +615,7 @@ k_mg_coarse(const __grid_constant__ SolverParams q) {
     const int nci = C.n - 2, ncj = C.m - 2;
     const size_t eo = (size_t)e * L.stride;
     for (int J = 1 + lane; J <= ncj; J += 32)
-#pragma unroll 2
+#pragma unroll kDownUnroll
       for (int I = 1 + warp; I <= nci; I += nw)
         down_block<false>(L, C, L.r + eo, L.d + eo, L.x + eo, C.r + (size_t)e * C.stride, I, J);
     __syncthreads();
