@@ -188,13 +188,19 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
       }
     }
   }
+  // the chunk's records are complete: tell the serial pass, which may already be running (k_xsum_chain)
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    *(volatile unsigned*)(q.xs_rflag + (size_t)e * q.xs_nchunks + c) = q.xs_epoch[e] + 1u;
+  }
 }
 
 // Serial pass.  One warp per environment walks the batch records: per entry one table application (checked),
 // three float additions, and the genuine additions of a run of serial segments where the entry says so.  If any
 // entry of a batch does not provably apply (or the batch has too many heads for a record), the whole batch is
 // redone from its start as 1024 genuine float additions.
-constexpr int kXsGroup = 8;       // batch records per cp.async group; the ring holds two groups
+constexpr int kXsGroup = kXsThreads / 32;   // batch records per cp.async group = one chunk of k_xsum_tables; the ring holds two
 constexpr int kXsRawPf = 4;       // serial segments per batch whose elements are prefetched
 
 __device__ __forceinline__ void xs_cp16(void* smem, const void* gmem) {
@@ -264,18 +270,41 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
 #pragma unroll 1
     for (int k = 0; k < 32; k++) redo(stage[k][lane]);
   };
+  // The records of chunk c are complete when xs_rflag[e][c] carries this pass's epoch.  k_xsum_tables may still be
+  // running (the two kernels are parallel branches of the step graph): wait chunk by chunk.  The wait is bounded --
+  // a flag that never comes is a bug, and a trap is better than a hung GPU.
   const int ngrp = (nb + kXsGroup - 1) / kXsGroup;
-  fetch(0);
+  const unsigned ep = q.xs_epoch[e] + 1u;
+  const volatile unsigned* rf = q.xs_rflag + (size_t)e * q.xs_nchunks;
+  auto ready = [&](int grp) { return rf[grp] == ep; };
+  auto wait_chunk = [&](int grp) {
+    if (lane == 0) {
+      long long spins = 0;
+      while (!ready(grp)) {
+        if (++spins > (1ll << 26)) __trap();
+      }
+    }
+    __syncwarp();
+    __threadfence();
+  };
   float rawn[kXsRawPf];                                           // elements of the next batch's first serial segments
 #pragma unroll
   for (int i = 0; i < kXsRawPf; i++) rawn[i] = 0.f;
-  bool have_raw = false;
+  bool have_raw = false, prefetched = false;
   for (int b = 0; b < nb; b++) {
-    if (b % kXsGroup == 0) {                                      // group boundary: next group in flight, this one landed
+    if (b % kXsGroup == 0) {                                      // chunk boundary
       const int grp = b / kXsGroup;
       __syncwarp();
-      if (grp + 1 < ngrp) { fetch(grp + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (!prefetched) { wait_chunk(grp); fetch(grp); }
+      prefetched = false;
+      if (grp + 1 < ngrp && __shfl_sync(0xffffffffu, (int)ready(grp + 1), 0)) {   // next chunk already there: in flight now
+        __threadfence();
+        fetch(grp + 1);
+        prefetched = true;
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
       __syncwarp();
     }
     const uint32_t* rec = ring[b % (2 * kXsGroup)];

@@ -74,6 +74,9 @@ struct rlfc_env {
   Group whole;                               // the entire batch on the handle's stream (eager / profiled path)
   cudaStream_t aux_stream = nullptr;         // used to capture the bodies of the conditional nodes
   cudaEvent_t fork_ev = nullptr;
+  cudaStream_t psum_stream = nullptr;        // side branch of the step graphs: Field.sum's serial pass (launch_psum_overlapped)
+  cudaEvent_t psum_fork = nullptr, psum_join = nullptr;
+  bool psum_overlap = true;                  // RLFC_PSUM_OVERLAP=0: serial pass after the table kernel
   bool use_graph = true;
   bool eager_groups = false;
   bool fused = true;                         // RLFC_FUSED=0: unfused residual/down0 and project/shift kernels (A/B experiments)
@@ -321,7 +324,7 @@ int capture_half_step(rlfc_env* E, Group& G, cudaStream_t st, const float* sx, c
     }
   }
   // ---- projection tail ----
-  *n_outer += launch_psum(sb, st);
+  *n_outer += E->psum_overlap ? launch_psum_overlapped(sb, st, E->psum_stream, E->psum_fork, E->psum_join) : launch_psum(sb, st);
   if (which == 1 && sp.fast_bc) {   // corrector: Heun average fused in (BDIM.pde:95-96); sx, sy = us, u0x, u0y = step-start buffer
     *n_outer += launch_project_shift_heun(sp, pB, pA, dx, dy, sx, sy, const_cast<float*>(u0x), const_cast<float*>(u0y), st);
     *n_outer += launch_bc_heun(sp, dx, dy, sx, sy, const_cast<float*>(u0x), const_cast<float*>(u0y), st);
@@ -455,6 +458,9 @@ void rlfc_env_destroy(rlfc_env* E) {
     if (g > 0 && G.st) { cudaStreamSynchronize(G.st); cudaStreamDestroy(G.st); }
   }
   if (E->aux_stream) cudaStreamDestroy(E->aux_stream);
+  if (E->psum_stream) cudaStreamDestroy(E->psum_stream);
+  if (E->psum_fork) cudaEventDestroy(E->psum_fork);
+  if (E->psum_join) cudaEventDestroy(E->psum_join);
   if (E->fork_ev) cudaEventDestroy(E->fork_ev);
   for (void* p : E->allocs) cudaFree(p);
   for (void* p : {(void*)E->h_actions, (void*)E->h_obs, (void*)E->h_reward, (void*)E->h_force, (void*)E->h_probes,
@@ -690,6 +696,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     if (!(ev && std::strcmp(ev, "serial") == 0)) {
       TRY(E->dmalloc(&sp.xs_ctot, (size_t)sp.xs_nchunks * B));
       TRY(E->dmalloc(&sp.xs_cflag, (size_t)sp.xs_nchunks * B));
+      TRY(E->dmalloc(&sp.xs_rflag, (size_t)sp.xs_nchunks * B));
       TRY(E->dmalloc(&sp.xs_epoch, (size_t)B));
       TRY(E->dmalloc(&sp.xs_recs, (size_t)sp.xs_nbatches * 192 * B));
     }
@@ -733,7 +740,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     v.sc.psum += e0; v.sc.any_active += g;
     if (v.xs_recs) {
       v.xs_ctot += (size_t)e0 * v.xs_nchunks;
-      v.xs_cflag += (size_t)e0 * v.xs_nchunks; v.xs_epoch += e0;
+      v.xs_cflag += (size_t)e0 * v.xs_nchunks; v.xs_rflag += (size_t)e0 * v.xs_nchunks; v.xs_epoch += e0;
       v.xs_recs += (size_t)e0 * v.xs_nbatches * 192;
     }
     v.xs_stats += 8 * e0;
@@ -749,7 +756,11 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   E->whole.spB = sp; E->whole.spB.lev[0].x = E->pB;
   E->whole.uAx = E->uAx; E->whole.uAy = E->uAy; E->whole.uBx = E->uBx; E->whole.uBy = E->uBy;
   E->whole.uCx = E->uCx; E->whole.uCy = E->uCy;
+  if (const char* ev = std::getenv("RLFC_PSUM_OVERLAP")) E->psum_overlap = std::atoi(ev) != 0;
   if (cudaStreamCreateWithFlags(&E->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&E->psum_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&E->psum_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&E->psum_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&E->fork_ev, cudaEventDisableTiming) != cudaSuccess)
     return bail(fail(RLFC_ECUDA, "stream/event creation failed"));
 

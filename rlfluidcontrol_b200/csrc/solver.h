@@ -102,6 +102,7 @@ struct SolverParams {
   // Field.sum as segment summaries (exact_sum.cuh); xs_recs == nullptr selects the plain serial chain (k_psum)
   double *xs_ctot;          // [B][xs_nchunks] chunk totals, valid when xs_cflag == xs_epoch + 1
   unsigned *xs_cflag;       // [B][xs_nchunks]
+  unsigned *xs_rflag;       // [B][xs_nchunks] == xs_epoch + 1 once the chunk's batch records are written
   unsigned *xs_epoch;       // [B] passes completed
   unsigned *xs_recs;        // [B][xs_nbatches][192] batch records (32 summaries condensed)
   int xs_nseg, xs_nchunks, xs_nbatches;
@@ -139,6 +140,9 @@ int launch_smooth0(const SolverParams& P, const float* r_in, float* r_out, int w
 // last node of the MG iteration body inside a CUDA-graph WHILE node: cond = any env still active
 int launch_loopcond(const SolverParams& P, unsigned long long cond_handle, cudaStream_t st);
 int launch_psum(const SolverParams& P, cudaStream_t st);
+// same, with the serial pass on `side` (forked from / joined to `st` through the two events) so that it runs WHILE the
+// table kernel produces the records it consumes chunk by chunk; for stream capture (parallel branches of the graph)
+int launch_psum_overlapped(const SolverParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join);
 int launch_project_u(const SolverParams& P, float* ux, float* uy, cudaStream_t st);
 int launch_shift_p(const SolverParams& P, cudaStream_t st);
 int launch_bc(const SolverParams& P, float* ux, float* uy, cudaStream_t st);

@@ -1343,6 +1343,18 @@ int launch_psum(const SolverParams& q, cudaStream_t st) {
   return 2;
 }
 
+int launch_psum_overlapped(const SolverParams& q, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join) {
+  if (!q.xs_recs) return launch_psum(q, st);
+  cudaEventRecord(fork, st);
+  cudaStreamWaitEvent(side, fork, 0);
+  const dim3 grid(q.B, q.xs_nchunks);
+  k_xsum_tables<<<grid, kXsThreads, 0, st>>>(q);
+  k_xsum_chain<<<q.B, 32, 0, side>>>(q);       // waits for each chunk's record flag (bounded), see the kernel
+  cudaEventRecord(join, side);
+  cudaStreamWaitEvent(st, join, 0);
+  return 2;
+}
+
 int launch_project_u(const SolverParams& q, float* ux, float* uy, cudaStream_t st) {
   dim3 blk(32, 8);
   k_project_u<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, ux, uy);
