@@ -76,7 +76,7 @@ struct rlfc_env {
   cudaEvent_t fork_ev = nullptr;
   cudaStream_t psum_stream = nullptr;        // side branch of the step graphs: Field.sum's serial pass (launch_psum_overlapped)
   cudaEvent_t psum_fork = nullptr, psum_join = nullptr;
-  bool psum_overlap = true;                  // RLFC_PSUM_OVERLAP=0: serial pass after the table kernel
+  bool psum_overlap = false;                 // RLFC_PSUM_OVERLAP=1: serial pass as a parallel graph branch (measured slower)
   bool use_graph = true;
   bool eager_groups = false;
   bool fused = true;                         // RLFC_FUSED=0: unfused residual/down0 and project/shift kernels (A/B experiments)
