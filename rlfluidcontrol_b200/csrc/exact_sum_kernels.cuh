@@ -211,6 +211,7 @@ __device__ __forceinline__ void xs_cp4(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 
+template <bool WAIT>              // WAIT: k_xsum_tables may still be running (parallel graph branch): poll the chunk flags
 __global__ void __launch_bounds__(32)
 k_xsum_chain(const __grid_constant__ SolverParams q) {
   __shared__ __align__(16) uint32_t ring[2 * kXsGroup][kXsRecWords];
@@ -295,10 +296,10 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
     if (b % kXsGroup == 0) {                                      // chunk boundary
       const int grp = b / kXsGroup;
       __syncwarp();
-      if (!prefetched) { wait_chunk(grp); fetch(grp); }
+      if (!prefetched) { if (WAIT) wait_chunk(grp); fetch(grp); }
       prefetched = false;
-      if (grp + 1 < ngrp && __shfl_sync(0xffffffffu, (int)ready(grp + 1), 0)) {   // next chunk already there: in flight now
-        __threadfence();
+      if (grp + 1 < ngrp && (!WAIT || __shfl_sync(0xffffffffu, (int)ready(grp + 1), 0))) {   // next chunk there: in flight now
+        if (WAIT) __threadfence();
         fetch(grp + 1);
         prefetched = true;
         asm volatile("cp.async.wait_group 1;" ::: "memory");

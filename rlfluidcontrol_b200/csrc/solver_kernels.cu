@@ -1339,7 +1339,7 @@ int launch_psum(const SolverParams& q, cudaStream_t st) {
   }
   const dim3 grid(q.B, q.xs_nchunks);     // chunk index slow: see the look-back in k_xsum_tables
   k_xsum_tables<<<grid, kXsThreads, 0, st>>>(q);
-  k_xsum_chain<<<q.B, 32, 0, st>>>(q);
+  k_xsum_chain<false><<<q.B, 32, 0, st>>>(q);
   return 2;
 }
 
@@ -1349,7 +1349,7 @@ int launch_psum_overlapped(const SolverParams& q, cudaStream_t st, cudaStream_t 
   cudaStreamWaitEvent(side, fork, 0);
   const dim3 grid(q.B, q.xs_nchunks);
   k_xsum_tables<<<grid, kXsThreads, 0, st>>>(q);
-  k_xsum_chain<<<q.B, 32, 0, side>>>(q);       // waits for each chunk's record flag (bounded), see the kernel
+  k_xsum_chain<true><<<q.B, 32, 0, side>>>(q);       // waits for each chunk's record flag (bounded), see the kernel
   cudaEventRecord(join, side);
   cudaStreamWaitEvent(st, join, 0);
   return 2;
