@@ -685,7 +685,11 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   sp.sc.rr_part = nullptr;
   TRY(E->dmalloc(&sp.sc.psum, B));
   {
-    // Field.sum: segment summaries (exact_sum.cuh) unless RLFC_PSUM=serial asks for the plain dependent-add chain
+    // Field.sum: segment summaries (exact_sum.cuh) or the plain dependent-add chain (k_psum).  The chain costs
+    // 6 cycles per cell of pure latency whatever the batch size and next to no issue slots; the summaries cost
+    // throughput proportional to batch x cells and a short serial pass.  Measured on B200 (default grid): summaries
+    // +2.5 % step throughput at 256 envs, -8 % at 512, so the default switches on the batch's cell count.
+    // RLFC_PSUM=serial | parallel overrides.
     const char* ev = std::getenv("RLFC_PSUM");
     const long long N = (long long)(g.n - 2) * (g.m - 2);
     sp.xs_nseg = (int)((N + 31) / 32);
@@ -693,7 +697,10 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     sp.xs_nbatches = (sp.xs_nseg + 31) / 32;
     sp.xs_ctot = nullptr; sp.xs_recs = nullptr;
     TRY(E->dmalloc(&sp.xs_stats, (size_t)8 * B));
-    if (!(ev && std::strcmp(ev, "serial") == 0)) {
+    bool summaries = N * B <= 24000000ll;
+    if (ev && std::strcmp(ev, "serial") == 0) summaries = false;
+    if (ev && std::strcmp(ev, "parallel") == 0) summaries = true;
+    if (summaries) {
       TRY(E->dmalloc(&sp.xs_ctot, (size_t)sp.xs_nchunks * B));
       TRY(E->dmalloc(&sp.xs_cflag, (size_t)sp.xs_nchunks * B));
       TRY(E->dmalloc(&sp.xs_rflag, (size_t)sp.xs_nchunks * B));
