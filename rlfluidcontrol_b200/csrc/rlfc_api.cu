@@ -58,6 +58,7 @@ struct rlfc_env {
   int *h_done = nullptr, *h_any = nullptr;
   long long launches = 0;
   long long mg_iter_launch_rounds = 0;
+  unsigned long long* chain_tickets = nullptr;   // [views][kMaxLevels] (smooth_chain.cuh)
   // Environment groups: the batch is split into contiguous groups, each advanced by its own stream (and its own
   // CUDA graphs), so the latency-bound per-env kernels of one group overlap the bandwidth-bound kernels of another.
   struct Group {
@@ -526,6 +527,11 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   sp.use_rows = 1;
   if (const char* ev = std::getenv("RLFC_SMOOTHER")) sp.use_rows = std::string(ev) != "strip";
   const bool force_wave = std::getenv("RLFC_SMOOTHER") && std::string(std::getenv("RLFC_SMOOTHER")) == "wave";
+  // RLFC_SMOOTHER=chain: the chained strip smoother (smooth_chain.cuh) on every level but the coarsest (tests); by default it
+  // takes the levels that are too wide for the row pipeline
+  const bool force_chain = std::getenv("RLFC_SMOOTHER") && std::string(std::getenv("RLFC_SMOOTHER")) == "chain";
+  int chain_wpb = 1;
+  if (const char* ev = std::getenv("RLFC_CHAIN_WPB")) chain_wpb = std::min(4, std::max(1, std::atoi(ev)));
   sp.nlevels = (int)g.levels.size();
   sp.resolution = cfg->resolution; sp.substeps = cfg->substeps; sp.mg_max_iters = cfg->mg_max_iters;
   sp.init_time = cfg->init_time; sp.episode_time = cfg->episode_time;
@@ -583,8 +589,36 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
       // levels too wide for the row pipeline (more than 8 columns per lane on level 0, 4 on coarse levels) are smoothed by
       // the wavefront fallback (smooth_wave.cuh); RLFC_SMOOTHER=wave forces it everywhere (tests)
       L.wave = (C > (l == 0 ? 8 : 4)) || force_wave;
+      L.ch = ChainLevel{};
+      if (sp.use_rows && !force_wave && l < sp.nlevels - 1 && (force_chain || L.wave) && sp.chain_levels == l) {
+        // chained strip smoother: static coefficient table in the strip-skewed layout (solver.h ChainLevel)
+        ChainLevel& ch = L.ch;
+        ch.on = 1; ch.NS = (mj + 31) / 32; ch.T = ni + 34;
+        ch.wpb = std::min(chain_wpb, ch.NS); ch.nb = (ch.NS + ch.wpb - 1) / ch.wpb;
+        ch.sk_stride = (size_t)ch.NS * ch.T * 32;
+        std::vector<float4> ct(ch.sk_stride, make_float4(0.f, 0.f, 0.f, 0.f));
+        for (int s = 0; s < ch.NS; s++)
+          for (int t = 0; t < ch.T; t++)
+            for (int ln = 0; ln < 32; ln++) {
+              const int i = t - ln, j = 32 * s + ln + 1;
+              if (j > mj || i < 0 || i > ni) continue;
+              float4 v = make_float4(H.lx[(size_t)(i + 1) * H.m + j], 0.f, 0.f, 0.f);   // row 0 only feeds lxW of row 1
+              if (i >= 1) {
+                const size_t k = (size_t)i * H.m + j;
+                v.y = H.ly[k]; v.z = H.ly[k + 1]; v.w = -H.inv[k];
+                if (H.diag[k] != -(H.lx[k] + H.lx[k + H.m] + H.ly[k] + H.ly[k + 1]))
+                  return bail(fail(RLFC_EGRID, "PoissonMatrix diagonal is not the plain coefficient sum"));
+              }
+              ct[((size_t)s * ch.T + t) * 32 + ln] = v;
+            }
+        TRY(upload_vec(E, ct, &ch.ct));
+        TRY(E->dmalloc(&ch.rsk, ch.sk_stride * B));
+        for (int gsw = 0; gsw < 5; gsw++) TRY(E->dmalloc(&ch.dsk[gsw], ch.sk_stride * B));
+        L.wave = 0;
+        sp.chain_levels = l + 1;
+      }
       L.rt.C = C; L.rt.K = K; L.rt.entries = 0; L.rt.copies = 1; L.rt.T = nullptr;
-      if (!L.wave) {
+      if (!L.wave && !L.ch.on) {
       std::vector<float4> T((size_t)entries * K * 32, make_float4(0.f, 0.f, 0.f, 0.f));
       std::vector<float> f(4 * K);
       for (int e = 0; e < entries; e++)
@@ -709,12 +743,19 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     }
   }
   TRY(E->dmalloc(&sp.sc.any_active, n_groups));
+  if (sp.chain_levels > 0) {
+    sp.rr_chain_n = chain_incr_blocks(g.n - 2, sp.lev[0].ch.NS);
+    TRY(E->dmalloc(&sp.rr_chain, (size_t)sp.rr_chain_n * B));
+    TRY(E->dmalloc(&sp.rr_count, (size_t)B));
+    // ticket counters: one per (view of the batch, level); views = the groups and the whole batch
+    TRY(E->dmalloc(&E->chain_tickets, (size_t)(n_groups + 1) * kMaxLevels));
+  }
   TRY(E->dmalloc(&E->d_actions, 2 * B)); TRY(E->dmalloc(&E->d_obs, 2 * B)); TRY(E->dmalloc(&E->d_reward, B));
   TRY(E->dmalloc(&E->d_done, B));
   TRY(E->dmalloc(&E->pB, S));
   {
     const int C0 = sp.lev[0].rt.C, mj0 = g.m - 2;
-    sp.rsk_stride = sp.lev[0].wave ? 32 : (size_t)round_up((int)rows_skew_floats(C0, g.n - 2, (mj0 + C0 - 1) / C0), 32);
+    sp.rsk_stride = (sp.lev[0].wave || sp.lev[0].ch.on) ? 32 : (size_t)round_up((int)rows_skew_floats(C0, g.n - 2, (mj0 + C0 - 1) / C0), 32);
     TRY(E->dmalloc(&sp.rsk, sp.rsk_stride * B));
   }
 #undef TRY
@@ -740,6 +781,14 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
       v.lev[l].r += o; v.lev[l].x += o; v.lev[l].d += o;
       if (v.lev[l].w) v.lev[l].w += o;
     }
+    for (int l = 0; l < v.chain_levels; l++) {
+      ChainLevel& ch = v.lev[l].ch;
+      ch.rsk += (size_t)e0 * ch.sk_stride;
+      for (int gsw = 0; gsw < 5; gsw++) ch.dsk[gsw] += (size_t)e0 * ch.sk_stride;
+      ch.ticket = E->chain_tickets + (size_t)g * kMaxLevels + l;
+      ch.tag_hi = (unsigned)(g + 1) << 26;
+    }
+    if (v.chain_levels > 0) { v.rr_chain += (size_t)e0 * v.rr_chain_n; v.rr_count += e0; }
     v.band_tmp += (size_t)e0 * (v.nband_x + v.nband_y);
     v.rsk += (size_t)e0 * v.rsk_stride;
     v.sc.xi += 2 * e0; v.sc.t += e0; v.sc.force += 2 * e0; v.sc.probes += (size_t)e0 * RLFC_NUM_PROBES;
@@ -760,7 +809,25 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     if (cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming) != cudaSuccess) return bail(fail(RLFC_ECUDA, "cudaEventCreate failed"));
   }
   E->whole.e0 = 0; E->whole.B = B; E->whole.sp = sp; E->whole.st = E->stream;
-  E->whole.spB = sp; E->whole.spB.lev[0].x = E->pB;
+  for (int l = 0; l < sp.chain_levels; l++) {
+    ChainLevel& ch = E->whole.sp.lev[l].ch;
+    ch.ticket = E->chain_tickets + (size_t)n_groups * kMaxLevels + l;
+    ch.tag_hi = (unsigned)(n_groups + 1) << 26;
+  }
+  if (sp.chain_levels > 0) {
+    // every counter starts at one full launch's worth of tickets, so that launch serials (the tags) start at 1 and
+    // never equal the 0 the arrays are initialised with
+    std::vector<unsigned long long> init((size_t)(n_groups + 1) * kMaxLevels, 0ull);
+    for (int gv = 0; gv <= n_groups; gv++)
+      for (int l = 0; l < sp.chain_levels; l++) {
+        const int Bv = gv < n_groups ? E->groups[gv].B : B;
+        init[(size_t)gv * kMaxLevels + l] = (unsigned long long)Bv * 4ull * (unsigned)sp.lev[l].ch.nb;
+      }
+    if (cudaMemcpyAsync(E->chain_tickets, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, E->stream) != cudaSuccess ||
+        cudaStreamSynchronize(E->stream) != cudaSuccess)
+      return bail(fail(RLFC_ECUDA, "ticket initialisation failed"));
+  }
+  E->whole.spB = E->whole.sp; E->whole.spB.lev[0].x = E->pB;
   E->whole.uAx = E->uAx; E->whole.uAy = E->uAy; E->whole.uBx = E->uBx; E->whole.uBy = E->uBy;
   E->whole.uCx = E->uCx; E->whole.uCy = E->uCy;
   if (const char* ev = std::getenv("RLFC_PSUM_OVERLAP")) E->psum_overlap = std::atoi(ev) != 0;

@@ -1,0 +1,343 @@
+// smooth_chain.cuh -- exact lexicographic Gauss-Seidel smoothing (MG.smooth, MG.pde:79-97) for WIDE levels: a sweep
+// spans many warps, CTAs and SMs (and, with peer pointers, GPUs), chained column block to column block through
+// global memory.  Included by solver_kernels.cu inside namespace rlfc::{anonymous}.
+//
+// The serial reference updates d[i][j] in place with i outer, j inner, so cell (i,j) sees NEW values at (i-1,j),
+// (i,j-1) and OLD values (previous sweep) at (i+1,j), (i,j+1).  Mapping:
+//   * the columns of a level are cut into strips of 32; lane L of strip s owns column j = 32 s + L + 1 and walks
+//     down the rows one per step, lanes skewed by one step: at local step t the strip works on ENTRY t = the cells
+//     (i = t - L, j) -- W comes from the lane's own previous result, S from lane L-1's previous result (shuffle);
+//   * one warp = one (sweep g, strip s); the four sweeps of a smooth(4) are four such warp chains running
+//     concurrently, sweep g consuming what sweep g-1 produced.  Every array the sweeps touch is STRIP-SKEWED
+//     (solver.h ChainLevel): entry t of a strip is one contiguous line, so E = (i+1,j) and N = (i,j+1) of the
+//     previous sweep are lanes L and L+1 of ITS entry t+1, lane 31's N is lane 0 of the next strip's entry t-31 and
+//     lane 0's S is lane 31 of the previous strip's entry t+31 of the SAME sweep;
+//   * there is no barrier and no flag: every element a sweep writes is an 8-byte {value, launch tag} pair (one
+//     store), and a consumer that finds an older tag simply reloads until the tag of THIS launch appears (the LL
+//     protocol of NCCL).  Operands are prefetched kChPF steps ahead with cp.async.cg (L2, no stale L1 lines) into a
+//     per-warp shared-memory ring, so a producer that is far enough ahead is never waited for; strips settle about
+//     31 + kChPF + (L2 round trip) steps behind their left neighbour and sweeps about kChPF + (L2 round trip) steps
+//     behind the previous sweep;
+//   * CTAs take their role (environment, sweep, column block) from a ticket counter, so roles start in dependency
+//     order whatever the block scheduler does: a CTA only ever waits for CTAs that have already started;
+//   * out-of-domain cells have zero coefficients (host table), so they evaluate to +-0 by themselves; ghosts of d
+//     act as 0 during the sweeps (their products with the boundary coefficients are +-0 on every level: level 0
+//     r_ghost = 0, coarse levels boundary coefficients = 0, MG.pde:120).
+// Arithmetic per update keeps the reference order:
+//     d = -(dW*lxW + dE*lxE + dS*lyS + dN*lyN - r) * inv      (the minus sign folded into ninv = -inv: exact)
+#pragma once
+
+constexpr int kChPF = 8;             // steps of prefetch
+constexpr int kChRing = 16;          // ring slots per warp (power of two > kChPF)
+constexpr int kChMaxWpb = 4;         // strips (warps) per CTA at most
+constexpr unsigned kChSpinMax = 1u << 24;   // bounded reload spin: a tag that never comes is a bug, and a trap beats a hung GPU
+
+struct __align__(16) ChainRing {     // one warp's operand ring
+  float4 coef[kChRing][32];          // {lx[i+1][j], ly[i][j], ly[i][j+1], -inv[i][j]}
+  float r[kChRing][32];
+  uint2 e[kChRing][32];              // previous sweep, entry t+1
+  uint2 aux[kChRing][4];             // [0..1] next strip's entry t-31 lanes 0,1 (N of lane 31); [2..3] previous strip's
+                                     // entry t+31 lanes 30,31 of this sweep (S of lane 0)
+};
+
+__device__ __forceinline__ void ch_cp16(unsigned smem, const void* gmem, bool pred) {
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q cp.async.cg.shared.global [%0], [%1], 16; }" ::"r"(smem), "l"(gmem),
+               "r"((unsigned)pred) : "memory");
+}
+__device__ __forceinline__ uint2 ch_ld_volatile(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+
+// element index of cell (i, j) in a strip-skewed array
+__device__ __forceinline__ size_t ch_index(int T, int i, int j) {
+  const int s = (j - 1) >> 5, L = (j - 1) & 31;
+  return ((size_t)s * T + (i + L)) * 32 + L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the four sweeps of one level: grid = B * 4 * nb CTAs of 32*wpb threads
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * kChMaxWpb)
+k_chain_sweeps(const __grid_constant__ SolverParams q, int level) {
+  extern __shared__ __align__(16) unsigned char ch_smem[];
+  __shared__ unsigned long long s_ticket;
+  const DevLevel& Lv = q.lev[level];
+  const ChainLevel& ch = Lv.ch;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long G = (unsigned long long)q.B * 4ull * (unsigned)ch.nb;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(ch.ticket, 1ull);
+  __syncthreads();
+  const unsigned long long ticket = s_ticket;
+  const unsigned tag = ch.tag_hi | (unsigned)((ticket / G) & 0x3ffffffull);      // same for every CTA of this launch
+  const unsigned role = (unsigned)(ticket % G);
+  const int e = (int)(role / (4u * ch.nb)), rem = (int)(role % (4u * ch.nb));
+  const int g = rem / ch.nb + 1, kb = rem % ch.nb;
+  const int s = kb * ch.wpb + warp;
+  if (!q.sc.active[e] || s >= ch.NS || warp >= ch.wpb) return;
+  const int ni = Lv.n - 2, T = ch.T, NS = ch.NS;
+  const int Tend = ni + 32;                                   // entries 0 .. Tend: rows 0 .. ni+1 of every lane
+  ChainRing& ring = *reinterpret_cast<ChainRing*>(ch_smem + (size_t)warp * sizeof(ChainRing));
+  const size_t eo = (size_t)e * ch.sk_stride;
+  const float4* ct = ch.ct + (size_t)s * T * 32;
+  const float* rsk = ch.rsk + eo + (size_t)s * T * 32;
+  const uint2* dprev = ch.dsk[g - 1] + eo;
+  uint2* dcur = ch.dsk[g] + eo;
+  const unsigned tag_prev = (g == 1) ? 0u : tag;              // sweep 0 (= r*inv) was written by the kernel before this one
+
+  // per-lane second copy of a step (16-byte chunks): lanes 0-7 r, 8-23 the previous sweep's entry q+1,
+  // 24 the next strip's entry q-31 (lanes 0,1), 25 the previous strip's entry q+31 of this sweep (lanes 30,31)
+  const char* src2 = nullptr;
+  unsigned dst2 = 0, slot2 = 0;
+  int q2min = 0, q2max = -1;
+  const unsigned ring_base = (unsigned)__cvta_generic_to_shared(&ring);
+  if (lane < 8) {
+    src2 = reinterpret_cast<const char*>(rsk + 4 * lane);
+    dst2 = ring_base + (unsigned)offsetof(ChainRing, r) + 16u * lane; slot2 = 128u; q2min = 0; q2max = Tend;
+  } else if (lane < 24) {
+    src2 = reinterpret_cast<const char*>(dprev + ((size_t)s * T + 1) * 32 + 2 * (lane - 8));
+    dst2 = ring_base + (unsigned)offsetof(ChainRing, e) + 16u * (lane - 8); slot2 = 256u; q2min = 0; q2max = Tend;
+  } else if (lane == 24) {
+    src2 = reinterpret_cast<const char*>(dprev + ((size_t)(s + 1) * T - 31) * 32);
+    dst2 = ring_base + (unsigned)offsetof(ChainRing, aux); slot2 = 32u; q2min = 32; q2max = (s + 1 < NS) ? ni + 31 : -1;
+  } else if (lane == 25) {
+    src2 = reinterpret_cast<const char*>(dcur + ((size_t)(s - 1) * T + 31) * 32 + 30);
+    dst2 = ring_base + (unsigned)offsetof(ChainRing, aux) + 16u; slot2 = 32u; q2min = 1; q2max = (s > 0) ? ni : -1;
+  }
+  const unsigned stride2 = (lane < 8) ? 128u : 256u;          // bytes per entry of the source array
+  const char* src1 = reinterpret_cast<const char*>(ct + lane);
+  const unsigned dst1 = ring_base + (unsigned)offsetof(ChainRing, coef) + 16u * lane;
+  // zero the aux slots (entries that are never copied must read as finite values)
+  for (int k = lane; k < kChRing * 4; k += 32) (&ring.aux[0][0])[k] = make_uint2(0u, 0u);
+  __syncwarp();
+  auto issue = [&](int qq) {
+    if (qq <= Tend) {
+      const unsigned sl = (unsigned)qq & (kChRing - 1);
+      ch_cp16(dst1 + sl * 512u, src1 + (size_t)qq * 512u, true);
+      ch_cp16(dst2 + sl * slot2, src2 + (size_t)qq * stride2, qq >= q2min && qq <= q2max);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int qq = 0; qq < kChPF; qq++) issue(qq);
+
+  float W = 0.f, cxW = 0.f;
+  uint2* out = dcur + (size_t)s * T * 32 + lane;
+  const uint2* e_src = dprev + ((size_t)s * T + 1) * 32 + lane;                 // entry t+1, this lane
+  const uint2* aux_src = (lane == 0) ? dcur + ((size_t)(s - 1) * T + 31) * 32 + 31
+                                     : dprev + ((size_t)(s + 1) * T - 31) * 32;  // lane 31 (others: unused)
+  const bool aux_lane = (lane == 0 && s > 0) || (lane == 31 && s + 1 < NS);
+  const unsigned aux_tag = (lane == 0) ? tag : tag_prev;
+  const int aux_idx = (lane == 0) ? 3 : 0;
+  for (int t = 0; t <= Tend; t++) {
+    issue(t + kChPF);
+    asm volatile("cp.async.wait_group %0;" ::"n"(kChPF) : "memory");
+    __syncwarp();
+    const unsigned sl = (unsigned)t & (kChRing - 1);
+    const float4 c = ring.coef[sl][lane];
+    const float rv = ring.r[sl][lane];
+    uint2 ev = ring.e[sl][lane];
+    uint2 ax = ring.aux[sl][aux_idx];
+    const int row = t - lane;
+    const bool need_aux = aux_lane && row >= 1 && row <= ni;
+    const bool need_e = t < Tend;
+    bool bad = (need_e && ev.y != tag_prev) || (need_aux && ax.y != aux_tag);
+    if (__any_sync(0xffffffffu, bad)) {                       // producer not far enough ahead: reload until the tag shows up
+      unsigned spins = 0;
+      while (true) {
+        if (need_e && ev.y != tag_prev) ev = ch_ld_volatile(e_src + (size_t)t * 32);
+        if (need_aux && ax.y != aux_tag) ax = ch_ld_volatile(aux_src + (size_t)t * 32);
+        bad = (need_e && ev.y != tag_prev) || (need_aux && ax.y != aux_tag);
+        if (!__any_sync(0xffffffffu, bad)) break;
+        if (++spins > kChSpinMax) __trap();
+      }
+    }
+    const float E = __uint_as_float(ev.x);
+    float N = __shfl_down_sync(0xffffffffu, E, 1);
+    float S = __shfl_up_sync(0xffffffffu, W, 1);
+    const float axv = need_aux ? __uint_as_float(ax.x) : 0.f;
+    if (lane == 31) N = axv;
+    if (lane == 0) S = axv;
+    const float res = (W * cxW + E * c.x + S * c.y + N * c.z - rv) * c.w;       // MG.pde:85-86
+    out[(size_t)t * 32] = make_uint2(__float_as_uint(res), tag);
+    W = res;
+    cxW = c.x;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// down pass of a wide coarse level, grid-wide (MG.pde:68-70): smooth(0) + increment + residual restriction
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_chain_down(const __grid_constant__ SolverParams q, int level) {
+  const int e = blockIdx.z;
+  if (!q.sc.active[e]) return;
+  const DevLevel& L = q.lev[level];
+  const DevLevel& C = q.lev[level + 1];
+  const int J = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int I = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (I > C.n - 2 || J > C.m - 2) return;
+  const size_t eo = (size_t)e * L.stride;
+  down_block<false>(L, C, L.r + eo, L.d + eo, L.x + eo, C.r + (size_t)e * C.stride, I, J);
+}
+
+// ------------------------------------------------------------------------------------------------
+// up pass of a chained level, one thread per COARSE cell (MG.pde:75-76,139-152): d = prolongate(coarse.x) incl. its
+// setBC, x += d, r -= A d.  The new residual and sweep 0 (d = r*inv, MG.pde:80) go to the strip-skewed arrays.
+// LEVEL0: x is the pressure, whose ghost cells are live data (x.plusEq(d) runs over all cells); `r` = the smoothed
+// residual the down pass left (level 0: the caller's buffer, coarse levels: L.d).
+// ------------------------------------------------------------------------------------------------
+template <bool LEVEL0>
+__global__ void __launch_bounds__(256)
+k_chain_up(const __grid_constant__ SolverParams q, int level, const float* __restrict__ r_all) {
+  const int e = blockIdx.z;
+  if (!q.sc.active[e]) return;
+  const DevLevel& L0 = q.lev[level];
+  const DevLevel& L1 = q.lev[level + 1];
+  const ChainLevel& ch = L0.ch;
+  const int P = L0.P, n = L0.n, m = L0.m, CPc = L1.P;
+  const int nci = L1.n - 2, ncj = L1.m - 2;
+  const int J = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int I = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (I > nci || J > ncj) return;
+  const float* __restrict__ xc = L1.x + (size_t)e * L1.stride;
+  const size_t eo = (size_t)e * L0.stride;
+  float* __restrict__ x = L0.x + eo;
+  const float* __restrict__ r = (LEVEL0 ? r_all : L0.d) + eo;
+  float* __restrict__ rsk = ch.rsk + (size_t)e * ch.sk_stride;
+  uint2* __restrict__ d0 = ch.dsk[0] + (size_t)e * ch.sk_stride;
+  const float dc = xc[I * CPc + J];
+  const float dWc = (I > 1) ? xc[(I - 1) * CPc + J] : dc, dEc = (I < nci) ? xc[(I + 1) * CPc + J] : dc;
+  const float dSc = (J > 1) ? xc[I * CPc + J - 1] : dc, dNc = (J < ncj) ? xc[I * CPc + J + 1] : dc;
+  const int i0 = 2 * I - 1, j0 = 2 * J - 1;
+  float xo[2][2], ro[2][2];
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++) { xo[a][b] = x[IDX(i0 + a, j0 + b)]; ro[a][b] = r[IDX(i0 + a, j0 + b)]; }
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      const int i = i0 + a, j = j0 + b, k = IDX(i, j);
+      const float dW = a ? dc : dWc, dE = a ? dEc : dc, dS = b ? dc : dSc, dN = b ? dNc : dc;
+      const float Ad = dc * L0.diag[k] + dW * L0.lx[k] + dE * L0.lx[k + P] + dS * L0.ly[k] + dN * L0.ly[k + 1];
+      x[k] = xo[a][b] + dc;
+      const float rn = ro[a][b] - Ad;
+      const size_t o = ch_index(ch.T, i, j);
+      rsk[o] = rn;
+      d0[o] = make_uint2(__float_as_uint(rn * L0.inv[k]), 0u);                  // MG.pde:80
+      if (LEVEL0) {
+        const int di = (i == 1) ? -1 : (i == n - 2 ? 1 : 0), dj = (j == 1) ? -1 : (j == m - 2 ? 1 : 0);
+        if (di) x[IDX(i + di, j)] += dc;
+        if (dj) x[IDX(i, j + dj)] += dc;
+        if (di && dj) x[IDX(i + di, j + dj)] += dc;
+      }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// increment after the four sweeps (MG.pde:90-97), threads mapped to the skewed layout: a warp owns a strip and a
+// run of kChIncEntries entries, lane L walks its column.  Coarse levels: x += d (the residual update is dead: nothing
+// reads r after the last smooth of a level).  LEVEL0: d.setBC (clamped neighbours), x += d on all cells (ghosts
+// included), r = r - A d written to the plain residual array, r.r accumulated in double; the last CTA of an
+// environment adds the per-CTA partial sums in index order and takes the MGsolver loop decision (MG.pde:32-35).
+// ------------------------------------------------------------------------------------------------
+constexpr int kChIncEntries = 32;
+constexpr int kChIncWarps = 4;
+
+template <bool LEVEL0>
+__global__ void __launch_bounds__(32 * kChIncWarps)
+k_chain_incr(const __grid_constant__ SolverParams q, int level, float* __restrict__ r_out_all, int which) {
+  const int e = blockIdx.z;
+  if (!q.sc.active[e]) return;
+  const DevLevel& Lv = q.lev[level];
+  const ChainLevel& ch = Lv.ch;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = Lv.n, m = Lv.m, P = Lv.P, ni = n - 2, mj = m - 2, T = ch.T, NS = ch.NS;
+  const int s = blockIdx.y;
+  const int t0 = (blockIdx.x * kChIncWarps + warp) * kChIncEntries + 1;        // first entry of this warp's run
+  const int j = 32 * s + lane + 1;
+  const size_t eo = (size_t)e * ch.sk_stride;
+  const uint2* __restrict__ d4 = ch.dsk[4] + eo;
+  const uint2* dcol = d4 + (size_t)s * T * 32 + lane;
+  float* __restrict__ x = Lv.x + (size_t)e * Lv.stride;
+  double rr = 0.0;
+  if (t0 <= ni + 31) {
+    const float4* ct = ch.ct + (size_t)s * T * 32 + lane;
+    const float* rsk = ch.rsk + eo + (size_t)s * T * 32 + lane;
+    float* __restrict__ r_out = LEVEL0 ? r_out_all + (size_t)e * Lv.stride : nullptr;
+    float dW = __uint_as_float(dcol[(size_t)(t0 - 1) * 32].x), dC = __uint_as_float(dcol[(size_t)t0 * 32].x);
+    float cxW = LEVEL0 ? ct[(size_t)(t0 - 1) * 32].x : 0.f;
+    const int t1 = min(t0 + kChIncEntries - 1, ni + 31);
+    for (int t = t0; t <= t1; t++) {
+      const int i = t - lane;
+      const bool ok = i >= 1 && i <= ni && j <= mj;
+      const float dE = __uint_as_float(dcol[(size_t)(t + 1) * 32].x);
+      if (LEVEL0) {
+        const float4 c = ct[(size_t)t * 32];
+        // S = (i, j-1): lane L-1 of entry t-1 = what that lane holds as dW; N = (i, j+1): lane L+1 of entry t+1 = its dE
+        float dS = __shfl_up_sync(0xffffffffu, dW, 1), dN = __shfl_down_sync(0xffffffffu, dE, 1);
+        if (lane == 0 && s > 0 && ok) dS = __uint_as_float(d4[((size_t)(s - 1) * T + t + 31) * 32 + 31].x);
+        if (lane == 31 && s + 1 < NS && ok) dN = __uint_as_float(d4[((size_t)(s + 1) * T + t - 31) * 32].x);
+        if (ok) {
+          const float w_ = (i == 1) ? dC : dW, e_ = (i == ni) ? dC : dE;          // d.setBC: ghost = adjacent interior
+          const float s_ = (j == 1) ? dC : dS, n_ = (j == mj) ? dC : dN;
+          const float dg = -(cxW + c.x + c.y + c.z);                              // PoissonMatrix.pde:46-48
+          const float Ad = dC * dg + w_ * cxW + e_ * c.x + s_ * c.y + n_ * c.z;   // PoissonMatrix.pde:56-61
+          const float rN = rsk[(size_t)t * 32] - Ad;
+          const int k = IDX(i, j);
+          r_out[k] = rN;
+          const float prod = rN * rN;                    // float product, double accumulation (Field.pde:304-307)
+          rr += (double)prod;
+          x[k] += dC;
+          const int di = (i == 1) ? -1 : (i == ni ? 1 : 0), dj = (j == 1) ? -1 : (j == mj ? 1 : 0);
+          if (di) x[IDX(i + di, j)] += dC;
+          if (dj) x[IDX(i, j + dj)] += dC;
+          if (di && dj) x[IDX(i + di, j + dj)] += dC;
+        }
+        cxW = c.x;
+      } else if (ok) {
+        x[IDX(i, j)] += dC;                              // x.plusEq(d), MG.pde:95
+      }
+      dW = dC; dC = dE;
+    }
+  }
+  if (LEVEL0) {
+    // r.r: fixed-order reduction (lanes by shuffle tree, warps in order, CTAs in index order)
+    __shared__ double wsum[kChIncWarps];
+    __shared__ bool s_last;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rr += __shfl_down_sync(0xffffffffu, rr, o);
+    if (lane == 0) wsum[warp] = rr;
+    __syncthreads();
+    const int nblk = gridDim.x * gridDim.y, blk = blockIdx.y * gridDim.x + blockIdx.x;
+    if (threadIdx.x == 0) {
+      double sblk = 0;
+      for (int w = 0; w < kChIncWarps; w++) sblk += wsum[w];
+      q.rr_chain[(size_t)e * q.rr_chain_n + blk] = sblk;
+      __threadfence();
+      s_last = atomicAdd(q.rr_count + e, 1u) == (unsigned)nblk - 1u;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const volatile double* part = q.rr_chain + (size_t)e * q.rr_chain_n;
+      double acc = 0;
+      for (int k = threadIdx.x; k < nblk; k += blockDim.x) acc += part[k];   // fixed assignment of partial sums to threads
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+      if (lane == 0) wsum[warp] = acc;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double sum = 0;
+        for (int w = 0; w < kChIncWarps; w++) sum += wsum[w];
+        q.rr_count[e] = 0u;
+        const int it = ++q.sc.iters[2 * e + which];
+        if ((float)sum < q.mg_tol || it >= q.mg_max_iters) q.sc.active[e] = 0;
+        else atomicExch(q.sc.any_active, 1);
+      }
+    }
+  }
+}

@@ -37,6 +37,22 @@ struct RowTab {
 
 #define IDX(i, j) ((i) * P + (j))
 
+// Chained strip smoother (smooth_chain.cuh): per level, the columns are cut into strips of 32 (lane L of strip s owns
+// column j = 32 s + L + 1) and every array the sweeps touch is stored STRIP-SKEWED: element (s, tau, L) at
+// (s*T + tau)*32 + L holds the cell (i = tau - L, j), so that the cells a warp works on in one step form one
+// contiguous 128-byte line.  Entries 0 .. T-1 with T = ni + 34; elements outside the interior are zero.
+struct ChainLevel {
+  int on;                   // 1 = this level is smoothed by the chained strip smoother
+  int NS, T;                // strips, entries per strip
+  int wpb, nb;              // strips (warps) per CTA, CTAs per sweep
+  size_t sk_stride;         // elements per environment of a skewed array = NS*T*32
+  const float4* ct;         // static coefficients {lx[i+1][j], ly[i][j], ly[i][j+1], -inv[i][j]}   [NS][T][32]
+  float* rsk;               // [B] residual entering smooth(4)                                     (4 B / element)
+  uint2* dsk[5];            // [B] iterate after sweep g = 0..4 as {value bits, launch tag}         (8 B / element)
+  unsigned long long* ticket;   // [1] CTA tickets of this level's sweep launches (role order = start order)
+  unsigned tag_hi;          // high bits of the launch tag (unique per ticket counter)
+};
+
 struct DevLevel {
   SkewLevel sk;
   RowTab rt;
@@ -46,6 +62,7 @@ struct DevLevel {
   float *r, *r2, *x, *d;    // per-env batch arrays (level 0: x = p; r2 = ping-pong residual)
   float *w;                 // level 0, wavefront smoother only: scratch for the Gauss-Seidel iterate
   int wave;                 // 1 = this level is smoothed by the wavefront fallback (smooth_wave.cuh)
+  ChainLevel ch;            // chained strip smoother (wide levels; smooth_chain.cuh)
 };
 
 struct BandFace {           // a face where the BDIM blend differs from the identity
@@ -83,6 +100,11 @@ struct SolverParams {
   float mg_tol;
   int   nlevels;
   int   coarse_strips;      // max strip count over levels >= 1 (warps of k_mg_coarse)
+  int   chain_levels;       // levels 0 .. chain_levels-1 run as grid-wide kernels with the chained strip smoother; the
+                            // one-CTA-per-env coarse kernel starts at level max(chain_levels, 1)
+  double *rr_chain;         // [B][rr_chain_n] per-CTA partial sums of r.r of the level-0 chain increment
+  unsigned *rr_count;       // [B] CTAs of the increment kernel that have delivered their partial sum
+  int   rr_chain_n;
   int   fast_bc;            // 1 = two-phase setBC kernels (no band face on the lines setBC reads; grid fits one CTA)
   int   use_rows;           // 1 = row-pipelined smoother (smooth_rows.cuh), 0 = strip smoother (smooth_strip.cuh)
   int   resolution, substeps, mg_max_iters;
@@ -112,6 +134,8 @@ struct SolverParams {
 
 // opt-in shared-memory attributes of the strip kernels; call once per handle before the first launch / capture
 int configure_kernels(const SolverParams& P);
+// CTAs of the level-0 chain increment kernel per environment (= per-env partial sums of r.r it writes)
+int chain_incr_blocks(int ni, int NS);
 
 // ---- launch wrappers (solver_kernels.cu).  All enqueue on `st`; return number of launches. ----
 int launch_advdif(const SolverParams& P, const float* srcx, const float* srcy, const float* u0x, const float* u0y,

@@ -791,7 +791,7 @@ __device__ __forceinline__ void rows_dispatch(const DevLevel& L, float* r, float
 }
 
 __global__ void __launch_bounds__(kRowsThreads, 2)
-k_mg_coarse_rows(const __grid_constant__ SolverParams q) {
+k_mg_coarse_rows(const __grid_constant__ SolverParams q, int first) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int e = blockIdx.x;
   if (!q.sc.active[e]) return;
@@ -806,7 +806,7 @@ k_mg_coarse_rows(const __grid_constant__ SolverParams q) {
 #else
 #define TICK(what, l)
 #endif
-  for (int l = 1; l < last; l++) {
+  for (int l = first; l < last; l++) {
     const DevLevel& L = q.lev[l];
     const DevLevel& C = q.lev[l + 1];
     const int nci = C.n - 2, ncj = C.m - 2;
@@ -825,7 +825,7 @@ k_mg_coarse_rows(const __grid_constant__ SolverParams q) {
     else rows_dispatch<1>(L, L.r + eo, L.x + eo, smem_raw);
     TICK("smooth", last);
   }
-  for (int l = last - 1; l >= 1; l--) {
+  for (int l = last - 1; l >= first; l--) {
     const DevLevel& L = q.lev[l];
     const DevLevel& C = q.lev[l + 1];
     const size_t eo = (size_t)e * L.stride;
@@ -955,6 +955,7 @@ k_psum(const __grid_constant__ SolverParams q) {
 }
 
 #include "exact_sum_kernels.cuh"
+#include "smooth_chain.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // projection tail (VectorField.pde:136-139): p += -sum/N on all cells; dp = grad p with its setBC
@@ -1243,7 +1244,7 @@ static size_t smooth0_smem(const SolverParams& q) {
 // opt-in shared-memory sizes; called once per handle, outside any stream capture
 static size_t coarse_rows_smem(const SolverParams& q) {
   size_t s = 0;
-  for (int l = 1; l < q.nlevels; l++)
+  for (int l = max(1, q.chain_levels); l < q.nlevels; l++)
     if (!q.lev[l].wave) s = max(s, rows_smem_bytes(min(q.lev[l].rt.C, 4), q.lev[l].P, false));
   return s;
 }
@@ -1269,8 +1270,11 @@ int configure_kernels(const SolverParams& q) {
       return -1;
   }
   cudaError_t e3 = cudaFuncSetAttribute(k_mg_coarse_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coarse_rows_smem(q));
+  if (q.chain_levels > 0 &&
+      cudaFuncSetAttribute(k_chain_sweeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kChMaxWpb * sizeof(ChainRing))) != cudaSuccess)
+    return -1;
   cudaError_t e4 = cudaSuccess;
-  if (!q.lev[0].wave) switch (q.lev[0].rt.C) {
+  if (!q.lev[0].wave && !q.lev[0].ch.on) switch (q.lev[0].rt.C) {
     case 1: e4 = set_smooth0_rows_attr<1>(q); break;
     case 2: e4 = set_smooth0_rows_attr<2>(q); break;
     case 3: e4 = set_smooth0_rows_attr<3>(q); break;
@@ -1283,10 +1287,37 @@ int configure_kernels(const SolverParams& q) {
   return (e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess && e4 == cudaSuccess) ? 0 : -1;
 }
 
+// chained strip smoother, one level: the four sweeps, then the increment (smooth_chain.cuh)
+static int launch_chain_smooth(const SolverParams& q, int l, float* r_out, int which, cudaStream_t st) {
+  const ChainLevel& ch = q.lev[l].ch;
+  k_chain_sweeps<<<q.B * 4 * ch.nb, 32 * ch.wpb, ch.wpb * sizeof(ChainRing), st>>>(q, l);
+  const int runs = (q.lev[l].n - 2 + 31 + kChIncEntries - 1) / kChIncEntries;
+  const dim3 grid((runs + kChIncWarps - 1) / kChIncWarps, ch.NS, q.B);
+  if (l == 0) k_chain_incr<true><<<grid, 32 * kChIncWarps, 0, st>>>(q, l, r_out, which);
+  else k_chain_incr<false><<<grid, 32 * kChIncWarps, 0, st>>>(q, l, nullptr, 0);
+  return 2;
+}
+
+int chain_incr_blocks(int ni, int NS) {
+  const int runs = (ni + 31 + kChIncEntries - 1) / kChIncEntries;
+  return ((runs + kChIncWarps - 1) / kChIncWarps) * NS;
+}
+
 int launch_mg_coarse(const SolverParams& q, cudaStream_t st) {
   if (q.use_rows) {
-    k_mg_coarse_rows<<<q.B, kRowsThreads, coarse_rows_smem(q), st>>>(q);
-    return 1;
+    // wide levels run as grid-wide kernels around the one-CTA-per-environment kernel of the small levels
+    int nl = 0;
+    const int first = max(1, q.chain_levels);
+    dim3 blk(32, 8);
+    for (int l = 1; l < first; l++, nl++)
+      k_chain_down<<<grid2d(q.lev[l + 1].m - 2, q.lev[l + 1].n - 2, q.B, blk), blk, 0, st>>>(q, l);
+    k_mg_coarse_rows<<<q.B, kRowsThreads, coarse_rows_smem(q), st>>>(q, first);
+    nl++;
+    for (int l = first - 1; l >= 1; l--) {
+      k_chain_up<false><<<grid2d(q.lev[l + 1].m - 2, q.lev[l + 1].n - 2, q.B, blk), blk, 0, st>>>(q, l, nullptr);
+      nl += 1 + launch_chain_smooth(q, l, nullptr, 0, st);
+    }
+    return nl;
   }
   const size_t smem = strip_smem(q.coarse_strips);
   k_mg_coarse<<<q.B, max(256, 32 * q.coarse_strips), smem, st>>>(q);
@@ -1295,19 +1326,21 @@ int launch_mg_coarse(const SolverParams& q, cudaStream_t st) {
 
 int launch_mg_up0(const SolverParams& q, float* r, cudaStream_t st) {
   dim3 blk(32, 8);
-  if (q.use_rows && !q.lev[0].wave) k_mg_up0_blk<<<grid2d(q.lev[1].m - 2, q.lev[1].n - 2, q.B, blk), blk, 0, st>>>(q, r);
+  if (q.lev[0].ch.on) k_chain_up<true><<<grid2d(q.lev[1].m - 2, q.lev[1].n - 2, q.B, blk), blk, 0, st>>>(q, 0, r);
+  else if (q.use_rows && !q.lev[0].wave) k_mg_up0_blk<<<grid2d(q.lev[1].m - 2, q.lev[1].n - 2, q.B, blk), blk, 0, st>>>(q, r);
   else k_mg_up0<false><<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, r);
   return 1;
 }
 
 int launch_unskew_r(const SolverParams& q, float* r, cudaStream_t st) {
-  if (!q.use_rows || q.lev[0].wave) return 0;
+  if (!q.use_rows || q.lev[0].wave || q.lev[0].ch.on) return 0;   // (the chain increment writes the plain residual itself)
   dim3 blk(32, 8);
   k_unskew_r<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, r);
   return 1;
 }
 
 int launch_smooth0(const SolverParams& q, const float* r_in, float* r_out, int which, cudaStream_t st) {
+  if (q.lev[0].ch.on) return launch_chain_smooth(q, 0, r_out, which, st);
   if (q.use_rows && q.lev[0].wave) {
     k_smooth0_wave<<<q.B, 1024, 0, st>>>(q, r_in, r_out, which);
     return 1;

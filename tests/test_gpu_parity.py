@@ -164,7 +164,8 @@ def test_other_grids(rlfc, oracle, resolution, xl, yl):
             assert_same(a, b, nm)
 
 
-@pytest.mark.parametrize("envvar,value", [("RLFC_SMOOTHER", "strip"), ("RLFC_SMOOTHER", "wave"), ("RLFC_NO_GRAPH", "1"),
+@pytest.mark.parametrize("envvar,value", [("RLFC_SMOOTHER", "strip"), ("RLFC_SMOOTHER", "wave"), ("RLFC_SMOOTHER", "chain"),
+                                          ("RLFC_NO_GRAPH", "1"),
                                           ("RLFC_GROUPS", "3"), ("RLFC_FAST_BC", "0"), ("RLFC_PSUM", "serial")])
 def test_alternative_execution_paths(rlfc, oracle, init_state, monkeypatch, envvar, value):
     """The strip smoother, the wavefront fallback smoother, eager launches, odd env-group splits, the literal setBC kernels and the plain
