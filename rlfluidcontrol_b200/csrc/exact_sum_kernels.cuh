@@ -376,3 +376,170 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
   }
 #undef XS_TICK
 }
+
+// Serial pass for LARGE domains (thousands of batches per environment, e.g. 2048 for a 2048 x 1024 grid): there almost
+// every batch record is ONE table (no binade change inside 1024 additions), and tables compose, so the warp first
+// condenses every block of 32 consecutive batch records -- a segmented scan of table compositions over the lanes, runs
+// broken at the records that are more than one table -- and then crosses a whole run with one checked table
+// application.  Records with float additions or serial segments are walked entry by entry as in k_xsum_chain; a run whose
+// composed table does not provably apply is walked record by record.  Exactness is unchanged: a table is only applied
+// when its validity condition holds for the true accumulator.
+__global__ void __launch_bounds__(32)
+k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
+  extern __shared__ __align__(16) uint32_t xs_dyn[];               // [2][32][kXsRecWords] record blocks | [32][32] float stage
+  uint32_t (*blk)[32][kXsRecWords] = reinterpret_cast<uint32_t (*)[32][kXsRecWords]>(xs_dyn);
+  float (*stage)[32] = reinterpret_cast<float (*)[32]>(xs_dyn + 2 * 32 * kXsRecWords);
+  const int e = blockIdx.x, lane = threadIdx.x;
+  const unsigned len = (unsigned)(q.m - 2), P = (unsigned)q.P;
+  const unsigned N = (unsigned)(q.n - 2) * len;
+  const int nb = q.xs_nbatches;
+  const float* p = q.lev[0].x + (size_t)e * q.stride;
+  const uint32_t* recs = q.xs_recs + (size_t)e * nb * kXsRecWords;
+  int st_rec = 0, st_walk = 0, st_ent = 0, st_redo = 0;
+  long long tk = clock64(), tacc[4] = {0, 0, 0, 0};                // cycles: [0] block set-up + scan, [1] table runs, [2] record walks, [3] batches redone
+#define XSB_TICK(i) do { const long long n_ = clock64(); tacc[i] += n_ - tk; tk = n_; } while (0)
+  uint32_t bits = 0u;                                             // s = +0.f
+  auto element = [&](unsigned g) {
+    const unsigned K = g * xsum::kSeg + lane;
+    return K < N ? p[(size_t)(1u + K / len) * P + 1u + K % len] : -0.f;
+  };
+  // 32 genuine additions of the values in seg[0..31] (shared memory; every lane runs the same chain on broadcast loads)
+  auto add_segment = [&](const float* seg) {
+    st_redo++;
+    float s = xsum::u2f(bits);
+    const float4* v4 = reinterpret_cast<const float4*>(seg);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const float4 v = v4[k];
+      s += v.x; s += v.y; s += v.z; s += v.w;
+    }
+    bits = xsum::f2u(s);
+  };
+  auto redo_batch = [&](int b) {                                  // the whole batch as 1024 genuine additions
+    st_walk++;
+    XSB_TICK(2);
+    __syncwarp();
+    {
+      // element (b*32 + k)*32 + lane for k = 0..31: one division, then 32 elements further per k
+      const unsigned K0 = (unsigned)b * 1024u + lane;
+      unsigned row = K0 / len, col = K0 - row * len, K = K0;
+      const float* src = p + (size_t)(1u + row) * P + 1u + col;
+#pragma unroll 4
+      for (int k = 0; k < 32; k++) {
+        if (K < N) xs_cp4(&stage[k][lane], src);
+        else stage[k][lane] = -0.f;
+        K += 32u; col += 32u; src += 32;
+        while (col >= len) { col -= len; src += P - len; }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");          // (also drains the record block in flight: rare path)
+    __syncwarp();
+    {
+      float s = xsum::u2f(bits);
+      const float4* v4 = reinterpret_cast<const float4*>(&stage[0][0]);
+#pragma unroll 8
+      for (int k = 0; k < 256; k++) {                              // every lane runs the same chain on broadcast loads
+        const float4 v = v4[k];
+        s += v.x; s += v.y; s += v.z; s += v.w;
+      }
+      bits = xsum::f2u(s);
+      st_redo += 32;
+    }
+    __syncwarp();
+    XSB_TICK(3);
+  };
+  auto walk_batch = [&](int b, const uint32_t* rec) {              // one record, entry by entry (as k_xsum_chain)
+    const uint4 hdr = *reinterpret_cast<const uint4*>(rec);
+    if (hdr.x == 0xffffffffu) { st_walk += 1 << 16; redo_batch(b); return; }
+    const uint32_t start = bits;
+    const int st_redo0 = st_redo;
+    bool ok = true;
+    const int count = (int)hdr.x;
+    for (int i = 0; i < count; i++) {
+      const uint4 t0 = *reinterpret_cast<const uint4*>(rec + 8 + kXsEntWords * i);
+      const uint4 t1 = *reinterpret_cast<const uint4*>(rec + 12 + kXsEntWords * i);
+      const uint4 t2 = *reinterpret_cast<const uint4*>(rec + 16 + kXsEntWords * i);
+      bits = xsum::apply_table(bits, t0.x, (int32_t)t0.y, (int32_t)t0.z, (int32_t)t0.w, (int32_t)t1.x, (int32_t)t1.y,
+                               (int32_t)t1.z, ok);
+      bits = xsum::f2u(((xsum::u2f(bits) + xsum::u2f(t1.w)) + xsum::u2f(t2.x)) + xsum::u2f(t2.y));
+      for (int j = 0; j < (int)t2.z; j++) {                        // a run of serial segments
+        __syncwarp();
+        stage[0][lane] = element((unsigned)(b * 32 + (int)t2.w + j));
+        __syncwarp();
+        add_segment(stage[0]);
+      }
+    }
+    if (ok) { st_rec++; st_ent += count; }
+    else { bits = start; st_redo = st_redo0; redo_batch(b); }
+  };
+  // record blocks land in shared memory by cp.async, one block ahead
+  auto fetch = [&](int b0, int buf) {
+    const int n16 = min(32, nb - b0) * (kXsRecWords / 4);
+    if (n16 > 0) {
+      uint32_t* dst = blk[buf][0];
+      const uint32_t* src = recs + (size_t)b0 * kXsRecWords;
+      for (int k = lane; k < n16; k += 32) xs_cp16(dst + 4 * k, src + 4 * k);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const uint32_t ident[7] = {xsum::kAnyKey, 0u, 0u, (uint32_t)INT32_MIN, (uint32_t)INT32_MAX, (uint32_t)INT32_MIN, (uint32_t)INT32_MAX};
+  fetch(0, 0);
+  for (int b0 = 0, buf = 0; b0 < nb; b0 += 32, buf ^= 1) {
+    __syncwarp();
+    fetch(b0 + 32, buf ^ 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncwarp();
+    const int kend = min(32, nb - b0);
+    const uint32_t* mine = blk[buf][lane];
+    const uint32_t cnt = lane < kend ? mine[0] : 0xffffffffu;
+    const bool pure = cnt == 1u;                                  // the whole batch is one table (no float additions, no serial run)
+    uint32_t acc[7];
+#pragma unroll
+    for (int w = 0; w < 7; w++) acc[w] = pure ? mine[8 + w] : ident[w];
+    const uint32_t puremask = __ballot_sync(0xffffffffu, pure);
+    const uint32_t headmask = ~puremask;
+    const uint32_t upto = headmask & ((2u << lane) - 1u);
+    const int dist = upto ? lane - (31 - __clz(upto)) : lane + 1;  // lanes since the last non-table record (itself: 0)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t prev[7];
+#pragma unroll
+      for (int w = 0; w < 7; w++) prev[w] = __shfl_up_sync(0xffffffffu, acc[w], o);
+      if (dist > o && lane >= o) xsum::compose_tables(prev, acc);  // (the partner is inside this lane's run)
+    }
+    int k = 0;
+    XSB_TICK(0);
+    while (k < kend) {
+      if ((puremask >> k) & 1u) {
+        const uint32_t rest = ~(puremask >> k);                    // first non-table record at or after k
+        int run = rest ? __ffs(rest) - 1 : 32 - k;
+        run = min(run, kend - k);
+        uint32_t tbl[7];
+#pragma unroll
+        for (int w = 0; w < 7; w++) tbl[w] = __shfl_sync(0xffffffffu, acc[w], k + run - 1);
+        bool ok = true;
+        const uint32_t nb_bits = xsum::apply_table(bits, tbl[0], (int32_t)tbl[1], (int32_t)tbl[2], (int32_t)tbl[3], (int32_t)tbl[4],
+                                                   (int32_t)tbl[5], (int32_t)tbl[6], ok);
+        if (ok) { bits = nb_bits; st_rec += run; st_ent++; }
+        else for (int j = 0; j < run; j++) walk_batch(b0 + k + j, blk[buf][k + j]);
+        k += run;
+        XSB_TICK(1);
+      } else {
+        walk_batch(b0 + k, blk[buf][k]);
+        k++;
+        XSB_TICK(2);
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (lane == 0) {
+    q.sc.psum[e] = xsum::u2f(bits);
+    q.xs_epoch[e] += 1u;
+    int* st = q.xs_stats + 8 * e;
+    st[0] = st_rec; st[1] = st_walk; st[2] = st_ent; st[3] = st_redo;
+    for (int k = 0; k < 4; k++) st[4 + k] = (int)tacc[k];
+  }
+#undef XSB_TICK
+}
+constexpr size_t kXsBlocksSmem = (size_t)(2 * 32 * kXsRecWords + 32 * 32) * 4;

@@ -222,16 +222,39 @@ int project_eager(rlfc_env* E, Group& G, float* Ux, float* Uy, int which) {
       E->run("k_unskew_r", 2, [&] { return launch_unskew_r(sb, r, st); }, st, gi);
       E->run("k_mg_down0", 4.25, [&] { return launch_mg_down0(sb, r, rs, st); }, st, gi);
     }
+    if (sp.chain_levels > 0 && E->profiling) {   // per-kernel timing of the chained levels
+      const int first = std::max(1, sp.chain_levels);
+      static const char* nm[4][4] = {{"k_chain_down_L1", "k_chain_up_L1", "k_chain_sweeps_L1", "k_chain_incr_L1"},
+                                     {"k_chain_down_L2", "k_chain_up_L2", "k_chain_sweeps_L2", "k_chain_incr_L2"},
+                                     {"k_chain_down_L3", "k_chain_up_L3", "k_chain_sweeps_L3", "k_chain_incr_L3"},
+                                     {"k_chain_down_L4+", "k_chain_up_L4+", "k_chain_sweeps_L4+", "k_chain_incr_L4+"}};
+      for (int l = 1; l < first; l++) E->run(nm[std::min(l, 4) - 1][0], 0, [&] { return launch_chain_down(sb, l, st); }, st, gi);
+      E->run("k_mg_coarse_cta", 0.5, [&] { return launch_coarse_cta(sb, st); }, st, gi);
+      for (int l = first - 1; l >= 1; l--) {
+        E->run(nm[std::min(l, 4) - 1][1], 0, [&] { return launch_chain_up(sb, l, nullptr, st); }, st, gi);
+        E->run(nm[std::min(l, 4) - 1][2], 0, [&] { return launch_chain_sweeps(sb, l, st); }, st, gi);
+        E->run(nm[std::min(l, 4) - 1][3], 0, [&] { return launch_chain_incr(sb, l, nullptr, 0, st); }, st, gi);
+      }
+      E->run("k_chain_up_L0", 4.25, [&] { return launch_chain_up(sb, 0, rs, st); }, st, gi);
+      E->run("k_chain_sweeps_L0", 3, [&] { return launch_chain_sweeps(sb, 0, st); }, st, gi);
+      E->run("k_chain_incr_L0", 4, [&] { return launch_chain_incr(sb, 0, r, which, st); }, st, gi);
+    } else {
     E->run("k_mg_coarse", 0.5, [&] { return launch_mg_coarse(sb, st); }, st, gi);
     E->run("k_mg_up0", 4.25, [&] { return launch_mg_up0(sb, rs, st); }, st, gi);
     E->run("k_smooth0", 4, [&] { return launch_smooth0(sb, rs, r, which, st); }, st, gi);
+    }
     E->mg_iter_launch_rounds++;
     if (E->fixed_iters > 0) continue;
     CU(cudaMemcpyAsync(E->h_any, sp.sc.any_active, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (!*E->h_any) break;
   }
-  E->run("k_psum", 1, [&] { return launch_psum(sb, st); }, st, gi);
+  if (E->profiling && sb.xs_recs) {
+    E->run("k_xsum_tables", 1, [&] { return launch_psum_tables(sb, st); }, st, gi);
+    E->run("k_xsum_pass", 0, [&] { return launch_psum_pass(sb, st); }, st, gi);
+  } else {
+    E->run("k_psum", 1, [&] { return launch_psum(sb, st); }, st, gi);
+  }
   if (E->fused && which == 1 && sp.fast_bc) {
     // corrector: Heun average fused into the projection and the boundary-condition kernels (BDIM.pde:95-96)
     E->run("k_project_shift_heun", 8, [&] { return launch_project_shift_heun(sp, pB, pA, Ux, Uy, G.uBx, G.uBy, G.uAx, G.uAy, st); }, st, gi);
@@ -530,8 +553,10 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   // RLFC_SMOOTHER=chain: the chained strip smoother (smooth_chain.cuh) on every level but the coarsest (tests); by default it
   // takes the levels that are too wide for the row pipeline
   const bool force_chain = std::getenv("RLFC_SMOOTHER") && std::string(std::getenv("RLFC_SMOOTHER")) == "chain";
+  int chain_min_cols = 32;            // RLFC_CHAIN_MIN_COLS: coarse levels at least this wide follow a chained level 0
+  if (const char* ev = std::getenv("RLFC_CHAIN_MIN_COLS")) chain_min_cols = std::max(1, std::atoi(ev));
   int chain_wpb = 1;
-  if (const char* ev = std::getenv("RLFC_CHAIN_WPB")) chain_wpb = std::min(4, std::max(1, std::atoi(ev)));
+  if (const char* ev = std::getenv("RLFC_CHAIN_WPB")) chain_wpb = std::min(3, std::max(1, std::atoi(ev)));
   sp.nlevels = (int)g.levels.size();
   sp.resolution = cfg->resolution; sp.substeps = cfg->substeps; sp.mg_max_iters = cfg->mg_max_iters;
   sp.init_time = cfg->init_time; sp.episode_time = cfg->episode_time;
@@ -590,13 +615,17 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
       // the wavefront fallback (smooth_wave.cuh); RLFC_SMOOTHER=wave forces it everywhere (tests)
       L.wave = (C > (l == 0 ? 8 : 4)) || force_wave;
       L.ch = ChainLevel{};
-      if (sp.use_rows && !force_wave && l < sp.nlevels - 1 && (force_chain || L.wave) && sp.chain_levels == l) {
+      // levels the row pipeline could take, but which are faster chained when one domain has the GPU to itself
+      const bool prefer_chain = sp.chain_levels > 0 && l >= 1 && mj >= chain_min_cols;
+      if (sp.use_rows && !force_wave && l < sp.nlevels - 1 && (force_chain || L.wave || prefer_chain) && sp.chain_levels == l) {
         // chained strip smoother: static coefficient table in the strip-skewed layout (solver.h ChainLevel)
         ChainLevel& ch = L.ch;
         ch.on = 1; ch.NS = (mj + 31) / 32; ch.T = ni + 34;
         ch.wpb = std::min(chain_wpb, ch.NS); ch.nb = (ch.NS + ch.wpb - 1) / ch.wpb;
         ch.sk_stride = (size_t)ch.NS * ch.T * 32;
-        std::vector<float4> ct(ch.sk_stride, make_float4(0.f, 0.f, 0.f, 0.f));
+        // (the sweeps form addresses up to kChPFS entries past a strip's end for copies of zero bytes: pad the arrays)
+        const size_t pad = (size_t)128 * 32;
+        std::vector<float4> ct(ch.sk_stride + pad, make_float4(0.f, 0.f, 0.f, 0.f));
         for (int s = 0; s < ch.NS; s++)
           for (int t = 0; t < ch.T; t++)
             for (int ln = 0; ln < 32; ln++) {
@@ -612,8 +641,8 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
               ct[((size_t)s * ch.T + t) * 32 + ln] = v;
             }
         TRY(upload_vec(E, ct, &ch.ct));
-        TRY(E->dmalloc(&ch.rsk, ch.sk_stride * B));
-        for (int gsw = 0; gsw < 5; gsw++) TRY(E->dmalloc(&ch.dsk[gsw], ch.sk_stride * B));
+        TRY(E->dmalloc(&ch.rsk, ch.sk_stride * B + pad));
+        for (int gsw = 0; gsw < 5; gsw++) TRY(E->dmalloc(&ch.dsk[gsw], ch.sk_stride * B + pad));
         L.wave = 0;
         sp.chain_levels = l + 1;
       }

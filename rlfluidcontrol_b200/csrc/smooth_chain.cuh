@@ -27,9 +27,17 @@
 //     d = -(dW*lxW + dE*lxE + dS*lyS + dN*lyN - r) * inv      (the minus sign folded into ninv = -inv: exact)
 #pragma once
 
-constexpr int kChPF = 8;             // steps of prefetch
-constexpr int kChRing = 16;          // ring slots per warp (power of two > kChPF)
-constexpr int kChMaxWpb = 4;         // strips (warps) per CTA at most
+#ifndef RLFC_CHPF
+#define RLFC_CHPF 12
+#endif
+#ifndef RLFC_CHPFS
+#define RLFC_CHPFS 48
+#endif
+constexpr int kChPF = RLFC_CHPF;     // steps of prefetch of the DYNAMIC operands (previous sweep, neighbour strips: L2 hits)
+constexpr int kChPFS = RLFC_CHPFS;   // steps of prefetch of the STATIC operands (coefficients, r: they stream from HBM --
+                                     // the arrays of one wide level fill the L2 -- and depend on no producer)
+constexpr int kChRing = 64;          // ring slots per warp (power of two > kChPFS)
+constexpr int kChMaxWpb = 3;         // strips (warps) per CTA at most
 constexpr unsigned kChSpinMax = 1u << 24;   // bounded reload spin: a tag that never comes is a bug, and a trap beats a hung GPU
 
 struct __align__(16) ChainRing {     // one warp's operand ring
@@ -38,8 +46,13 @@ struct __align__(16) ChainRing {     // one warp's operand ring
   uint2 e[kChRing][32];              // previous sweep, entry t+1
   uint2 aux[kChRing][4];             // [0..1] next strip's entry t-31 lanes 0,1 (N of lane 31); [2..3] previous strip's
                                      // entry t+31 lanes 30,31 of this sweep (S of lane 0)
+  float4 dummy[32];                  // landing area of the zero-byte copies of lanes without a share
 };
 
+// 16-byte async copy whose source size is 16 or 0 (0 = write zeros, nothing is read): no predicate, no branch
+__device__ __forceinline__ void ch_cp16z(unsigned smem, const void* gmem, unsigned src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem), "l"(gmem), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void ch_cp16(unsigned smem, const void* gmem, bool pred) {
   asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q cp.async.cg.shared.global [%0], [%1], 16; }" ::"r"(smem), "l"(gmem),
                "r"((unsigned)pred) : "memory");
@@ -47,6 +60,21 @@ __device__ __forceinline__ void ch_cp16(unsigned smem, const void* gmem, bool pr
 __device__ __forceinline__ uint2 ch_ld_volatile(const uint2* p) {
   uint2 v;
   asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ch_lds128(unsigned a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 ch_lds64(unsigned a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float ch_lds32(unsigned a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
   return v;
 }
 
@@ -77,8 +105,7 @@ k_chain_sweeps(const __grid_constant__ SolverParams q, int level) {
   const int s = kb * ch.wpb + warp;
   if (!q.sc.active[e] || s >= ch.NS || warp >= ch.wpb) return;
   const int ni = Lv.n - 2, T = ch.T, NS = ch.NS;
-  const int Tend = ni + 32;                                   // entries 0 .. Tend: rows 0 .. ni+1 of every lane
-  ChainRing& ring = *reinterpret_cast<ChainRing*>(ch_smem + (size_t)warp * sizeof(ChainRing));
+  int Tend = ni + 32;                                         // entries 0 .. Tend: rows 0 .. ni+1 of every lane
   const size_t eo = (size_t)e * ch.sk_stride;
   const float4* ct = ch.ct + (size_t)s * T * 32;
   const float* rsk = ch.rsk + eo + (size_t)s * T * 32;
@@ -86,84 +113,191 @@ k_chain_sweeps(const __grid_constant__ SolverParams q, int level) {
   uint2* dcur = ch.dsk[g] + eo;
   const unsigned tag_prev = (g == 1) ? 0u : tag;              // sweep 0 (= r*inv) was written by the kernel before this one
 
-  // per-lane second copy of a step (16-byte chunks): lanes 0-7 r, 8-23 the previous sweep's entry q+1,
-  // 24 the next strip's entry q-31 (lanes 0,1), 25 the previous strip's entry q+31 of this sweep (lanes 30,31)
-  const char* src2 = nullptr;
-  unsigned dst2 = 0, slot2 = 0;
-  int q2min = 0, q2max = -1;
-  const unsigned ring_base = (unsigned)__cvta_generic_to_shared(&ring);
+  // Copies of one step (16-byte chunks): every lane its coefficient vector; then lanes 0-7 r, 8-23 the previous sweep's
+  // entry q+1, 24 the next strip's entry q-31 (lanes 0,1), 25 the previous strip's entry q+31 of this sweep (lanes 30,31).
+  // A copy is issued for steps q2lo <= q <= q2lo + q2span.
+  const unsigned ring_base = (unsigned)__cvta_generic_to_shared(ch_smem + (size_t)warp * sizeof(ChainRing));
+  const char* g2 = reinterpret_cast<const char*>(rsk);
+  unsigned s2 = ring_base + (unsigned)offsetof(ChainRing, dummy) + 16u * lane, sh2 = 0, stride2 = 0, q2span = 0;
+  int q2lo = 1 << 30;
   if (lane < 8) {
-    src2 = reinterpret_cast<const char*>(rsk + 4 * lane);
-    dst2 = ring_base + (unsigned)offsetof(ChainRing, r) + 16u * lane; slot2 = 128u; q2min = 0; q2max = Tend;
+    g2 = reinterpret_cast<const char*>(rsk + 4 * lane);
+    s2 = ring_base + (unsigned)offsetof(ChainRing, r) + 16u * lane; sh2 = 7; stride2 = 128; q2lo = 0; q2span = Tend;
   } else if (lane < 24) {
-    src2 = reinterpret_cast<const char*>(dprev + ((size_t)s * T + 1) * 32 + 2 * (lane - 8));
-    dst2 = ring_base + (unsigned)offsetof(ChainRing, e) + 16u * (lane - 8); slot2 = 256u; q2min = 0; q2max = Tend;
-  } else if (lane == 24) {
-    src2 = reinterpret_cast<const char*>(dprev + ((size_t)(s + 1) * T - 31) * 32);
-    dst2 = ring_base + (unsigned)offsetof(ChainRing, aux); slot2 = 32u; q2min = 32; q2max = (s + 1 < NS) ? ni + 31 : -1;
-  } else if (lane == 25) {
-    src2 = reinterpret_cast<const char*>(dcur + ((size_t)(s - 1) * T + 31) * 32 + 30);
-    dst2 = ring_base + (unsigned)offsetof(ChainRing, aux) + 16u; slot2 = 32u; q2min = 1; q2max = (s > 0) ? ni : -1;
+    g2 = reinterpret_cast<const char*>(dprev + ((size_t)s * T + 1) * 32 + 2 * (lane - 8));
+    s2 = ring_base + (unsigned)offsetof(ChainRing, e) + 16u * (lane - 8); sh2 = 8; stride2 = 256; q2lo = 0; q2span = Tend;
+  } else if (lane == 24 && s + 1 < NS) {
+    g2 = reinterpret_cast<const char*>(dprev + ((size_t)(s + 1) * T + 1) * 32) - 32 * 256;   // entry q-31 at step q
+    s2 = ring_base + (unsigned)offsetof(ChainRing, aux); sh2 = 5; stride2 = 256; q2lo = 32; q2span = ni - 1;
+  } else if (lane == 25 && s > 0) {
+    g2 = reinterpret_cast<const char*>(dcur + ((size_t)(s - 1) * T + 31) * 32 + 30);         // entry q+31 at step q
+    s2 = ring_base + (unsigned)offsetof(ChainRing, aux) + 16u; sh2 = 5; stride2 = 256; q2lo = 1; q2span = ni - 1;
   }
-  const unsigned stride2 = (lane < 8) ? 128u : 256u;          // bytes per entry of the source array
-  const char* src1 = reinterpret_cast<const char*>(ct + lane);
-  const unsigned dst1 = ring_base + (unsigned)offsetof(ChainRing, coef) + 16u * lane;
+  const char* g1 = reinterpret_cast<const char*>(ct + lane);
+  const unsigned s1 = ring_base + (unsigned)offsetof(ChainRing, coef) + 16u * lane;
   // zero the aux slots (entries that are never copied must read as finite values)
-  for (int k = lane; k < kChRing * 4; k += 32) (&ring.aux[0][0])[k] = make_uint2(0u, 0u);
+  {
+    uint2* aux0 = reinterpret_cast<uint2*>(ch_smem + (size_t)warp * sizeof(ChainRing) + offsetof(ChainRing, aux));
+    for (int k = lane; k < kChRing * 4; k += 32) aux0[k] = make_uint2(0u, 0u);
+  }
   __syncwarp();
-  auto issue = [&](int qq) {
-    if (qq <= Tend) {
-      const unsigned sl = (unsigned)qq & (kChRing - 1);
-      ch_cp16(dst1 + sl * 512u, src1 + (size_t)qq * 512u, true);
-      ch_cp16(dst2 + sl * slot2, src2 + (size_t)qq * stride2, qq >= q2min && qq <= q2max);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  for (int qq = 0; qq < kChPF; qq++) issue(qq);
-
   float W = 0.f, cxW = 0.f;
   uint2* out = dcur + (size_t)s * T * 32 + lane;
-  const uint2* e_src = dprev + ((size_t)s * T + 1) * 32 + lane;                 // entry t+1, this lane
-  const uint2* aux_src = (lane == 0) ? dcur + ((size_t)(s - 1) * T + 31) * 32 + 31
-                                     : dprev + ((size_t)(s + 1) * T - 31) * 32;  // lane 31 (others: unused)
+  const uint2* e_src = dprev + ((size_t)s * T + 1) * 32 + lane;                 // entry t+1, this lane (reload path)
   const bool aux_lane = (lane == 0 && s > 0) || (lane == 31 && s + 1 < NS);
+  const uint2* aux_src = e_src;
+  if (aux_lane) aux_src = (lane == 0) ? dcur + ((size_t)(s - 1) * T + 31) * 32 + 31 : dprev + ((size_t)(s + 1) * T + 1) * 32 - 32 * 32;
   const unsigned aux_tag = (lane == 0) ? tag : tag_prev;
-  const int aux_idx = (lane == 0) ? 3 : 0;
-  for (int t = 0; t <= Tend; t++) {
-    issue(t + kChPF);
-    asm volatile("cp.async.wait_group %0;" ::"n"(kChPF) : "memory");
+  const int aux_lo = aux_lane ? (lane == 0 ? 1 : 32) : (1 << 30);               // steps at which the aux operand is a cell
+  const unsigned aux_span = ni - 1;
+  // shared addresses of this lane's operands in slot 0
+  const unsigned a_coef = s1;
+  const unsigned a_r = ring_base + (unsigned)offsetof(ChainRing, r) + 4u * lane;
+  const unsigned a_e = ring_base + (unsigned)offsetof(ChainRing, e) + 8u * lane;
+  const unsigned a_aux = ring_base + (unsigned)offsetof(ChainRing, aux) + (lane == 0 ? 24u : 0u);
+#ifdef RLFC_CHAIN_STATS        // one launch's pipeline shape: start/end time, reload events and spins per (sweep, strip)
+  unsigned long long st_t0, st_t1;
+  unsigned st_miss = 0, st_spins = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(st_t0));
+#endif
+  unsigned l0 = lane == 0, l31 = lane == 31;
+  unsigned a_coef_ = a_coef, a_r_ = a_r, a_e_ = a_e, a_aux_ = a_aux, s1_ = s1, tagp = tag_prev, tagc = tag, taga = aux_tag;
+  int aux_lo_ = aux_lo;
+  unsigned aux_span_ = aux_span;
+  // pin the loop invariants in registers (otherwise they are rematerialised from the kernel parameters / special registers
+  // in every step)
+  asm volatile("" : "+r"(Tend), "+r"(l0), "+r"(l31), "+r"(a_coef_), "+r"(a_r_), "+r"(a_e_), "+r"(a_aux_), "+r"(s1_), "+r"(s2),
+               "+r"(sh2), "+r"(stride2), "+r"(q2lo), "+r"(q2span), "+r"(tagp), "+r"(tagc), "+r"(taga), "+r"(aux_lo_),
+               "+r"(aux_span_));
+  // One cp.async group per step, two copy instructions, no branches: every lane its coefficient vector of step
+  // i + kChPFS, and its share of the other operands -- of step i + kChPFS for the lanes that copy r, of step i + kChPF
+  // for the lanes that copy the previous sweep / the neighbour strips (lanes without a share copy 0 bytes into a dummy).
+  int qq = 0;                                                 // next step whose dynamic operands are fetched
+  unsigned qslot = 0;
+  const unsigned lead2 = (lane < 8) ? (unsigned)(kChPFS - kChPF) : 0u;
+  unsigned mask2 = (q2lo == (1 << 30)) ? 0u : (unsigned)(kChRing - 1);    // lanes without a share always use their one dummy slot
+  asm volatile("" : "+r"(mask2));
+  int q2lo_ = q2lo - (int)lead2;                              // in terms of qq
+  asm volatile("" : "+r"(q2lo_));
+  auto issue = [&]() {
+    const unsigned sslot = (qslot + (kChPFS - kChPF)) & (kChRing - 1);
+    ch_cp16z(s1_ + (sslot << 9), g1, (qq + (kChPFS - kChPF) <= Tend) ? 16u : 0u);
+    ch_cp16z(s2 + (((qslot + lead2) & mask2) << sh2), g2, ((unsigned)(qq - q2lo_) <= q2span) ? 16u : 0u);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    g1 += 512; g2 += stride2;
+    qq++; qslot = (qslot + 1) & (kChRing - 1);
+  };
+  // When a step finds an operand with an older tag, its producer is less than the prefetch distance ahead, and then every
+  // copy in flight is stale as well.  Wait until the operands of the FURTHEST step in flight are visible (a strip's
+  // entries become visible in order; nothing depends on that: every operand's tag is checked when it is used), copy the
+  // dynamic operands of all steps in flight again and wait for them: one round trip instead of one per step.  This is
+  // also how a strip starts: its first step finds nothing and waits here until the producers are far enough ahead.
+  const char* g2base = g2;                                    // (re-issue path, lanes >= 8: source of step q = g2base + q*stride2)
+  auto refill = [&](int t) {
+    const int tt = min(t + kChPF + 1, Tend);                  // steps t .. tt are in flight
+    const int te = min(tt, Tend - 1);                         // last step whose E operand is checked
+    const int ta = min(tt, aux_lo_ + (int)aux_span_);         // last step in flight that needs the aux operand
+    const bool chk_e = te >= t, chk_a = ta >= t && ta >= aux_lo_;
+    unsigned spins = 0;
+    while (true) {
+      bool ok = true;
+      if (chk_e) ok = ch_ld_volatile(e_src + (size_t)te * 32).y == tagp;
+      if (chk_a) ok = ok && ch_ld_volatile(aux_src + (size_t)ta * 32).y == taga;
+      if (__all_sync(0xffffffffu, ok)) break;
+      if (++spins > kChSpinMax) __trap();
+#ifdef RLFC_CHAIN_STATS
+      st_spins++;
+#endif
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");     // (the stale copies must not land after their replacements)
+    if (lane >= 8)
+      for (int qv = t; qv <= tt; qv++)
+        ch_cp16(s2 + (((unsigned)qv & (kChRing - 1)) << sh2), g2base + (size_t)qv * stride2, (unsigned)(qv - q2lo) <= q2span);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    const unsigned sl = (unsigned)t & (kChRing - 1);
-    const float4 c = ring.coef[sl][lane];
-    const float rv = ring.r[sl][lane];
-    uint2 ev = ring.e[sl][lane];
-    uint2 ax = ring.aux[sl][aux_idx];
-    const int row = t - lane;
-    const bool need_aux = aux_lane && row >= 1 && row <= ni;
-    const bool need_e = t < Tend;
-    bool bad = (need_e && ev.y != tag_prev) || (need_aux && ax.y != aux_tag);
-    if (__any_sync(0xffffffffu, bad)) {                       // producer not far enough ahead: reload until the tag shows up
+  };
+  for (int k = 0; k < kChPFS - kChPF; k++) {                  // static operands of steps 0 .. kChPFS - kChPF - 1
+    ch_cp16(s1_ + ((unsigned)k << 9), g1, k <= Tend);
+    if (lane < 8) { ch_cp16(s2 + ((unsigned)k << sh2), g2, k <= Tend); g2 += stride2; }
+    g1 += 512;
+  }
+  for (int k = 0; k <= kChPF; k++) issue();                   // dynamic operands of steps 0 .. kChPF (static: up to kChPFS)
+  asm volatile("cp.async.wait_group %0;" ::"n"(kChPF) : "memory");
+  __syncwarp();
+  // operands of the current step live in registers, loaded one step ahead (the shared-memory latency hides behind the
+  // previous step's arithmetic)
+  float4 c = ch_lds128(a_coef_);
+  float rv = ch_lds32(a_r_);
+  uint2 ev = ch_lds64(a_e_);
+  uint2 ax = ch_lds64(a_aux_);
+  unsigned tslot = 1;
+  // the tag test and the N operand of a step are prepared at the end of the step before it (vote and shuffle latencies
+  // overlap the start of the next step)
+  auto stale = [&](int t, const uint2& ev_, const uint2& ax_, bool& need_aux) {
+    need_aux = (unsigned)(t - aux_lo_) <= aux_span_;
+#ifdef RLFC_CH_NOCHECK
+    return false;
+#else
+    return (t < Tend && ev_.y != tagp) || (need_aux && ax_.y != taga);
+#endif
+  };
+  bool need_aux;
+  bool any_bad = __any_sync(0xffffffffu, stale(0, ev, ax, need_aux));
+  float N = __shfl_down_sync(0xffffffffu, __uint_as_float(ev.x), 1);
+#pragma unroll 2
+  for (int t = 0; t <= Tend; t++) {
+    float S = __shfl_up_sync(0xffffffffu, W, 1);              // the loop-carried chain starts first
+    const float WcxW = W * cxW;
+#ifndef RLFC_CH_NOISSUE
+    issue();                                                  // copies of step t + kChPF + 1
+#endif
+    if (any_bad) {
+#ifdef RLFC_CHAIN_STATS
+      st_miss++;
+#endif
       unsigned spins = 0;
-      while (true) {
-        if (need_e && ev.y != tag_prev) ev = ch_ld_volatile(e_src + (size_t)t * 32);
-        if (need_aux && ax.y != aux_tag) ax = ch_ld_volatile(aux_src + (size_t)t * 32);
-        bad = (need_e && ev.y != tag_prev) || (need_aux && ax.y != aux_tag);
-        if (!__any_sync(0xffffffffu, bad)) break;
-        if (++spins > kChSpinMax) __trap();
-      }
+      do {
+        refill(t);
+        const unsigned sl = (unsigned)t & (kChRing - 1);
+        ev = ch_lds64(a_e_ + (sl << 8));
+        ax = ch_lds64(a_aux_ + (sl << 5));
+        if (++spins > 1024u) __trap();
+      } while (__any_sync(0xffffffffu, stale(t, ev, ax, need_aux)));
+      N = __shfl_down_sync(0xffffffffu, __uint_as_float(ev.x), 1);
     }
     const float E = __uint_as_float(ev.x);
-    float N = __shfl_down_sync(0xffffffffu, E, 1);
-    float S = __shfl_up_sync(0xffffffffu, W, 1);
     const float axv = need_aux ? __uint_as_float(ax.x) : 0.f;
-    if (lane == 31) N = axv;
-    if (lane == 0) S = axv;
-    const float res = (W * cxW + E * c.x + S * c.y + N * c.z - rv) * c.w;       // MG.pde:85-86
-    out[(size_t)t * 32] = make_uint2(__float_as_uint(res), tag);
+    const float4 cc = c;
+    const float rc = rv;
+    // next step's operands (independent of the arithmetic below)
+#ifndef RLFC_CH_NOWAIT
+    asm volatile("cp.async.wait_group %0;" ::"n"(kChPF) : "memory");
+#endif
+    __syncwarp();
+    c = ch_lds128(a_coef_ + (tslot << 9));
+    rv = ch_lds32(a_r_ + (tslot << 7));
+    ev = ch_lds64(a_e_ + (tslot << 8));
+    ax = ch_lds64(a_aux_ + (tslot << 5));
+    tslot = (tslot + 1) & (kChRing - 1);
+    if (l31) N = axv;
+    if (l0) S = axv;
+    const float res = (WcxW + E * cc.x + S * cc.y + N * cc.z - rc) * cc.w;      // MG.pde:85-86
+#ifndef RLFC_CH_NOSTORE
+    *out = make_uint2(__float_as_uint(res), tagc);
+#endif
+    out += 32;
     W = res;
-    cxW = c.x;
+    cxW = cc.x;
+    any_bad = __any_sync(0xffffffffu, stale(t + 1, ev, ax, need_aux));
+    N = __shfl_down_sync(0xffffffffu, __uint_as_float(ev.x), 1);
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
+#ifdef RLFC_CHAIN_STATS
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(st_t1));
+  if (lane == 0 && (ticket / G) == RLFC_CHAIN_STATS)
+    printf("chain L%d g%d s%d start %llu end %llu miss %u spins %u steps %d\n", level, g, s, st_t0, st_t1, st_miss, st_spins, Tend + 1);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

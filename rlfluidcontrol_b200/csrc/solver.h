@@ -157,6 +157,12 @@ int launch_bc_heun(const SolverParams& P, float* ux, float* uy, const float* usx
 // r_in/r_out are the level-0 ping-pong residual buffers
 int launch_mg_down0(const SolverParams& P, const float* r_in, float* r_out, cudaStream_t st);
 int launch_mg_coarse(const SolverParams& P, cudaStream_t st);
+// the pieces launch_mg_coarse / launch_mg_up0 / launch_smooth0 are made of when levels use the chained strip smoother
+int launch_chain_down(const SolverParams& P, int level, cudaStream_t st);
+int launch_coarse_cta(const SolverParams& P, cudaStream_t st);
+int launch_chain_up(const SolverParams& P, int level, const float* r, cudaStream_t st);
+int launch_chain_sweeps(const SolverParams& P, int level, cudaStream_t st);
+int launch_chain_incr(const SolverParams& P, int level, float* r_out, int which, cudaStream_t st);
 int launch_mg_up0(const SolverParams& P, float* r, cudaStream_t st);
 // rows smoother only: plain level-0 residual <- skewed residual (needed before a further MG iteration's down0)
 int launch_unskew_r(const SolverParams& P, float* r, cudaStream_t st);
@@ -164,6 +170,8 @@ int launch_smooth0(const SolverParams& P, const float* r_in, float* r_out, int w
 // last node of the MG iteration body inside a CUDA-graph WHILE node: cond = any env still active
 int launch_loopcond(const SolverParams& P, unsigned long long cond_handle, cudaStream_t st);
 int launch_psum(const SolverParams& P, cudaStream_t st);
+int launch_psum_tables(const SolverParams& P, cudaStream_t st);   // (the two kernels of launch_psum, segment-summary mode)
+int launch_psum_pass(const SolverParams& P, cudaStream_t st);
 // same, with the serial pass on `side` (forked from / joined to `st` through the two events) so that it runs WHILE the
 // table kernel produces the records it consumes chunk by chunk; for stream capture (parallel branches of the graph)
 int launch_psum_overlapped(const SolverParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join);

@@ -222,7 +222,35 @@ __device__ __forceinline__ float ub_y(const SolverParams& q, int k, float dphi1,
   return v + u2 * q.w2_y[k];
 }
 
+// BDIM.updateUP blend of one band face (BDIM.pde:109-122): u = del*R - ub*(del + (-1)) + del1 * normalGrad(R - ub)
+template <bool XCOMP>
+__device__ __forceinline__ float band_face(const SolverParams& q, const float* u, const BandFace& f, float dphi1, float dphi2) {
+  const int P = q.P, k = IDX(f.i, f.j);
+  auto ub = [&](int kk) { return XCOMP ? ub_x(q, kk, dphi1, dphi2) : ub_y(q, kk, dphi1, dphi2); };
+  const float R = u[k], ubc = ub(k);
+  const float v = f.del * R - ubc * (f.del + (-1.f));
+  const float duE = u[k + P] - ub(k + P), duW = u[k - P] - ub(k - P);
+  const float duN = u[k + 1] - ub(k + 1), duS = u[k - 1] - ub(k - 1);
+  const float g = 0.5f * (f.wnx * (duE - duW) + f.wny * (duN - duS));         // VectorField.pde:50-51
+  return v + f.del1 * g;
+}
+
+// the blend for a whole (large) band, grid-wide: values go to band_tmp, k_band_bc<true> writes them back
+__global__ void __launch_bounds__(256)
+k_band_blend(const __grid_constant__ SolverParams q, const float* ux_all, const float* uy_all) {
+  const int e = blockIdx.y, b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= q.nband_x + q.nband_y) return;
+  const float* ux = ux_all + (size_t)e * q.stride;
+  const float* uy = uy_all + (size_t)e * q.stride;
+  float* tmp = q.band_tmp + (size_t)e * (q.nband_x + q.nband_y);
+  const float xi1_m = q.action_scale * q.sc.xi[2 * e], xi2_m = q.action_scale * q.sc.xi[2 * e + 1];   // AFCCylinder.pde:48-49
+  const float dphi1 = (2 * xi1_m * q.dt) / q.dRD, dphi2 = (2 * xi2_m * q.dt) / q.dRD;
+  tmp[b] = (b < q.nband_x) ? band_face<true>(q, ux, q.band_x[b], dphi1, dphi2)
+                           : band_face<false>(q, uy, q.band_y[b - q.nband_x], dphi1, dphi2);
+}
+
 // BDIM.updateUP blend on the body band (everywhere else it is the identity), then u.setBC()
+template <bool PREBLENDED>
 __global__ void __launch_bounds__(1024)
 k_band_bc(const __grid_constant__ SolverParams q, float* ux_all, float* uy_all) {
   extern __shared__ float scol[];
@@ -230,30 +258,14 @@ k_band_bc(const __grid_constant__ SolverParams q, float* ux_all, float* uy_all) 
   float* ux = ux_all + (size_t)e * q.stride;
   float* uy = uy_all + (size_t)e * q.stride;
   float* tmp = q.band_tmp + (size_t)e * (q.nband_x + q.nband_y);
-  // AFCCylinder.pde:48-49
-  const float xi1_m = q.action_scale * q.sc.xi[2 * e], xi2_m = q.action_scale * q.sc.xi[2 * e + 1];
-  const float dphi1 = (2 * xi1_m * q.dt) / q.dRD, dphi2 = (2 * xi2_m * q.dt) / q.dRD;
-  for (int b = threadIdx.x; b < q.nband_x; b += blockDim.x) {
-    const BandFace f = q.band_x[b];
-    const int k = IDX(f.i, f.j);
-    float R = ux[k], ub = ub_x(q, k, dphi1, dphi2);
-    float v = f.del * R - ub * (f.del + (-1.f));
-    float duE = ux[k + P] - ub_x(q, k + P, dphi1, dphi2), duW = ux[k - P] - ub_x(q, k - P, dphi1, dphi2);
-    float duN = ux[k + 1] - ub_x(q, k + 1, dphi1, dphi2), duS = ux[k - 1] - ub_x(q, k - 1, dphi1, dphi2);
-    float g = 0.5f * (f.wnx * (duE - duW) + f.wny * (duN - duS));       // VectorField.pde:50
-    tmp[b] = v + f.del1 * g;
+  if (!PREBLENDED) {
+    // AFCCylinder.pde:48-49
+    const float xi1_m = q.action_scale * q.sc.xi[2 * e], xi2_m = q.action_scale * q.sc.xi[2 * e + 1];
+    const float dphi1 = (2 * xi1_m * q.dt) / q.dRD, dphi2 = (2 * xi2_m * q.dt) / q.dRD;
+    for (int b = threadIdx.x; b < q.nband_x; b += blockDim.x) tmp[b] = band_face<true>(q, ux, q.band_x[b], dphi1, dphi2);
+    for (int b = threadIdx.x; b < q.nband_y; b += blockDim.x) tmp[q.nband_x + b] = band_face<false>(q, uy, q.band_y[b], dphi1, dphi2);
+    __syncthreads();
   }
-  for (int b = threadIdx.x; b < q.nband_y; b += blockDim.x) {
-    const BandFace f = q.band_y[b];
-    const int k = IDX(f.i, f.j);
-    float R = uy[k], ub = ub_y(q, k, dphi1, dphi2);
-    float v = f.del * R - ub * (f.del + (-1.f));
-    float duE = uy[k + P] - ub_y(q, k + P, dphi1, dphi2), duW = uy[k - P] - ub_y(q, k - P, dphi1, dphi2);
-    float duN = uy[k + 1] - ub_y(q, k + 1, dphi1, dphi2), duS = uy[k - 1] - ub_y(q, k - 1, dphi1, dphi2);
-    float g = 0.5f * (f.wnx * (duE - duW) + f.wny * (duN - duS));       // VectorField.pde:51
-    tmp[q.nband_x + b] = v + f.del1 * g;
-  }
-  __syncthreads();
   for (int b = threadIdx.x; b < q.nband_x; b += blockDim.x) ux[IDX(q.band_x[b].i, q.band_x[b].j)] = tmp[b];
   for (int b = threadIdx.x; b < q.nband_y; b += blockDim.x) uy[IDX(q.band_y[b].i, q.band_y[b].j)] = tmp[q.nband_x + b];
   __syncthreads();
@@ -1177,7 +1189,11 @@ static size_t bc2_smem(const SolverParams& q) { return sizeof(float) * (2 * (3 *
 
 int launch_band_bc(const SolverParams& q, float* ux, float* uy, cudaStream_t st) {
   if (q.fast_bc) k_bc2<true, false><<<q.B, 1024, bc2_smem(q), st>>>(q, ux, uy, nullptr, nullptr, nullptr, nullptr);
-  else k_band_bc<<<q.B, 1024, sizeof(float) * q.m, st>>>(q, ux, uy);
+  else if (q.nband_x + q.nband_y > 4096) {             // a large band (single wide domain): blend grid-wide first
+    k_band_blend<<<dim3((q.nband_x + q.nband_y + 255) / 256, q.B), 256, 0, st>>>(q, ux, uy);
+    k_band_bc<true><<<q.B, 1024, sizeof(float) * q.m, st>>>(q, ux, uy);
+    return 2;
+  } else k_band_bc<false><<<q.B, 1024, sizeof(float) * q.m, st>>>(q, ux, uy);
   return 1;
 }
 
@@ -1269,6 +1285,7 @@ int configure_kernels(const SolverParams& q) {
         cudaFuncSetAttribute(k_bc2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc2_smem(q)) != cudaSuccess)
       return -1;
   }
+  if (cudaFuncSetAttribute(k_xsum_chain_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kXsBlocksSmem) != cudaSuccess) return -1;
   cudaError_t e3 = cudaFuncSetAttribute(k_mg_coarse_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coarse_rows_smem(q));
   if (q.chain_levels > 0 &&
       cudaFuncSetAttribute(k_chain_sweeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kChMaxWpb * sizeof(ChainRing))) != cudaSuccess)
@@ -1287,15 +1304,34 @@ int configure_kernels(const SolverParams& q) {
   return (e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess && e4 == cudaSuccess) ? 0 : -1;
 }
 
-// chained strip smoother, one level: the four sweeps, then the increment (smooth_chain.cuh)
-static int launch_chain_smooth(const SolverParams& q, int l, float* r_out, int which, cudaStream_t st) {
+// chained strip smoother (smooth_chain.cuh): the pieces of one level, individually launchable (profiling) ...
+int launch_chain_sweeps(const SolverParams& q, int l, cudaStream_t st) {
   const ChainLevel& ch = q.lev[l].ch;
   k_chain_sweeps<<<q.B * 4 * ch.nb, 32 * ch.wpb, ch.wpb * sizeof(ChainRing), st>>>(q, l);
+  return 1;
+}
+int launch_chain_incr(const SolverParams& q, int l, float* r_out, int which, cudaStream_t st) {
+  const ChainLevel& ch = q.lev[l].ch;
   const int runs = (q.lev[l].n - 2 + 31 + kChIncEntries - 1) / kChIncEntries;
   const dim3 grid((runs + kChIncWarps - 1) / kChIncWarps, ch.NS, q.B);
   if (l == 0) k_chain_incr<true><<<grid, 32 * kChIncWarps, 0, st>>>(q, l, r_out, which);
   else k_chain_incr<false><<<grid, 32 * kChIncWarps, 0, st>>>(q, l, nullptr, 0);
-  return 2;
+  return 1;
+}
+int launch_chain_down(const SolverParams& q, int l, cudaStream_t st) {
+  dim3 blk(32, 8);
+  k_chain_down<<<grid2d(q.lev[l + 1].m - 2, q.lev[l + 1].n - 2, q.B, blk), blk, 0, st>>>(q, l);
+  return 1;
+}
+int launch_chain_up(const SolverParams& q, int l, const float* r, cudaStream_t st) {
+  dim3 blk(32, 8);
+  if (l == 0) k_chain_up<true><<<grid2d(q.lev[1].m - 2, q.lev[1].n - 2, q.B, blk), blk, 0, st>>>(q, 0, r);
+  else k_chain_up<false><<<grid2d(q.lev[l + 1].m - 2, q.lev[l + 1].n - 2, q.B, blk), blk, 0, st>>>(q, l, nullptr);
+  return 1;
+}
+int launch_coarse_cta(const SolverParams& q, cudaStream_t st) {
+  k_mg_coarse_rows<<<q.B, kRowsThreads, coarse_rows_smem(q), st>>>(q, max(1, q.chain_levels));
+  return 1;
 }
 
 int chain_incr_blocks(int ni, int NS) {
@@ -1303,19 +1339,18 @@ int chain_incr_blocks(int ni, int NS) {
   return ((runs + kChIncWarps - 1) / kChIncWarps) * NS;
 }
 
+// ... and as the composites the step graph captures
 int launch_mg_coarse(const SolverParams& q, cudaStream_t st) {
   if (q.use_rows) {
     // wide levels run as grid-wide kernels around the one-CTA-per-environment kernel of the small levels
     int nl = 0;
     const int first = max(1, q.chain_levels);
-    dim3 blk(32, 8);
-    for (int l = 1; l < first; l++, nl++)
-      k_chain_down<<<grid2d(q.lev[l + 1].m - 2, q.lev[l + 1].n - 2, q.B, blk), blk, 0, st>>>(q, l);
-    k_mg_coarse_rows<<<q.B, kRowsThreads, coarse_rows_smem(q), st>>>(q, first);
-    nl++;
+    for (int l = 1; l < first; l++) nl += launch_chain_down(q, l, st);
+    nl += launch_coarse_cta(q, st);
     for (int l = first - 1; l >= 1; l--) {
-      k_chain_up<false><<<grid2d(q.lev[l + 1].m - 2, q.lev[l + 1].n - 2, q.B, blk), blk, 0, st>>>(q, l, nullptr);
-      nl += 1 + launch_chain_smooth(q, l, nullptr, 0, st);
+      nl += launch_chain_up(q, l, nullptr, st);
+      nl += launch_chain_sweeps(q, l, st);
+      nl += launch_chain_incr(q, l, nullptr, 0, st);
     }
     return nl;
   }
@@ -1326,8 +1361,8 @@ int launch_mg_coarse(const SolverParams& q, cudaStream_t st) {
 
 int launch_mg_up0(const SolverParams& q, float* r, cudaStream_t st) {
   dim3 blk(32, 8);
-  if (q.lev[0].ch.on) k_chain_up<true><<<grid2d(q.lev[1].m - 2, q.lev[1].n - 2, q.B, blk), blk, 0, st>>>(q, 0, r);
-  else if (q.use_rows && !q.lev[0].wave) k_mg_up0_blk<<<grid2d(q.lev[1].m - 2, q.lev[1].n - 2, q.B, blk), blk, 0, st>>>(q, r);
+  if (q.lev[0].ch.on) return launch_chain_up(q, 0, r, st);
+  if (q.use_rows && !q.lev[0].wave) k_mg_up0_blk<<<grid2d(q.lev[1].m - 2, q.lev[1].n - 2, q.B, blk), blk, 0, st>>>(q, r);
   else k_mg_up0<false><<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(q, r);
   return 1;
 }
@@ -1340,7 +1375,7 @@ int launch_unskew_r(const SolverParams& q, float* r, cudaStream_t st) {
 }
 
 int launch_smooth0(const SolverParams& q, const float* r_in, float* r_out, int which, cudaStream_t st) {
-  if (q.lev[0].ch.on) return launch_chain_smooth(q, 0, r_out, which, st);
+  if (q.lev[0].ch.on) return launch_chain_sweeps(q, 0, st) + launch_chain_incr(q, 0, r_out, which, st);
   if (q.use_rows && q.lev[0].wave) {
     k_smooth0_wave<<<q.B, 1024, 0, st>>>(q, r_in, r_out, which);
     return 1;
@@ -1365,15 +1400,23 @@ int launch_smooth0(const SolverParams& q, const float* r_in, float* r_out, int w
   return 1;
 }
 
+// Field.sum as segment summaries: the table kernel, then the serial pass (individually launchable for profiling)
+int launch_psum_tables(const SolverParams& q, cudaStream_t st) {
+  const dim3 grid(q.B, q.xs_nchunks);     // chunk index slow: see the look-back in k_xsum_tables
+  k_xsum_tables<<<grid, kXsThreads, 0, st>>>(q);
+  return 1;
+}
+int launch_psum_pass(const SolverParams& q, cudaStream_t st) {
+  if (q.xs_nbatches >= 256) k_xsum_chain_blocks<<<q.B, 32, kXsBlocksSmem, st>>>(q);   // large domains: runs of records condensed first
+  else k_xsum_chain<false><<<q.B, 32, 0, st>>>(q);
+  return 1;
+}
 int launch_psum(const SolverParams& q, cudaStream_t st) {
   if (!q.xs_recs) {                     // RLFC_PSUM=serial: the plain dependent-add chain, one warp per environment
     k_psum<<<q.B, 32, 0, st>>>(q);
     return 1;
   }
-  const dim3 grid(q.B, q.xs_nchunks);     // chunk index slow: see the look-back in k_xsum_tables
-  k_xsum_tables<<<grid, kXsThreads, 0, st>>>(q);
-  k_xsum_chain<false><<<q.B, 32, 0, st>>>(q);
-  return 2;
+  return launch_psum_tables(q, st) + launch_psum_pass(q, st);
 }
 
 int launch_psum_overlapped(const SolverParams& q, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join) {
