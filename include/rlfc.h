@@ -82,16 +82,41 @@ void rlfc_env_destroy(rlfc_env *env);
    reset_accumulators != 0 to also restore them to (16, 0, 0). */
 int  rlfc_env_reset(rlfc_env *env, const int *env_ids, int n, int reset_accumulators);
 
-/* One RL step for every environment: xi = actions[e], xi_m = action_scale*xi, then `substeps`
-   solver steps with the clientCFD.draw() accumulation.  All pointers are HOST memory.
+/* One RL step for every environment, with the cadence of clientCFD.draw() (clientCFD.pde:35-55).  All pointers are
+   HOST memory.
      actions [n_envs][2] in [-1,1]
      obs     [n_envs][2] = (Cl, Cd) exactly as clientCFD.pde:44-47 forms them (incl. the carry-over)
      reward  [n_envs]    = -Cd - pi/8*0.0097*3.66^3*sum|a|^3 (server.py:61-65), may be NULL
-     done    [n_envs]    = t >= episode_time, may be NULL                                        */
+     done    [n_envs]    = t >= episode_time, may be NULL
+   Every environment advances to ITS next observation and then waits (the sketch blocks in callAction until the agent
+   answers, clientCFD.pde:50):
+     * an environment that emitted an observation at the end of the previous call (t > init_time, callLearn back at
+       `substeps`) takes actions[e] as its new xi (xi_m = action_scale*xi) and runs exactly `substeps` solver steps --
+       the reference changes xi only at a callLearn boundary, so each observation covers `substeps` steps under ONE action;
+     * an environment that has not reached its first callLearn boundary yet -- fresh from rlfc_env_reset with
+       t <= init_time, or mid-window after an episode change with the sketch-global accumulators kept -- IGNORES
+       actions[e] (the reference has not asked for an action yet: xi stays what it is, 0 after a reset) and runs,
+       uncontrolled, until t > init_time and then through its first accumulation window (defaults: 133 + 16 solver
+       steps).  The first call after a reset therefore returns the reference's first observation; pass zeros as its
+       action (the reward formula uses what is passed).  While such an environment catches up the others stay put;
+     * an environment whose episode is over (t >= episode_time, clientCFD.pde:36) takes no more solver steps: done[e]
+       stays 1 and obs[e] is the last observation until the caller resets it.
+   With init_time < 0 every environment is at a boundary right after a reset and every call is `substeps` steps. */
 int  rlfc_env_step(rlfc_env *env, const float *actions, float *obs, float *reward, int *done);
 
-/* Same, DEVICE pointers, asynchronous on the handle's stream (no host copies, no sync). */
+/* Same, DEVICE pointers, asynchronous on the handle's stream (no host copies, no sync).  Runs ONE round of `substeps`
+   solver steps with the same per-environment rules; an environment that is still short of its first observation after
+   the round (see above) simply continues in the next call -- rlfc_env_running() tells.  For batches whose environments
+   are all at a callLearn boundary (the steady state) it is identical to rlfc_env_step. */
 int  rlfc_env_step_device(rlfc_env *env, const float *d_actions, float *d_obs, float *d_reward, int *d_done);
+
+/* Number of environments that had NOT emitted their observation when the last RL-step round ended (0 in the steady
+   state).  Synchronises the handle's stream. */
+int  rlfc_env_running(rlfc_env *env, int *n_running);
+
+/* Per-environment health flags, flags[n_envs]: bit 0 = a non-finite force was produced since the last reset (the
+   environment has diverged; SURVEY section 5 failure detection).  Synchronises the handle's stream. */
+int  rlfc_env_get_flags(rlfc_env *env, int *flags);
 
 /* One solver step (AFCCylinder.update2) without the draw() accumulation.  HOST pointers.
      actions [n_envs][2] (NULL = keep current xi); force [n_envs][2] raw (fx, fy) = -pressForce;

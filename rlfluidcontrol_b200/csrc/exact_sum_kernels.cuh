@@ -54,6 +54,7 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
   __shared__ double base_pred;
   __shared__ double wpart[kXsThreads / 32];
   const int e = blockIdx.x, c = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (q.sc.frozen[e]) return;
   const int len = q.m - 2;
   const long long N = (long long)(q.n - 2) * len, base = (long long)c * kXsChunk;
   const float* p = q.lev[0].x + (size_t)e * q.stride;
@@ -217,6 +218,7 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
   __shared__ __align__(16) uint32_t ring[2 * kXsGroup][kXsRecWords];
   __shared__ float stage[32][32];
   const int e = blockIdx.x, lane = threadIdx.x;
+  if (q.sc.frozen[e]) return;
   const unsigned len = (unsigned)(q.m - 2), P = (unsigned)q.P;
   const unsigned N = (unsigned)(q.n - 2) * len;                   // rlfc_env_create rejects grids beyond 2^31 cells
   const int nseg = q.xs_nseg, nb = q.xs_nbatches;
@@ -390,6 +392,7 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
   uint32_t (*blk)[32][kXsRecWords] = reinterpret_cast<uint32_t (*)[32][kXsRecWords]>(xs_dyn);
   float (*stage)[32] = reinterpret_cast<float (*)[32]>(xs_dyn + 2 * 32 * kXsRecWords);
   const int e = blockIdx.x, lane = threadIdx.x;
+  if (q.sc.frozen[e]) return;
   const unsigned len = (unsigned)(q.m - 2), P = (unsigned)q.P;
   const unsigned N = (unsigned)(q.n - 2) * len;
   const int nb = q.xs_nbatches;

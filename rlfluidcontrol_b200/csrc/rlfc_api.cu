@@ -745,6 +745,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   TRY(E->dmalloc(&sp.sc.probes, (size_t)B * RLFC_NUM_PROBES));
   TRY(E->dmalloc(&sp.sc.callLearn, B)); TRY(E->dmalloc(&sp.sc.Cd, B)); TRY(E->dmalloc(&sp.sc.Cl, B));
   TRY(E->dmalloc(&sp.sc.obs, 2 * B)); TRY(E->dmalloc(&sp.sc.active, B)); TRY(E->dmalloc(&sp.sc.iters, 2 * B));
+  TRY(E->dmalloc(&sp.sc.frozen, B)); TRY(E->dmalloc(&sp.sc.non_finite, B)); TRY(E->dmalloc(&sp.sc.n_running, 1));
   sp.sc.rr_part = nullptr;
   TRY(E->dmalloc(&sp.sc.psum, B));
   {
@@ -822,6 +823,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     v.rsk += (size_t)e0 * v.rsk_stride;
     v.sc.xi += 2 * e0; v.sc.t += e0; v.sc.force += 2 * e0; v.sc.probes += (size_t)e0 * RLFC_NUM_PROBES;
     v.sc.callLearn += e0; v.sc.Cd += e0; v.sc.Cl += e0; v.sc.obs += 2 * e0; v.sc.active += e0; v.sc.iters += 2 * e0;
+    v.sc.frozen += e0; v.sc.non_finite += e0;
     v.sc.psum += e0; v.sc.any_active += g;
     if (v.xs_recs) {
       v.xs_ctot += (size_t)e0 * v.xs_nchunks;
@@ -892,6 +894,8 @@ int rlfc_env_reset(rlfc_env* E, const int* env_ids, int n, int reset_accumulator
     CU(cudaMemsetAsync(sp.sc.xi + 2 * e, 0, 2 * sizeof(float), E->stream));
     CU(cudaMemsetAsync(sp.sc.t + e, 0, sizeof(float), E->stream));
     CU(cudaMemsetAsync(sp.sc.force + 2 * e, 0, 2 * sizeof(float), E->stream));
+    CU(cudaMemsetAsync(sp.sc.frozen + e, 0, sizeof(int), E->stream));
+    CU(cudaMemsetAsync(sp.sc.non_finite + e, 0, sizeof(int), E->stream));
     if (reset_accumulators) {
       CU(cudaMemcpyAsync(sp.sc.callLearn + e, &one16, sizeof(int), cudaMemcpyHostToDevice, E->stream));
       CU(cudaMemsetAsync(sp.sc.Cd + e, 0, sizeof(float), E->stream));
@@ -903,30 +907,47 @@ int rlfc_env_reset(rlfc_env* E, const int* env_ids, int n, int reset_accumulator
   return RLFC_OK;
 }
 
-int rlfc_env_step_device(rlfc_env* E, const float* d_actions, float* d_obs, float* d_reward, int* d_done) {
-  if (!E || !d_actions) return fail(RLFC_EINVAL, "null argument");
-  CU(cudaSetDevice(E->device));
+// one round of an RL step: `substeps` solver steps with the draw() accumulation, then the observation read-out
+static int step_round(rlfc_env* E, const float* d_actions, float* d_obs, float* d_reward, int* d_done) {
   SolverParams& sp = E->sp;
-  E->launches += launch_set_actions(sp, d_actions, E->stream);
   int rc = solver_steps(E, sp.substeps, 1);
   if (rc) return rc;
+  CU(cudaMemsetAsync(sp.sc.n_running, 0, sizeof(int), E->stream));
   E->launches += launch_emit_obs(sp, d_actions, d_obs, d_reward, d_done, E->stream);
   CU(cudaGetLastError());
   return RLFC_OK;
 }
 
+int rlfc_env_step_device(rlfc_env* E, const float* d_actions, float* d_obs, float* d_reward, int* d_done) {
+  if (!E || !d_actions) return fail(RLFC_EINVAL, "null argument");
+  CU(cudaSetDevice(E->device));
+  E->launches += launch_set_actions(E->sp, d_actions, 1, E->stream);
+  return step_round(E, d_actions, d_obs, d_reward, d_done);
+}
+
 int rlfc_env_step(rlfc_env* E, const float* actions, float* obs, float* reward, int* done) {
   if (!E || !actions || !obs) return fail(RLFC_EINVAL, "null argument");
   CU(cudaSetDevice(E->device));
-  const int B = E->sp.B;
+  const SolverParams& sp = E->sp;
+  const int B = sp.B;
   std::memcpy(E->h_actions, actions, 2 * B * sizeof(float));
   CU(cudaMemcpyAsync(E->d_actions, E->h_actions, 2 * B * sizeof(float), cudaMemcpyHostToDevice, E->stream));
-  int rc = rlfc_env_step_device(E, E->d_actions, E->d_obs, E->d_reward, E->d_done);
-  if (rc) return rc;
-  CU(cudaMemcpyAsync(E->h_obs, E->d_obs, 2 * B * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
-  if (reward) CU(cudaMemcpyAsync(E->h_reward, E->d_reward, B * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
-  if (done) CU(cudaMemcpyAsync(E->h_done, E->d_done, B * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
-  CU(cudaStreamSynchronize(E->stream));
+  E->launches += launch_set_actions(sp, E->d_actions, 1, E->stream);
+  // Every environment advances to ITS next observation (clientCFD.pde:39-50).  Environments at a callLearn boundary need
+  // exactly `substeps` solver steps -- one round; an environment fresh from a reset first runs uncontrolled until
+  // t > init_time and then through its first accumulation window, over several rounds, while the others stay frozen.
+  const int max_rounds = 3 + (int)((sp.init_time > 0 ? sp.init_time : 0) / sp.dt_over_res) / sp.substeps;
+  for (int round = 0;; round++) {
+    int rc = step_round(E, E->d_actions, E->d_obs, E->d_reward, E->d_done);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(E->h_any, sp.sc.n_running, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+    CU(cudaMemcpyAsync(E->h_obs, E->d_obs, 2 * B * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+    if (reward) CU(cudaMemcpyAsync(E->h_reward, E->d_reward, B * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+    if (done) CU(cudaMemcpyAsync(E->h_done, E->d_done, B * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+    CU(cudaStreamSynchronize(E->stream));
+    if (*E->h_any == 0) break;
+    if (round >= max_rounds) return fail(RLFC_ENOTCONV, "an environment did not reach its next observation");
+  }
   std::memcpy(obs, E->h_obs, 2 * B * sizeof(float));
   if (reward) std::memcpy(reward, E->h_reward, B * sizeof(float));
   if (done) std::memcpy(done, E->h_done, B * sizeof(int));
@@ -941,8 +962,8 @@ int rlfc_env_substep(rlfc_env* E, const float* actions, float* force, float* pro
   if (actions) {
     std::memcpy(E->h_actions, actions, 2 * B * sizeof(float));
     CU(cudaMemcpyAsync(E->d_actions, E->h_actions, 2 * B * sizeof(float), cudaMemcpyHostToDevice, E->stream));
-    E->launches += launch_set_actions(sp, E->d_actions, E->stream);
   }
+  E->launches += launch_set_actions(sp, actions ? E->d_actions : nullptr, 0, E->stream);
   int rc = solver_steps(E, 1, 0);
   if (rc) return rc;
   if (force) CU(cudaMemcpyAsync(E->h_force, sp.sc.force, 2 * B * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
@@ -1028,6 +1049,24 @@ int rlfc_env_get_time(rlfc_env* E, float* t) {
   return RLFC_OK;
 }
 
+int rlfc_env_running(rlfc_env* E, int* n_running) {
+  if (!E || !n_running) return fail(RLFC_EINVAL, "null argument");
+  CU(cudaSetDevice(E->device));
+  CU(cudaMemcpyAsync(E->h_any, E->sp.sc.n_running, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaStreamSynchronize(E->stream));
+  *n_running = *E->h_any;
+  return RLFC_OK;
+}
+
+int rlfc_env_get_flags(rlfc_env* E, int* flags) {
+  if (!E || !flags) return fail(RLFC_EINVAL, "null argument");
+  CU(cudaSetDevice(E->device));
+  CU(cudaMemcpyAsync(E->h_done, E->sp.sc.non_finite, E->sp.B * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaStreamSynchronize(E->stream));
+  for (int e = 0; e < E->sp.B; e++) flags[e] = E->h_done[e] ? 1 : 0;
+  return RLFC_OK;
+}
+
 int rlfc_env_get_mg_iters(rlfc_env* E, int* iters) {
   if (!E || !iters) return fail(RLFC_EINVAL, "null argument");
   CU(cudaSetDevice(E->device));
@@ -1039,6 +1078,7 @@ int rlfc_env_get_mg_iters(rlfc_env* E, int* iters) {
 int rlfc_env_field_sum(rlfc_env* E, float* sums) {
   if (!E || !sums) return fail(RLFC_EINVAL, "null argument");
   CU(cudaSetDevice(E->device));
+  E->launches += launch_set_actions(E->sp, nullptr, 0, E->stream);      // (no environment is frozen for this evaluation)
   E->launches += launch_psum(E->whole.sp, E->stream);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(sums, E->sp.sc.psum, E->sp.B * sizeof(float), cudaMemcpyDeviceToHost, E->stream));

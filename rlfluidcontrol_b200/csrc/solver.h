@@ -82,6 +82,10 @@ struct EnvScalars {
   int   *callLearn; // [B]    draw() accumulators (clientCFD.pde:11-13)
   float *Cd, *Cl;   // [B]
   float *obs;       // [B][2] last produced (Cl, Cd)
+  int   *frozen;    // [B]    env takes no part in the solver steps of this call: it has emitted its observation and waits
+                    //        for the next action (clientCFD.pde:44-54), or its episode is over (clientCFD.pde:36)
+  int   *non_finite;// [B]    sticky: a non-finite force was produced (diverged environment)
+  int   *n_running; // [1]    environments not frozen, counted by k_emit_obs
   int   *active;    // [B]    MG: env still iterating
   int   *iters;     // [B][2] MG iterations of the last predictor/corrector solve
   double *rr_part;  // [B][rr_blocks] partial sums of r.r
@@ -182,7 +186,10 @@ int launch_heun(const SolverParams& P, const float* ucx, const float* ucy, const
                 float* uax, float* uay, cudaStream_t st);
 // force + probes + time advance; accumulate != 0 applies the clientCFD.draw() accumulation
 int launch_force(const SolverParams& P, int accumulate, cudaStream_t st);
-int launch_set_actions(const SolverParams& P, const float* d_actions, cudaStream_t st);
+// mode 0 (single solver steps): xi = actions (NULL keeps xi), every env runs.  mode 1 (RL step): an env takes its
+// action only where the reference would have asked for one (t > init_time and at a callLearn boundary); envs whose
+// episode is over (t >= episode_time) are frozen for the call
+int launch_set_actions(const SolverParams& P, const float* d_actions, int mode, cudaStream_t st);
 int launch_emit_obs(const SolverParams& P, const float* d_actions, float* d_obs, float* d_reward, int* d_done,
                     cudaStream_t st);
 

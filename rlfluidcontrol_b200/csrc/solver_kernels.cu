@@ -89,7 +89,8 @@ template <bool PREDICTOR>
 __global__ void __launch_bounds__(128)
 k_advdif(const float* __restrict__ srcx, const float* __restrict__ srcy, const float* __restrict__ u0x,
          const float* __restrict__ u0y, float* __restrict__ dstx, float* __restrict__ dsty, int n, int m, int P,
-         size_t stride, float dt, float nu) {
+         size_t stride, float dt, float nu, const int* __restrict__ frozen) {
+  if (frozen[blockIdx.z]) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ni = n - 2, mj = m - 2;
   const int jw0 = 1 + blockIdx.x * kAdvCols;                         // first output column of this warp
@@ -239,7 +240,7 @@ __device__ __forceinline__ float band_face(const SolverParams& q, const float* u
 __global__ void __launch_bounds__(256)
 k_band_blend(const __grid_constant__ SolverParams q, const float* ux_all, const float* uy_all) {
   const int e = blockIdx.y, b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= q.nband_x + q.nband_y) return;
+  if (b >= q.nband_x + q.nband_y || q.sc.frozen[e]) return;
   const float* ux = ux_all + (size_t)e * q.stride;
   const float* uy = uy_all + (size_t)e * q.stride;
   float* tmp = q.band_tmp + (size_t)e * (q.nband_x + q.nband_y);
@@ -255,6 +256,7 @@ __global__ void __launch_bounds__(1024)
 k_band_bc(const __grid_constant__ SolverParams q, float* ux_all, float* uy_all) {
   extern __shared__ float scol[];
   const int e = blockIdx.x, P = q.P;
+  if (q.sc.frozen[e]) return;
   float* ux = ux_all + (size_t)e * q.stride;
   float* uy = uy_all + (size_t)e * q.stride;
   float* tmp = q.band_tmp + (size_t)e * (q.nband_x + q.nband_y);
@@ -277,6 +279,7 @@ __global__ void __launch_bounds__(1024)
 k_bc(const __grid_constant__ SolverParams q, float* ux_all, float* uy_all) {
   extern __shared__ float scol[];
   const int e = blockIdx.x;
+  if (q.sc.frozen[e]) return;
   cta_setBC(ux_all + (size_t)e * q.stride, q.n, q.m, q.P, 1, 1.f, true, scol);
   cta_setBC(uy_all + (size_t)e * q.stride, q.n, q.m, q.P, 2, 0.f, false, scol);
 }
@@ -332,6 +335,7 @@ k_bc2(const __grid_constant__ SolverParams q, float* ux_all, float* uy_all, cons
       float* uox_all, float* uoy_all) {
   extern __shared__ float bc_smem[];
   const int e = blockIdx.x, P = q.P, n = q.n, m = q.m, tid = threadIdx.x;
+  if (q.sc.frozen[e]) return;
   float* ux = ux_all + (size_t)e * q.stride;
   float* uy = uy_all + (size_t)e * q.stride;
   BcLines sx, sy;
@@ -429,6 +433,7 @@ k_residual(const __grid_constant__ SolverParams q, const float* __restrict__ ux_
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y * blockDim.y + threadIdx.y;
   const int e = blockIdx.z;
+  if (q.sc.frozen[e]) return;                          // (active[e] is 0 after every completed solve: the MG kernels skip it too)
   if (i == 0 && j == 0) { q.sc.active[e] = 1; q.sc.iters[2 * e + which] = 0; }
   if (i < 1 || j < 1 || i > q.n - 2 || j > q.m - 2) return;
   const size_t eo = (size_t)e * q.stride;
@@ -520,6 +525,7 @@ k_resid_down0(const __grid_constant__ SolverParams q, const float* __restrict__ 
   const DevLevel& C = q.lev[1];
   const int P = L.P, n = L.n, m = L.m;
   const int e = blockIdx.z;
+  if (q.sc.frozen[e]) return;                          // (active[e] is 0 after every completed solve: the MG kernels skip it too)
   const int tid = threadIdx.y * kRdJ + threadIdx.x;
   if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) { q.sc.active[e] = 1; q.sc.iters[2 * e + which] = 0; }
   const size_t eo = (size_t)e * L.stride;
@@ -926,6 +932,7 @@ k_psum(const __grid_constant__ SolverParams q) {
   constexpr int G = 8;                                   // 32-element chunks per group (one row segment each)
   __shared__ __align__(16) float buf[2][G * 32];
   const int e = blockIdx.x, lane = threadIdx.x;
+  if (q.sc.frozen[e]) return;
   const int P = q.P, ni = q.n - 2, len = q.m - 2;
   const int cpr = (len + 31) / 32;                       // chunks per row; row tails are padded with +0.f (s + 0.f == s)
   const float* p = q.lev[0].x + (size_t)e * q.stride;
@@ -981,7 +988,7 @@ k_project_u(const __grid_constant__ SolverParams q, float* __restrict__ ux_all, 
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y * blockDim.y + threadIdx.y;
   const int e = blockIdx.z;
-  if (i < 1 || j < 1 || i > n - 2 || j > m - 2) return;
+  if (i < 1 || j < 1 || i > n - 2 || j > m - 2 || q.sc.frozen[e]) return;
   const size_t eo = (size_t)e * q.stride;
   const float* p = q.lev[0].x + eo;
   const float shift = -1 * q.sc.psum[e] / q.inv_cells;
@@ -1002,7 +1009,7 @@ k_shift_p(const __grid_constant__ SolverParams q) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y * blockDim.y + threadIdx.y;
   const int e = blockIdx.z;
-  if (i >= q.n || j >= q.m) return;
+  if (i >= q.n || j >= q.m || q.sc.frozen[e]) return;
   float* p = q.lev[0].x + (size_t)e * q.stride;
   const float shift = -1 * q.sc.psum[e] / q.inv_cells;
   p[IDX(i, j)] += shift;
@@ -1026,7 +1033,7 @@ k_project_shift(const __grid_constant__ SolverParams q, const float* __restrict_
   const int P = q.P, n = q.n, m = q.m, nv = P >> 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int e = blockIdx.y;
-  if (idx >= n * nv) return;
+  if (idx >= n * nv || q.sc.frozen[e]) return;
   const int i = idx / nv, j4 = (idx - i * nv) << 2;
   const size_t eo = (size_t)e * q.stride;
   const float shift = -1 * q.sc.psum[e] / q.inv_cells;
@@ -1080,10 +1087,10 @@ k_project_shift(const __grid_constant__ SolverParams q, const float* __restrict_
 __global__ void __launch_bounds__(256)
 k_heun(const float* __restrict__ ucx, const float* __restrict__ ucy, const float* __restrict__ ubx,
        const float* __restrict__ uby, float* __restrict__ uax, float* __restrict__ uay, int n, int m, int P,
-       size_t stride) {
+       size_t stride, const int* __restrict__ frozen) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y * blockDim.y + threadIdx.y;
-  if (i >= n || j >= m) return;
+  if (i >= n || j >= m || frozen[blockIdx.z]) return;
   const size_t k = (size_t)blockIdx.z * stride + IDX(i, j);
   uax[k] = (ucx[k] + ubx[k]) * 0.5f;
   uay[k] = (ucy[k] + uby[k]) * 0.5f;
@@ -1100,6 +1107,7 @@ __device__ __forceinline__ float sample_linear(const float* a, int P, int i, int
 __global__ void __launch_bounds__(64)
 k_force(const __grid_constant__ SolverParams q, int accumulate) {
   const int e = blockIdx.x, tid = threadIdx.x, P = q.P;
+  if (q.sc.frozen[e]) return;
   const float* p = q.lev[0].x + (size_t)e * q.stride;
   __shared__ float sx[64], sy[64];
   if (tid < q.nforce) {
@@ -1121,6 +1129,8 @@ k_force(const __grid_constant__ SolverParams q, int accumulate) {
     q.sc.force[2 * e + 1] = fy;
     const float t = q.sc.t[e] + q.dt_over_res;                                    // AFCCylinder.pde:56
     q.sc.t[e] = t;
+    if (!isfinite(fx) || !isfinite(fy)) q.sc.non_finite[e] = 1;                   // diverged environment (sticky flag)
+    if (accumulate && t >= q.episode_time) q.sc.frozen[e] = 1;                    // clientCFD.pde:36: no frame past Time
     if (accumulate && t > q.init_time) {                                          // clientCFD.pde:39-47
       int cl = q.sc.callLearn[e] - 1;
       float Cd = q.sc.Cd[e] + fx, Cl = q.sc.Cl[e] + fy;
@@ -1130,6 +1140,7 @@ k_force(const __grid_constant__ SolverParams q, int accumulate) {
         Cl = Cl / cl * 2 / q.resolution;
         q.sc.obs[2 * e] = Cl;
         q.sc.obs[2 * e + 1] = Cd;
+        q.sc.frozen[e] = 1;            // the sketch now blocks in callAction until the agent answers (clientCFD.pde:50)
       }
       q.sc.callLearn[e] = cl;
       q.sc.Cd[e] = Cd;
@@ -1138,9 +1149,21 @@ k_force(const __grid_constant__ SolverParams q, int accumulate) {
   }
 }
 
-__global__ void k_set_actions(const __grid_constant__ SolverParams q, const float* __restrict__ act) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < 2 * q.B) q.sc.xi[k] = act[k];
+// Start of a call.  mode 0 (single solver steps): xi = act where given, every env runs.  mode 1 (RL step): the reference
+// changes xi only when callAction returns, i.e. right after an observation was emitted (clientCFD.pde:44-54): an env
+// that has not reached its first callLearn boundary yet (t <= initTime after a reset, or mid-window after an episode
+// change with the sketch-global accumulators kept) keeps its xi.  An env past the episode end takes no more steps.
+__global__ void k_set_actions(const __grid_constant__ SolverParams q, const float* __restrict__ act, int mode) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= q.B) return;
+  bool take = act != nullptr, frozen = false;
+  if (mode == 1) {
+    const float t = q.sc.t[e];
+    take = take && t > q.init_time && q.sc.callLearn[e] == q.substeps;
+    frozen = t >= q.episode_time;
+  }
+  if (take) { q.sc.xi[2 * e] = act[2 * e]; q.sc.xi[2 * e + 1] = act[2 * e + 1]; }
+  q.sc.frozen[e] = frozen ? 1 : 0;
 }
 
 // obs/reward/done of one RL step; reward = server/server.py:61-65 evaluated in double
@@ -1156,6 +1179,7 @@ __global__ void k_emit_obs(const __grid_constant__ SolverParams q, const float* 
     reward[e] = (float)(-(double)Cd - pen);
   }
   if (done) done[e] = q.sc.t[e] >= q.episode_time ? 1 : 0;
+  if (!q.sc.frozen[e]) atomicAdd(q.sc.n_running, 1);      // still on its way to the next observation
 }
 
 // end of one MGsolver iteration inside a CUDA-graph WHILE node: continue while any env is still active
@@ -1179,9 +1203,9 @@ int launch_advdif(const SolverParams& q, const float* srcx, const float* srcy, c
   const int ni = q.n - 2, mj = q.m - 2;
   dim3 grid((mj + kAdvCols - 1) / kAdvCols, ((ni + kAdvRows - 1) / kAdvRows + 3) / 4, q.B);
   if (srcx == u0x && srcy == u0y)
-    k_advdif<true><<<grid, 128, 0, st>>>(srcx, srcy, u0x, u0y, dstx, dsty, q.n, q.m, q.P, q.stride, q.dt, q.nu);
+    k_advdif<true><<<grid, 128, 0, st>>>(srcx, srcy, u0x, u0y, dstx, dsty, q.n, q.m, q.P, q.stride, q.dt, q.nu, q.sc.frozen);
   else
-    k_advdif<false><<<grid, 128, 0, st>>>(srcx, srcy, u0x, u0y, dstx, dsty, q.n, q.m, q.P, q.stride, q.dt, q.nu);
+    k_advdif<false><<<grid, 128, 0, st>>>(srcx, srcy, u0x, u0y, dstx, dsty, q.n, q.m, q.P, q.stride, q.dt, q.nu, q.sc.frozen);
   return 1;
 }
 
@@ -1446,7 +1470,7 @@ int launch_shift_p(const SolverParams& q, cudaStream_t st) {
 int launch_heun(const SolverParams& q, const float* ucx, const float* ucy, const float* ubx, const float* uby,
                 float* uax, float* uay, cudaStream_t st) {
   dim3 blk(32, 8);
-  k_heun<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(ucx, ucy, ubx, uby, uax, uay, q.n, q.m, q.P, q.stride);
+  k_heun<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(ucx, ucy, ubx, uby, uax, uay, q.n, q.m, q.P, q.stride, q.sc.frozen);
   return 1;
 }
 
@@ -1455,8 +1479,8 @@ int launch_force(const SolverParams& q, int accumulate, cudaStream_t st) {
   return 1;
 }
 
-int launch_set_actions(const SolverParams& q, const float* d_actions, cudaStream_t st) {
-  k_set_actions<<<(2 * q.B + 127) / 128, 128, 0, st>>>(q, d_actions);
+int launch_set_actions(const SolverParams& q, const float* d_actions, int mode, cudaStream_t st) {
+  k_set_actions<<<(q.B + 127) / 128, 128, 0, st>>>(q, d_actions, mode);
   return 1;
 }
 

@@ -43,7 +43,7 @@ def library_path() -> Path:
 def default_init_state() -> Path:
     """The developed-wake state every reference episode resumes from (saved/init/init.bdim,
     AFCCylinder.pde:35-37), shipped here in binary form."""
-    return _PKG.parent / "tests" / "golden" / "init_state.bdimb"
+    return _PKG / "data" / "init_state.bdimb"
 
 
 def load_library():
@@ -72,6 +72,8 @@ def load_library():
     L.rlfc_env_dims.argtypes = [vp, ip, ip, ip]
     L.rlfc_env_get_time.argtypes = [vp, fp]
     L.rlfc_env_get_mg_iters.argtypes = [vp, ip]
+    L.rlfc_env_running.argtypes = [vp, ip]
+    L.rlfc_env_get_flags.argtypes = [vp, ip]
     L.rlfc_env_field_sum.argtypes = [vp, fp]
     L.rlfc_env_field_sum_stats.argtypes = [vp, ip]
     L.rlfc_env_get_static.argtypes = [vp, C.c_char_p, C.c_int, fp, ip, ip]
@@ -204,6 +206,18 @@ class AFCCylinderBatch:
         t = np.empty(self.n_envs, np.float32)
         self._check(self._L.rlfc_env_get_time(self._h, _fp(t)), "rlfc_env_get_time")
         return t
+
+    def running(self):
+        """Environments that had not emitted their observation when the last RL-step round ended."""
+        n = C.c_int()
+        self._check(self._L.rlfc_env_running(self._h, C.byref(n)), "rlfc_env_running")
+        return n.value
+
+    def flags(self):
+        """Per-environment health flags (bit 0: a non-finite force was produced since the last reset)."""
+        f = np.empty(self.n_envs, np.int32)
+        self._check(self._L.rlfc_env_get_flags(self._h, f.ctypes.data_as(C.POINTER(C.c_int))), "rlfc_env_get_flags")
+        return f
 
     def mg_iters(self):
         it = np.empty((self.n_envs, 2), np.int32)

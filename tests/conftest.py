@@ -25,7 +25,7 @@ def oracle():
 
 @pytest.fixture(scope="session")
 def init_state(oracle):
-    return oracle.read_bdimb(GOLDEN / "init_state.bdimb")
+    return oracle.read_bdimb(ROOT / "rlfluidcontrol_b200" / "data" / "init_state.bdimb")
 
 
 @pytest.fixture(scope="session")

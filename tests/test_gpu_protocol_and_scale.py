@@ -140,3 +140,69 @@ def test_c_client_speaks_reference_protocol(rlfc, oracle, init_state, tmp_path):
     lines = (tmp_path / "saved" / "1.txt").read_text().splitlines()
     assert lines[0].startswith("%% Force and pressure") and len(lines) == 4 + steps
     assert len(lines[4].split()) == 5 + 32
+
+
+def test_env_step_default_init_time_matches_reference_cadence(rlfc, oracle, init_state):
+    """rlfc_env_step with the DEFAULT init_time = 1 (clientCFD.pde:5): the first call after a reset runs uncontrolled
+    until the reference's first observation (133 steps with t <= 1, then one 16-step window; the action passed is
+    ignored, as the sketch has not asked for one), every later call is 16 solver steps under one action.  Compared with
+    the oracle's draw() loop (ora_driver_step) driven the way clientCFD.pde:35-55 drives it."""
+    ref = oracle.OracleEnv(literal=False)
+    ref.set_state(init_state["ux"], init_state["uy"], init_state["p"])
+
+    def ref_until_obs(limit=400):
+        for k in range(1, limit + 1):
+            o = ref.driver_step(1.0)
+            if o is not None:
+                return o, k
+        raise AssertionError("no observation")
+
+    with rlfc.AFCCylinderBatch(2) as env:                 # default config: init_time = 1
+        obs, _, done = env.step(np.array([[0.7, -0.7], [0.0, 0.0]], np.float32))   # env 0's action must be ignored
+        o, k = ref_until_obs()
+        assert k == 149                                   # 133 steps with t <= 1, then callLearn 16 -> 0
+        assert obs[0, 0] == o[0] and obs[0, 1] == o[1] and obs[1, 0] == o[0] and obs[1, 1] == o[1]
+        assert env.running() == 0 and done.tolist() == [0, 0]
+        for step in range(3):
+            a = config1_actions(step)
+            obs, _, _ = env.step(np.stack([a, a]))
+            ref.set_xi(a[0], a[1])                        # callAction's answer, applied from the next frame on
+            o, k = ref_until_obs()
+            assert k == 16
+            assert obs[0, 0] == o[0] and obs[0, 1] == o[1], (step, obs[0], o)
+        # env 1 is reset alone: it catches up over several rounds (uncontrolled) while env 0 stays put
+        ux0 = env.get_fields(0)[0].copy()
+        t0 = env.t.copy()
+        env.reset([1], reset_accumulators=True)
+        obs, _, _ = env.step(np.zeros((2, 2), np.float32))
+        t1 = env.t
+        # env 0 advanced exactly 16 solver steps, env 1 149 from t = 0
+        assert abs(t1[0] - (t0[0] + 16 * 0.0075)) < 1e-4 and abs(t1[1] - 149 * 0.0075) < 1e-4
+        ref2 = oracle.OracleEnv(literal=False)
+        ref2.set_state(init_state["ux"], init_state["uy"], init_state["p"])
+        for k in range(149):
+            o2 = ref2.driver_step(1.0)
+        assert obs[1, 0] == o2[0] and obs[1, 1] == o2[1]
+        assert np.array_equal(env.get_fields(1)[0], ref2.get_state()[0])
+        assert not np.array_equal(env.get_fields(0)[0], ux0)
+
+
+def test_episode_end_freezes_and_flags(rlfc):
+    """An environment past episode_time takes no more steps (clientCFD.pde:36); a diverged one raises its flag."""
+    with rlfc.AFCCylinderBatch(2, init_time=-1.0, episode_time=0.2) as env:   # 0.2 / 0.0075 = 26.7 solver steps
+        z = np.zeros((2, 2), np.float32)
+        _, _, d = env.step(z)
+        assert d.tolist() == [0, 0]
+        _, _, d = env.step(z)                              # t reaches 0.2025 at step 27: frozen there, mid-window
+        assert d.tolist() == [1, 1]
+        t = env.t.copy()
+        assert abs(t[0] - 27 * 0.0075) < 1e-5
+        o1, _, d = env.step(z)
+        assert np.array_equal(env.t, t) and d.tolist() == [1, 1]
+        assert env.flags().tolist() == [0, 0]
+        env.reset([0])
+        ux, uy, p = env.get_fields(0)
+        p[10, 10] = np.nan
+        env.set_fields(0, p=p)
+        env.step(z)
+        assert env.flags().tolist() == [1, 0]
