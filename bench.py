@@ -1,21 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- env-steps/s of batched AFCCylinder environments (BASELINE.json metric).
+"""bench.py -- throughput of the B200 Lilypad environment step (BASELINE.json metric and configs).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs-per-gpu B] [--impl b200|reference]
+  python bench.py [--config 2|3|4|5] [--gpus N] [--steps K] [--warmup W] [--envs-per-gpu B] [--envs-total T]
+                  [--impl b200|reference]
 
-A "step" is one RL step of every environment in the batch: 16 solver steps (AFCCylinder.update2) with
-the clientCFD.draw() force accumulation -> (Cl, Cd).  Workload (BASELINE configs[1]): default
-AFCCylinder grid (384x192 cells), 256 environments per GPU, all resumed from init.bdim, synthetic
-per-env action sequences.  N > 1 (torchrun, one rank per GPU): environments are independent, so each
-rank owns its own 256 envs (weak scaling) and there is no data-path collective.
+  --config 2 (default)  BASELINE configs[1]: default AFCCylinder grid (384x192), 256 envs PER GPU from init.bdim, synthetic
+                        per-env actions; a step = one RL step of every env = 16 solver steps + the draw() accumulation.
+                        N > 1 (torchrun): every rank owns its own 256 envs (scaling "weak"), one observation all-gather
+                        per env-step, no data-path collective.  metric env-steps/s.
+  --config 4            BASELINE configs[3]: --envs-total (4096) envs split contiguously over the N ranks (scaling
+                        "strong"), otherwise as config 2.
+  --config 3            BASELINE configs[2]: ONE 2048x1024 domain (resolution 128, t_step = 0.18/128, uniform start, SURVEY
+                        8d), a step = one solver step (AFCCylinder.update2); metric solver-steps/s; roofline against the
+                        240 B/cell model.  N > 1 runs N independent replicas (the path does not shard on one domain
+                        without the slab decomposition of config 5).
+  --config 5            BASELINE configs[4] (8192x4096 over 8 GPUs): not built; prints {"unavailable": ...}.
 
-`value`  : device-resident throughput (actions already in HBM, rlfc_env_step_device, CUDA events).
-`e2e`    : the same metric through the host-pointer C-ABI call rlfc_env_step (pinned host buffers,
-           H2D actions + D2H obs/reward/done inside the timed region).
-`roofline`: dominant kernel's algorithmic bytes / its CUDA-event duration vs measured HBM peak.
+`value`  : device-resident throughput (inputs already in HBM, *_device entry points, CUDA events on the handle's stream).
+`e2e`    : the same metric through the host-pointer C-ABI call (pinned host buffers, H2D actions + D2H results inside the
+           timed region).
+`roofline`: dominant kernel's algorithmic bytes / its CUDA-event duration vs the measured HBM peak; `kernels` has every
+           kernel (k_advdif also against the fp32 instruction-issue roofline: it is issue-bound under --fmad=false).
 `cpu_baseline`: the oracle (literal C port of the reference step) on all host cores, bounded sample.
-`--impl reference`: the CPU arm alone (reference Java cannot run here: no JVM; the literal C port of
-           oracle/ stands in, one single-threaded process per host core).
+`--impl reference`: the CPU arm alone (the reference Java cannot run here: no JVM; the literal C port of oracle/ stands
+           in, one single-threaded process per host core); its `config` says exactly what a "step" of that arm is.
 """
 from __future__ import annotations
 
@@ -39,26 +47,46 @@ METRIC = "env-steps/sec (batched BDIM cylinders)"
 UNIT = "env-steps/s"
 
 
-def workload_config(envs_per_gpu, n_gpus):
+METRIC3 = "solver-steps/sec (single 2048x1024 BDIM domain)"
+UNIT3 = "solver-steps/s"
+
+
+def workload_config(envs_per_gpu, n_gpus, config=2, n_total=None):
+    n_total = n_total if n_total is not None else envs_per_gpu * n_gpus
+    split = (f"{envs_per_gpu} batched envs per GPU" if config == 2 else
+             f"{n_total} batched envs split contiguously over {n_gpus} GPU(s) ({envs_per_gpu} on rank 0)")
     return {
-        "workload": "AFCCylinder default grid 384x192 (386x194 arrays), Re=500, "
-                    f"{envs_per_gpu} batched envs per GPU from init.bdim, 16 solver steps per env-step, "
+        "workload": f"BASELINE config {config}: AFCCylinder default grid 384x192 (386x194 arrays), Re=500, "
+                    f"{split}, from init.bdim, 16 solver steps per env-step, "
                     "synthetic per-env actions a=clip(0.8 sin(2 pi k/25 + 2 pi e/256)+0.1 N(0,1)) (env 0: config-1 sequence)",
-        "envs_per_gpu": envs_per_gpu, "n_envs_total": envs_per_gpu * n_gpus, "substeps": 16,
+        "baseline_config": config, "envs_per_gpu": envs_per_gpu, "n_envs_total": n_total, "substeps": 16,
         "mode": "exact (bit-identical to the oracle)", "l2": "per-GPU state >> 126 MB L2 (inputs larger than L2)",
         "parallelism": f"env-sharded x{n_gpus}, no data-path collective (observations all-gathered once per env-step)",
     }
 
 
-def make_actions(n_steps, B, rank):
-    """BASELINE config 2 synthetic actions."""
+def workload_config3(n_gpus):
+    return {
+        "workload": "BASELINE config 3: single 2048x1024 cylinder-wake domain (resolution 128, 16x8 lengths, Re=500, "
+                    "t_step=0.18/128 so dt=0.18 grid units), uniform start u=(1,0) p=0, actions 0 then (0.5,-0.5); "
+                    "one step = one solver step (AFCCylinder.update2: 2 advection-diffusion passes + 2 MG pressure solves)",
+        "baseline_config": 3, "grid": "2048x1024", "n_envs_total": n_gpus, "substeps": 1,
+        "mode": "exact (bit-identical to the oracle)",
+        "l2": "L2 flushed between timed steps: no (working set ~0.5 GB per step >> 126 MB L2: inputs larger than L2)",
+        "parallelism": "one domain on one GPU" if n_gpus == 1 else f"{n_gpus} independent replicas (one domain per GPU; a single domain "
+                       "only shards with the slab decomposition of config 5, which is not built)",
+    }
+
+
+def make_actions(n_steps, B, rank, e0=None):
+    """BASELINE config 2 synthetic actions for the envs [e0, e0 + B) of the global batch."""
     rng = np.random.default_rng(1234 + rank)
     k = np.arange(n_steps)[:, None]
-    e = (np.arange(B) + rank * B)[None, :]
+    e = (np.arange(B) + (rank * B if e0 is None else e0))[None, :]
     a1 = 0.8 * np.sin(2 * np.pi * k / 25 + 2 * np.pi * e / 256) + 0.1 * rng.standard_normal((n_steps, B))
     a2 = -0.8 * np.sin(2 * np.pi * k / 25 + 2 * np.pi * e / 256 + 1.0) + 0.1 * rng.standard_normal((n_steps, B))
     a = np.clip(np.stack([a1, a2], axis=-1), -1, 1).astype(np.float32)
-    if rank == 0:
+    if (rank == 0 if e0 is None else e0 == 0):
         kk = np.arange(n_steps)
         a[:, 0, 0] = (0.8 * np.sin(2 * np.pi * kk / 25.0)).astype(np.float32)
         a[:, 0, 1] = (-0.8 * np.sin(2 * np.pi * kk / 25.0 + 1.0)).astype(np.float32)
@@ -68,15 +96,19 @@ def make_actions(n_steps, B, rank):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle on all host cores (persistent single-threaded worker per core)
 # ------------------------------------------------------------------------------------------------
-def _cpu_worker(conn, core, state_path):
+def _cpu_worker(conn, core, state_path, wide):
     try:
         os.sched_setaffinity(0, {core})
     except Exception:
         pass
     from oracle import oracle_py as O
-    st = O.read_bdimb(state_path)
-    env = O.OracleEnv(literal=True)          # reference behaviour: coefficients rebuilt every step
-    env.set_state(st["ux"], st["uy"], st["p"])
+    if wide:                                 # BASELINE config 3: one 2048x1024 domain per process, uniform start
+        env = O.OracleEnv(literal=True, resolution=128, xLengths=16, yLengths=8, tStep=float(np.float32(0.18) / np.float32(128)))
+        env.set_xi(0.5, -0.5)
+    else:
+        st = O.read_bdimb(state_path)
+        env = O.OracleEnv(literal=True)      # reference behaviour: coefficients rebuilt every step
+        env.set_state(st["ux"], st["uy"], st["p"])
     k = 0
     conn.send("ready")
     while True:
@@ -84,14 +116,17 @@ def _cpu_worker(conn, core, state_path):
         if msg is None:
             break
         for _ in range(msg):
-            a = (0.8 * np.sin(2 * np.pi * k / 25.0), -0.8 * np.sin(2 * np.pi * k / 25.0 + 1.0))
-            env.env_step(a)
+            if wide:
+                env.update2()                # a "step" of config 3 is one solver step
+            else:
+                a = (0.8 * np.sin(2 * np.pi * k / 25.0), -0.8 * np.sin(2 * np.pi * k / 25.0 + 1.0))
+                env.env_step(a)
             k += 1
         conn.send(k)
 
 
 class CpuArm:
-    def __init__(self, cores=None):
+    def __init__(self, cores=None, wide=False):
         from oracle import oracle_py as O
         O.build()
         import rlfluidcontrol_b200 as R
@@ -101,7 +136,7 @@ class CpuArm:
         core_ids = sorted(os.sched_getaffinity(0))[: self.cores]
         for c in core_ids:
             parent, child = ctx.Pipe()
-            p = ctx.Process(target=_cpu_worker, args=(child, c, str(R.default_init_state())), daemon=True)
+            p = ctx.Process(target=_cpu_worker, args=(child, c, str(R.default_init_state()), wide), daemon=True)
             p.start()
             self.workers.append((p, parent))
         for _, conn in self.workers:
@@ -140,27 +175,61 @@ def cpu_baseline(sample_env_steps=4, reps=2):
     }
 
 
+def cpu_baseline_wide(sample_steps=2):
+    """Config 3 on the host: every core advances its OWN 2048x1024 domain (the reference is single-threaded per domain), so
+    the aggregate is cores x the single-domain rate; both are reported."""
+    arm = CpuArm(wide=True)
+    arm.step(1)   # warm-up (first step builds the geometry)
+    sec = arm.step(sample_steps)
+    arm.close()
+    return {
+        "value": arm.cores * sample_steps / sec, "unit": UNIT3, "cores": arm.cores, "kind": "port",
+        "single_domain_value": sample_steps / sec,
+        "sample": f"{arm.cores} single-threaded oracle processes (one per host core), each advancing its own 2048x1024 domain "
+                  f"(uniform start, actions (0.5,-0.5), coefficients rebuilt every step as the reference does) by {sample_steps} solver "
+                  "steps; value = aggregate over the cores, single_domain_value = one domain on one core (what one Lilypad "
+                  "instance achieves: it has no intra-domain parallelism)",
+    }
+
+
 def run_reference(args):
+    """The CPU arm.  What one "step" of THIS arm is, is stated in its config (it is a bounded sample of the workload, sized
+    for the host, not the GPU arm's batch)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    arm = CpuArm()
-    per_step = args.ref_env_steps
+    wide = args.config == 3
+    if args.config == 5:
+        print(json.dumps({"impl": "reference", "unavailable": "config 5 (8192x4096 over 8 GPUs) is not built; the CPU port would need ~20 s per solver step"}))
+        return
+    arm = CpuArm(wide=wide)
+    per_step = 1 if wide else args.ref_env_steps
     for _ in range(args.warmup):
         arm.step(per_step)
     secs = [arm.step(per_step) for _ in range(args.steps)]
     arm.close()
     total = sum(secs)
     value = arm.cores * per_step * args.steps / total
-    cfg = workload_config(args.envs_per_gpu, args.gpus)
+    unit = UNIT3 if wide else UNIT
+    if wide:
+        cfg = workload_config3(args.gpus)
+        what = (f"one step of this arm = {arm.cores} single-threaded processes (one per host core), each advancing its own 2048x1024 "
+                "domain by 1 solver step")
+    else:
+        cfg = workload_config(args.envs_per_gpu, args.gpus, args.config, args.envs_total if args.config == 4 else None)
+        what = (f"one step of this arm = {arm.cores} single-threaded processes (one per host core) x {per_step} env-steps each = "
+                f"{arm.cores * per_step} env-steps of the default-grid AFCCylinder from init.bdim (config-1 actions) -- a bounded sample "
+                "of the workload, NOT the GPU arm's batch; compare `value` (env-steps/s), not ms_per_step")
+    cfg["reference_arm"] = {"what_ran": what, "cores": arm.cores, "units_per_step": arm.cores * per_step,
+                            "implementation": "literal C port of the reference step (oracle/lilypad_oracle.c, gcc -O2 -ffp-contract=off, "
+                                              "coefficients rebuilt every step as the reference does); the Java itself cannot run: no JVM in the image"}
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC3 if wide else METRIC, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.config == 4 else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port",
-                         "sample": f"each step = {arm.cores} single-threaded processes (one per host core) x {per_step} env-steps of "
-                                   "the literal C port of the reference step (no JVM in the image, so the Java itself cannot run)"},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": arm.cores, "kind": "port", "sample": what},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -217,20 +286,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def ncu_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` summary (profiles/r01_ncu_summary.json,
-    same workload: 256 envs, default grid), or None."""
-    p = ROOT / "profiles" / "r01_ncu_summary.json"
-    if not p.exists():
-        return None
-    try:
-        tab = json.loads(p.read_text())
-    except Exception:
-        return None
+def ncu_summary(config=2):
+    """The committed `ncu --set full` summary of the same workload (newest round available), or {}."""
+    names = ["r02_ncu_summary_cfg3.json"] if config == 3 else ["r02_ncu_summary.json", "r01_ncu_summary.json"]
+    for nm in names:
+        p = ROOT / "profiles" / nm
+        if p.exists():
+            try:
+                return json.loads(p.read_text())
+            except Exception:
+                pass
+    return {}
+
+
+def ncu_lookup(tab, kernel, key):
     for name, rec in tab.items():
-        base = name.split("<")[0].replace("_rows", "").replace("_blk", "")
-        if base == kernel or name.split("<")[0] == kernel:
-            return float(rec["dram_traffic_B_per_launch"])
+        base = name.split("<")[0]
+        if base == kernel or base.replace("_rows", "").replace("_blk", "") == kernel:
+            if key in rec:
+                return float(rec[key])
     return None
 
 
@@ -244,8 +318,32 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def kernel_table(prof, steps, peak, clk_mhz, ncu):
+    """Per-kernel view of the live CUDA-event pass: algorithmic GB/s vs the HBM peak, and for the issue-bound stencil
+    (k_advdif, --fmad=false) the warp-instruction rate vs the issue roofline 148 SMs x 4 schedulers x clock."""
+    kern = sorted(prof, key=lambda r: -r["ms"])
+    tot_ms = sum(r["ms"] for r in kern) or 1.0
+    table = []
+    for r in kern:
+        avg_ms = r["ms"] / max(r["launches"], 1)
+        gbs = r["bytes_per_launch"] / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        row = {"kernel": r["name"], "share": round(r["ms"] / tot_ms, 4), "avg_ms": round(avg_ms, 4),
+               "launches_per_step": r["launches"] / max(steps, 1),
+               "algorithmic_GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4)}
+        if r["name"] == "k_advdif" and clk_mhz:
+            inst = ncu_lookup(ncu, "k_advdif", "inst")          # warp instructions per launch (ncu smsp__inst_executed.sum)
+            if inst and avg_ms > 0:
+                issue_peak = 148 * 4 * clk_mhz * 1e6
+                row["fp32_issue"] = {"warp_inst_per_launch": inst, "achieved_Ginst_s": round(inst / (avg_ms * 1e-3) / 1e9, 1),
+                                     "peak_Ginst_s": round(issue_peak / 1e9, 1), "frac": round(inst / (avg_ms * 1e-3) / issue_peak, 4),
+                                     "note": "instruction count from the committed ncu capture of the same workload; peak = 148 SMs x 4 "
+                                             "schedulers x SM clock (one warp instruction per scheduler per cycle)"}
+        table.append(row)
+    return kern, tot_ms, table
+
+
 # ------------------------------------------------------------------------------------------------
-def run_b200(args):
+def dist_setup(args):
     import torch
     import torch.distributed as dist
 
@@ -266,24 +364,35 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     from rlfluidcontrol_b200 import build as product_build
     if rank == 0:
         product_build.build()
     barrier()
-    import rlfluidcontrol_b200 as R
+    return rank, world, local, barrier
 
-    B, K, W = args.envs_per_gpu, args.steps, args.warmup
+
+def run_b200(args):
+    """Configs 2 and 4: batched default-grid environments, sharded over the ranks (rlfluidcontrol_b200/sharding.py)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local, barrier = dist_setup(args)
+    import rlfluidcontrol_b200 as R
+    from rlfluidcontrol_b200 import sharding
+
+    K, W = args.steps, args.warmup
+    if args.config == 4:
+        if args.envs_total % world:
+            raise SystemExit(f"--envs-total {args.envs_total} must divide by the {world} ranks")
+        e_lo, e_hi = sharding.shard_range(args.envs_total, rank, world)
+        B, total_envs, scaling = e_hi - e_lo, args.envs_total, "strong"
+    else:
+        B, total_envs, scaling = args.envs_per_gpu, args.envs_per_gpu * world, "weak"
+        e_lo = rank * B
     stream = torch.cuda.Stream()
     env = R.AFCCylinderBatch(B, device=local, stream=stream.cuda_stream, init_time=-1.0)
     n_total = 2 * (W + K) + args.profile_steps
-    acts_np = make_actions(n_total, B, rank)
+    acts_np = make_actions(n_total, B, rank, e0=e_lo)
     acts_dev = torch.from_numpy(acts_np).cuda()
     acts_host = torch.from_numpy(acts_np).pin_memory()
     obs_dev = torch.empty((B, 2), dtype=torch.float32, device="cuda")
@@ -296,7 +405,7 @@ def run_b200(args):
     def dev_step(k):
         env.step_device(acts_dev[k].data_ptr(), obs_dev.data_ptr(), rew_dev.data_ptr(), done_dev.data_ptr())
         if world > 1:   # the one exchange of the env-sharded path: every rank sees the whole batch's observations
-            dist.all_gather_into_tensor(obs_all, obs_dev)
+            sharding.gather_observations_equal(obs_dev, obs_all)
 
     step_idx = 0
     with torch.cuda.stream(stream):
@@ -314,11 +423,12 @@ def run_b200(args):
             dev_step(step_idx); step_idx += 1
         e1.record(stream)
         barrier()
-        ms = max_over_ranks(e0.elapsed_time(e1))
+        ms = sharding.max_over_ranks(e0.elapsed_time(e1), world, device="cuda")
         launches = env.launch_count - l0
         clk = clocks.stop() if rank == 0 else None
         obs_check = obs_dev.cpu().numpy()
         assert np.isfinite(obs_check).all(), "non-finite observation"
+        assert env.running() == 0 and not env.flags().any()
 
         # ---- end-to-end arm: host buffers through rlfc_env_step ----
         for _ in range(W):
@@ -328,7 +438,7 @@ def run_b200(args):
         for _ in range(K):
             obs, rew, done = env.step(acts_host[step_idx].numpy()); step_idx += 1
         torch.cuda.synchronize()
-        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e_s = sharding.max_over_ranks(time.perf_counter() - t0, world, device="cuda")
         barrier()
 
         # ---- per-kernel CUDA-event pass (same workload, live) ----
@@ -346,26 +456,19 @@ def run_b200(args):
     barrier()
 
     if rank == 0:
-        total_envs = B * world
         value = total_envs * K / (ms / 1e3)
         e2e = total_envs * K / e2e_s
         peak, peak_src = measured_peak()
-        kern = sorted(prof, key=lambda r: -r["ms"])
-        tot_ms = sum(r["ms"] for r in kern) or 1.0
+        ncu = ncu_summary(2)
+        kern, tot_ms, table = kernel_table(prof, args.profile_steps, peak, clk.get("sm_mhz") if clk else None, ncu)
         roof = None
-        table = []
-        for r in kern:
-            avg_ms = r["ms"] / max(r["launches"], 1)
-            gbs = r["bytes_per_launch"] / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-            table.append({"kernel": r["name"], "share": round(r["ms"] / tot_ms, 4), "avg_ms": round(avg_ms, 4),
-                          "launches_per_env_step": r["launches"] / max(args.profile_steps, 1),
-                          "algorithmic_GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4)})
         if kern:
             top = kern[0]
             avg_ms = top["ms"] / max(top["launches"], 1)
             ach = top["bytes_per_launch"] / (avg_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": ncu_traffic(top["name"]), "peak_source": peak_src, "share_of_step": top["ms"] / tot_ms,
+                    "traffic": ncu_lookup(ncu, top["name"], "dram_traffic_B_per_launch") if B == 256 else None,
+                    "peak_source": peak_src, "share_of_step": top["ms"] / tot_ms,
                     "algorithmic_bytes_per_launch": top["bytes_per_launch"], "avg_launch_ms": avg_ms}
         # whole-step view against the SURVEY 8d model: 4 B * N_int * (28 + 13 (kP + kC)) per env per solver step
         nint = 384 * 192
@@ -375,14 +478,111 @@ def run_b200(args):
         whole["frac_of_hbm_peak"] = whole["achieved_GBps"] / peak
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(B, world), "clocks": clk,
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(B, world, args.config, total_envs), "clocks": clk,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * 2 * 4), "d2h_bytes_per_step": int(B * (2 + 1 + 1) * 4)},
             "gpu_launches": int(launches), "roofline": roof, "whole_step_roofline": whole, "kernels": table,
             "mg_iters_per_solve": k_sum / 2,
         }
+        if world > 1:
+            line["nccl_ranks"] = dist.get_world_size()
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample_env_steps)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_wide(args):
+    """Config 3: one 2048x1024 domain per GPU, one solver step per bench step."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local, barrier = dist_setup(args)
+    import rlfluidcontrol_b200 as R
+    from rlfluidcontrol_b200 import sharding
+
+    K, W = args.steps, max(args.warmup, 3)
+    res = args.resolution
+    t_step = float(np.float32(0.18) / np.float32(res))
+    stream = torch.cuda.Stream()
+    env = R.AFCCylinderBatch(1, init_state=None, device=local, stream=stream.cuda_stream, resolution=res, x_lengths=16, y_lengths=8,
+                             t_step=t_step)
+    cells = (env.n - 2) * (env.m - 2)
+    act_dev = torch.tensor([[0.5, -0.5]], dtype=torch.float32, device="cuda")
+    act_host = np.array([[0.5, -0.5]], np.float32)
+    with torch.cuda.stream(stream):
+        # SURVEY 8d: actions 0 for the impulsive start (the first solves take several MG iterations), then (0.5, -0.5)
+        for _ in range(args.settle_steps):
+            env.update2_device()
+        env.update2_device(act_dev.data_ptr())
+        for _ in range(W):
+            env.update2_device()
+        barrier()
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        l0 = env.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(K):
+            env.update2_device()
+        e1.record(stream)
+        barrier()
+        ms = sharding.max_over_ranks(e0.elapsed_time(e1), world, device="cuda")
+        launches = env.launch_count - l0
+        clk = clocks.stop() if rank == 0 else None
+        # ---- end-to-end: host action in, force + probes out, every step ----
+        for _ in range(W):
+            env.update2(act_host, want_probes=True)
+        barrier()
+        t0 = time.perf_counter()
+        its = []
+        for _ in range(K):
+            f, pr = env.update2(act_host, want_probes=True)
+        torch.cuda.synchronize()
+        e2e_s = sharding.max_over_ranks(time.perf_counter() - t0, world, device="cuda")
+        assert np.isfinite(f).all() and not env.flags().any()
+        barrier()
+        prof = []
+        if rank == 0 and args.profile_steps > 0:
+            env.set_profiling(True)
+            for _ in range(args.profile_steps):
+                env.update2()
+                its.append(env.mg_iters()[0].tolist())
+            prof = env.get_profile()
+            env.set_profiling(False)
+    env.close()
+    barrier()
+    if rank == 0:
+        value = world * K / (ms / 1e3)
+        e2e = world * K / e2e_s
+        peak, peak_src = measured_peak()
+        kern, tot_ms, table = kernel_table(prof, args.profile_steps, peak, clk.get("sm_mhz") if clk else None, ncu_summary(3))
+        k_sum = float(np.sum(its, axis=1).mean()) if its else 2.0
+        # SURVEY 8d, coarse levels off chip: 4 B * N_int * (28 + 16 (kP + kC)) per solver step = 240 B/cell at one iteration per solve
+        model_bytes = 4.0 * cells * (28 + 16 * k_sum)
+        ach = model_bytes / (ms / K * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "whole solver step (every kernel of the step is a latency chain or a small grid; no single "
+                                          "kernel dominates: see `kernels`)",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": model_bytes, "avg_launch_ms": ms / K,
+                "model": "4 B x N_int x (28 + 16 (kP + kC)) = 240 B/cell at one MG iteration per solve (SURVEY 8d)"}
+        if kern:
+            top = kern[0]
+            roof["dominant_kernel"] = {"kernel": top["name"], "share_of_step": top["ms"] / tot_ms,
+                                       "avg_launch_ms": top["ms"] / max(top["launches"], 1)}
+        line = {
+            "metric": METRIC3, "value": value, "unit": UNIT3, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config3(world), "clocks": clk,
+            "e2e": {"value": e2e, "unit": UNIT3, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": int((2 + 32) * 4)},
+            "gpu_launches": int(launches), "roofline": roof, "kernels": table, "mg_iters_per_solve": k_sum / 2,
+        }
+        if res != 128:
+            line["config"]["workload"] += f" [scaled run: resolution {res}, grid {env.n - 2}x{env.m - 2}]"
+        if world == 1 and not args.no_cpu_baseline and res == 128:
+            line["cpu_baseline"] = cpu_baseline_wide(args.cpu_sample_wide_steps)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -391,19 +591,32 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--envs-per-gpu", type=int, default=256)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json configs[] entry (1-based)")
+    ap.add_argument("--envs-per-gpu", type=int, default=256, help="config 2: environments per GPU (weak scaling)")
+    ap.add_argument("--envs-total", type=int, default=4096, help="config 4: environments in total, split over the ranks")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--profile-steps", type=int, default=1)
     ap.add_argument("--cpu-sample-env-steps", type=int, default=4)
+    ap.add_argument("--cpu-sample-wide-steps", type=int, default=2)
     ap.add_argument("--ref-env-steps", type=int, default=2, help="env-steps per core per step in --impl reference")
+    ap.add_argument("--resolution", type=int, default=128, help="config 3: cells per diameter (128 = the 2048x1024 domain)")
+    ap.add_argument("--settle-steps", type=int, default=12, help="config 3: untimed solver steps after the impulsive start")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 200 if (args.config == 3 and args.impl == "b200") else 8
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == 5:
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"metric": "solver-steps/sec (single 8192x4096 BDIM domain, slab-decomposed)", "unavailable":
+                              "config 5 (slab decomposition over 8 GPUs with NVLink halo exchange) is not built; see DESIGN.md section 5"}))
+    elif args.config == 3:
+        run_wide(args)
     else:
         run_b200(args)
 

@@ -123,6 +123,11 @@ int  rlfc_env_get_flags(rlfc_env *env, int *flags);
      probes  [n_envs][32] surface pressure samples or NULL.                                     */
 int  rlfc_env_substep(rlfc_env *env, const float *actions, float *force, float *probes);
 
+/* Same solver step, asynchronous on the handle's stream: d_actions is a DEVICE pointer ([n_envs][2]) or NULL (keep xi);
+   nothing is copied back (force and probes stay on the device: rlfc_env_substep(env, NULL, ...) style read-outs or
+   rlfc_env_get_fields synchronise later). */
+int  rlfc_env_substep_device(rlfc_env *env, const float *d_actions);
+
 /* Field export/import for one environment, reference layout (n+2)*(m+2) floats each; NULL skips. */
 int  rlfc_env_get_fields(rlfc_env *env, int e, float *ux, float *uy, float *p);
 int  rlfc_env_set_fields(rlfc_env *env, int e, const float *ux, const float *uy, const float *p);

@@ -954,6 +954,13 @@ int rlfc_env_step(rlfc_env* E, const float* actions, float* obs, float* reward, 
   return RLFC_OK;
 }
 
+int rlfc_env_substep_device(rlfc_env* E, const float* d_actions) {
+  if (!E) return fail(RLFC_EINVAL, "null handle");
+  CU(cudaSetDevice(E->device));
+  E->launches += launch_set_actions(E->sp, d_actions, 0, E->stream);
+  return solver_steps(E, 1, 0);
+}
+
 int rlfc_env_substep(rlfc_env* E, const float* actions, float* force, float* probes) {
   if (!E) return fail(RLFC_EINVAL, "null handle");
   CU(cudaSetDevice(E->device));

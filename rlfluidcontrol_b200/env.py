@@ -65,6 +65,7 @@ def load_library():
     L.rlfc_env_step.argtypes = [vp, fp, fp, fp, ip]
     L.rlfc_env_step_device.argtypes = [vp, vp, vp, vp, vp]
     L.rlfc_env_substep.argtypes = [vp, fp, fp, fp]
+    L.rlfc_env_substep_device.argtypes = [vp, vp]
     L.rlfc_env_get_fields.argtypes = [vp, C.c_int, fp, fp, fp]
     L.rlfc_env_set_fields.argtypes = [vp, C.c_int, fp, fp, fp]
     L.rlfc_env_save_bdim.argtypes = [vp, C.c_int, C.c_char_p]
@@ -184,6 +185,10 @@ class AFCCylinderBatch:
         rc = self._L.rlfc_env_substep(self._h, _fp(a), _fp(force), _fp(probes))
         self._check(rc, "rlfc_env_substep")
         return (force, probes) if want_probes else force
+
+    def update2_device(self, d_actions=0):
+        """One solver step, asynchronous on the handle's stream; d_actions = device pointer (int) or 0 to keep xi."""
+        self._check(self._L.rlfc_env_substep_device(self._h, C.c_void_p(d_actions) if d_actions else None), "rlfc_env_substep_device")
 
     # -- state / introspection --------------------------------------------------------------
     def get_fields(self, e=0):

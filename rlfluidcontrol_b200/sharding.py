@@ -14,15 +14,35 @@ def shard_range(n_envs_total: int, rank: int, world: int) -> tuple[int, int]:
 
 
 def gather_observations(obs, world: int, group=None):
-    """All-gather the (B_local, 2) observation tensors of every rank into (B_total, 2) (equal shard sizes).
+    """All-gather the (B_local, 2) observation tensors of every rank into (B_total, 2), in global env order.
+    Shards may differ in size by one (shard_range): they are padded to the largest shard for the collective and the
+    padding is dropped again.  `out` (optional) is a preallocated (world * B_max, ...) buffer for the equal-shard case.
     Works with the gloo backend on CPU tensors and the nccl backend on CUDA tensors."""
     import torch
     import torch.distributed as dist
 
     if world == 1:
         return obs
-    out = torch.empty((world * obs.shape[0],) + tuple(obs.shape[1:]), dtype=obs.dtype, device=obs.device)
+    sizes = torch.tensor([obs.shape[0]], dtype=torch.int64, device=obs.device)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    all_sizes = [int(s.item()) for s in all_sizes]
+    bmax = max(all_sizes)
+    if obs.shape[0] < bmax:
+        pad = torch.zeros((bmax - obs.shape[0],) + tuple(obs.shape[1:]), dtype=obs.dtype, device=obs.device)
+        obs = torch.cat([obs, pad])
+    out = torch.empty((world * bmax,) + tuple(obs.shape[1:]), dtype=obs.dtype, device=obs.device)
     dist.all_gather_into_tensor(out, obs.contiguous(), group=group)
+    if min(all_sizes) == bmax:
+        return out
+    return torch.cat([out[r * bmax: r * bmax + all_sizes[r]] for r in range(world)])
+
+
+def gather_observations_equal(obs, out, group=None):
+    """The steady-state form used inside timed loops: equal shards, preallocated output, one collective."""
+    import torch.distributed as dist
+
+    dist.all_gather_into_tensor(out, obs, group=group)
     return out
 
 

@@ -15,15 +15,22 @@ def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch
     import torch.distributed as dist
-    from rlfluidcontrol_b200.sharding import gather_observations, max_over_ranks, shard_range
+    from rlfluidcontrol_b200.sharding import gather_observations, gather_observations_equal, max_over_ranks, shard_range
     import bench
 
     dist.init_process_group("gloo", rank=rank, world_size=world)
     e0, e1 = shard_range(16, rank, world)
-    acts = bench.make_actions(3, e1 - e0, rank)
+    acts = bench.make_actions(3, e1 - e0, rank, e0=e0)
     # stand-in observation: a deterministic function of the global env id and this rank's first action
     obs = torch.tensor([[float(e), float(acts[0, e - e0, 0])] for e in range(e0, e1)], dtype=torch.float32)
     full = gather_observations(obs, world)
+    # the preallocated equal-shard form bench.py uses inside its timed loop
+    pre = torch.empty((world * obs.shape[0], 2), dtype=torch.float32)
+    assert torch.equal(gather_observations_equal(obs, pre), full)
+    # uneven shards (17 envs over 2 ranks: 8 + 9) keep the global env order
+    u0, u1 = shard_range(17, rank, world)
+    uneven = gather_observations(torch.arange(u0, u1, dtype=torch.float32).reshape(-1, 1), world)
+    assert torch.equal(uneven[:, 0], torch.arange(17, dtype=torch.float32))
     t = max_over_ranks(1.0 + rank, world)
     out.put((rank, full.numpy().copy(), t, (e0, e1)))
     dist.barrier()
