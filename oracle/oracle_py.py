@@ -290,6 +290,11 @@ class OracleEnv:
             raise KeyError(name)
         return np.ctypeslib.as_array(ptr, shape=(self.n, self.m)).copy()
 
+    def adopt_driver(self, other):
+        """Take over another environment's draw() accumulators: callLearn, Cd, Cl are sketch globals that survive
+        setUpNewSim (clientCFD.pde:11-13)."""
+        self._drv = other._drv
+
     def driver_step(self, init_time=-1.0):
         """One solver step + clientCFD.draw() accumulation.  Returns (Cl, Cd) when an observation was
         produced on this step, else None."""

@@ -157,7 +157,7 @@ class AgentServer:
         self.server = SimpleXMLRPCServer((host, port), logRequests=False, allow_none=True)
         self.port = self.server.server_address[1]
         for name in ("init", "start_episode", "request_stochastic_action", "request_deterministic_action", "train", "save",
-                     "save_eval", "restore", "request_batch_action"):
+                     "save_eval", "restore", "request_batch_action", "finish_envs"):
             self.server.register_function(getattr(self, "_" + name), name)
 
     def _stamp(self, s):
@@ -201,13 +201,29 @@ class AgentServer:
         return self._request_action(raw_data, False)
 
     def _request_batch_action(self, raw_data):
-        """Extension: "Cl_Cd;Cl_Cd;..." -> "a1_a2;a1_a2;..." with one record stream per environment."""
+        """Extension: "Cl_Cd;Cl_Cd;..." -> "a1_a2;a1_a2;..." with one record stream per environment.  An empty field
+        ("Cl_Cd;;Cl_Cd") marks an environment that has no observation this round (still in its uncontrolled start): it
+        gets the action "0.0_0.0" and nothing is recorded for it."""
         self.calls.append(("request_batch_action", raw_data))
-        states = np.array([[float(v) for v in s.split("_")] for s in raw_data.split(";")])
-        actions = self.agent.get_action(states, stochastic=True)
-        for e, (s, a) in enumerate(zip(states, actions)):
-            self.batch_records.setdefault(e, []).append((s[None, :], a[None, :]))
-        return ";".join("_".join(str(i) for i in a) for a in actions)
+        fields = raw_data.split(";")
+        live = [e for e, f in enumerate(fields) if f]
+        out = ["0.0_0.0"] * len(fields)
+        if live:
+            states = np.array([[float(v) for v in fields[e].split("_")] for e in live])
+            actions = self.agent.get_action(states, stochastic=True)
+            for e, s, a in zip(live, states, actions):
+                self.batch_records.setdefault(e, []).append((s[None, :], a[None, :]))
+                out[e] = "_".join(str(i) for i in a)
+        return ";".join(out)
+
+    def _finish_envs(self, raw_data):
+        """Extension: "3;7" -- the episodes of these environments are over (batched auto-reset): their record streams
+        become transitions now (consecutive records of ONE environment, server.py:157-165) and start afresh."""
+        self.calls.append(("finish_envs", raw_data))
+        for e in (int(v) for v in raw_data.split(";") if v):
+            rec = self.batch_records.pop(e, [])
+            self._store_transitions([s for s, _ in rec], [a for _, a in rec])
+        return True
 
     # ---- server.py:148-203 ----
     def _store_transitions(self, states, actions):
@@ -224,6 +240,7 @@ class AgentServer:
         self._store_transitions(self.state_record, self.action_record)
         for rec in self.batch_records.values():
             self._store_transitions([s for s, _ in rec], [a for _, a in rec])
+        self.batch_records = {}
         self._stamp("Training Start!")
         for _ in range(steps):
             self.agent.train_iter()
