@@ -145,6 +145,12 @@ int  rlfc_env_field_sum_stats(rlfc_env *env, int *stats);
 int  rlfc_env_save_bdim(rlfc_env *env, int e, const char *path);
 int  rlfc_env_load_bdim(rlfc_env *env, int e, const char *path);
 
+/* BDIM.checkCFL (BDIM.pde:217-219, VectorField.CFL VectorField.pde:225-235) of every environment's current velocity:
+   dt[n_envs] = min(1 / (max_interior(|ux| + |uy|) + 3 nu), 1), the time step the reference's adaptive variant
+   AFCCylinder.update() (AFCCylinder.pde:63-84) would take next.  The environment step itself runs the fixed dt of
+   AFCCylinder.update2 (what clientCFD.pde calls); stepping with a per-environment dt is not implemented. */
+int  rlfc_env_check_cfl(rlfc_env *env, float *dt);
+
 /* Introspection. */
 int  rlfc_env_dims(const rlfc_env *env, int *n_with_ghosts, int *m_with_ghosts, int *n_envs);
 int  rlfc_env_get_time(rlfc_env *env, float *t /*[n_envs]*/);

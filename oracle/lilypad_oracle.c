@@ -991,6 +991,33 @@ void ora_env_update2(ora_env *e) {
   e->forcex = fx * -1; e->forcey = fy * -1;     /* PVector.mult(-1) */
 }
 
+/* VectorField.CFL VectorField.pde:225-235 (Processing float literals: 1./(b+3.*nu) is float arithmetic) */
+float ora_vfield_CFL(const ora_vfield *u, float nu) {
+  float b = pabs(AT(&u->x, 0, 0)) + pabs(AT(&u->y, 0, 0));
+  for (int i = 1; i < u->x.n - 1; i++)
+    for (int j = 1; j < u->x.m - 1; j++) {
+      float c = pabs(AT(&u->x, i, j)) + pabs(AT(&u->y, i, j));
+      if (c > b) b = c;
+    }
+  return 1.f / (b + 3.f * nu);
+}
+
+/* BDIM.checkCFL BDIM.pde:217-219 */
+float ora_env_check_cfl(const ora_env *e) { return pmin(ora_vfield_CFL(&e->u, e->nu), 1.f); }
+
+/* One pass of the NT loop of AFCCylinder.update() AFCCylinder.pde:63-84 (QUICK: dt = flow.checkCFL() before every
+   step).  dt changes from step to step, so c = del*rhoi*dt and the whole Poisson hierarchy change with it: the step runs
+   in the literal mode (everything rebuilt where the reference rebuilds it) whatever the env was created with. */
+void ora_env_update_adaptive(ora_env *e) {
+  const int lit = e->cfg.literal;
+  e->cfg.literal = 1;
+  e->dt = ora_env_check_cfl(e);
+  ora_env_update2(e);               /* from `flow.dt = dt` on the two methods are the same statements */
+  e->cfg.literal = lit;
+}
+
+float ora_env_dt(const ora_env *e) { return e->dt; }
+
 /* SaveScalar.addData03 SaveScalar.pde:61-72 with the ctor's centX=n/4, centY=m/2 (:36-40) */
 void ora_env_probes(const ora_env *e, int numTheta, float *out) {
   float res = (float)e->cfg.resolution;

@@ -124,6 +124,10 @@ void     ora_env_get_state(const ora_env *e, float *ux, float *uy, float *p);
 void     ora_env_set_xi(ora_env *e, float xi1, float xi2);                /* clientCFD.pde:51-54 */
 void     ora_env_update2(ora_env *e);                                     /* AFCCylinder.pde:45-61 */
 float    ora_env_t(const ora_env *e);
+float    ora_vfield_CFL(const ora_vfield *u, float nu);                   /* VectorField.pde:225-235 */
+float    ora_env_check_cfl(const ora_env *e);                             /* BDIM.pde:217-219 */
+void     ora_env_update_adaptive(ora_env *e);                             /* AFCCylinder.pde:63-84 (one NT pass) */
+float    ora_env_dt(const ora_env *e);
 void     ora_env_force(const ora_env *e, float *fx, float *fy);
 void     ora_env_probes(const ora_env *e, int numTheta, float *out);      /* SaveScalar.pde:61-72 */
 int      ora_env_last_mg_iters(const ora_env *e, int which /*0 predictor, 1 corrector*/);

@@ -69,6 +69,12 @@ def lib():
         L.ora_env_get_state.argtypes = [C.c_void_p, fp, fp, fp]
         L.ora_env_set_xi.argtypes = [C.c_void_p, C.c_float, C.c_float]
         L.ora_env_update2.argtypes = [C.c_void_p]
+        L.ora_env_check_cfl.restype = C.c_float
+        L.ora_env_check_cfl.argtypes = [C.c_void_p]
+        L.ora_env_dt.restype = C.c_float
+        L.ora_env_dt.argtypes = [C.c_void_p]
+        L.ora_env_update_adaptive.restype = None
+        L.ora_env_update_adaptive.argtypes = [C.c_void_p]
         L.ora_env_t.restype = C.c_float
         L.ora_env_t.argtypes = [C.c_void_p]
         L.ora_env_force.argtypes = [C.c_void_p, fp, fp]
@@ -267,6 +273,10 @@ class OracleEnv:
         return ux, uy, p
 
     def set_xi(self, xi1, xi2): lib().ora_env_set_xi(self._e, float(xi1), float(xi2))
+    def check_cfl(self): return np.float32(lib().ora_env_check_cfl(self._e))          # BDIM.checkCFL
+    def update_adaptive(self): lib().ora_env_update_adaptive(self._e)                 # AFCCylinder.update(), one pass
+    @property
+    def dt(self): return np.float32(lib().ora_env_dt(self._e))
     def update2(self): lib().ora_env_update2(self._e)
 
     @property

@@ -377,7 +377,20 @@ int read_checkpoint(const std::string& path, int n, int m, float& t, float& dt, 
       q = end;
       while (*q == ',' || *q == ' ') q++;
     }
+    // BDIM.write puts exactly three numbers on a line: anything behind them means another format
+    while (*q == '\r' || *q == '\n' || *q == ' ' || *q == '\t') q++;
+    if (*q) { std::fclose(f); err = "trailing data on a line of " + path; return RLFC_EIO; }
     ux[k] = v[0]; uy[k] = v[1]; p[k] = v[2];
+  }
+  // ... and exactly n*m cell lines: a checkpoint of a larger grid would otherwise be accepted with its rows reinterpreted
+  while (next()) {
+    const char* q = line;
+    while (*q == '\r' || *q == '\n' || *q == ' ' || *q == '\t') q++;
+    if (*q) {
+      std::fclose(f);
+      err = "checkpoint " + path + " has more lines than the " + std::to_string(n) + "x" + std::to_string(m) + " grid";
+      return RLFC_EIO;
+    }
   }
   std::fclose(f);
   return RLFC_OK;

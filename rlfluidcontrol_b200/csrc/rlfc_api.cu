@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -219,7 +220,9 @@ int project_eager(rlfc_env* E, Group& G, float* Ux, float* Uy, int which) {
     if (it == 0 && E->fused)
       E->run("k_resid_down0", 5.25, [&] { return launch_resid_down0(sp, Ux, Uy, pA, pB, rs, which, st); }, st, gi);
     else {
-      E->run("k_unskew_r", 2, [&] { return launch_unskew_r(sb, r, st); }, st, gi);
+      // (the plain residual is fresh from k_residual in the first iteration of the unfused path; afterwards the row
+      // smoother has left it skewed)
+      if (it > 0) E->run("k_unskew_r", 2, [&] { return launch_unskew_r(sb, r, st); }, st, gi);
       E->run("k_mg_down0", 4.25, [&] { return launch_mg_down0(sb, r, rs, st); }, st, gi);
     }
     if (sp.chain_levels > 0 && E->profiling) {   // per-kernel timing of the chained levels
@@ -741,6 +744,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   if (const char* ev = std::getenv("RLFC_EAGER_GROUPS")) E->eager_groups = std::atoi(ev) != 0;
   if (const char* ev = std::getenv("RLFC_TRACE")) E->trace_path = ev;
   if (const char* ev = std::getenv("RLFC_FUSED")) E->fused = std::atoi(ev) != 0;
+  TRY(E->dmalloc(&sp.sc.flow_t, B));
   TRY(E->dmalloc(&sp.sc.xi, 2 * B)); TRY(E->dmalloc(&sp.sc.t, B)); TRY(E->dmalloc(&sp.sc.force, 2 * B));
   TRY(E->dmalloc(&sp.sc.probes, (size_t)B * RLFC_NUM_PROBES));
   TRY(E->dmalloc(&sp.sc.callLearn, B)); TRY(E->dmalloc(&sp.sc.Cd, B)); TRY(E->dmalloc(&sp.sc.Cl, B));
@@ -821,6 +825,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     if (v.chain_levels > 0) { v.rr_chain += (size_t)e0 * v.rr_chain_n; v.rr_count += e0; }
     v.band_tmp += (size_t)e0 * (v.nband_x + v.nband_y);
     v.rsk += (size_t)e0 * v.rsk_stride;
+    v.sc.flow_t += e0;
     v.sc.xi += 2 * e0; v.sc.t += e0; v.sc.force += 2 * e0; v.sc.probes += (size_t)e0 * RLFC_NUM_PROBES;
     v.sc.callLearn += e0; v.sc.Cd += e0; v.sc.Cl += e0; v.sc.obs += 2 * e0; v.sc.active += e0; v.sc.iters += 2 * e0;
     v.sc.frozen += e0; v.sc.non_finite += e0;
@@ -893,6 +898,7 @@ int rlfc_env_reset(rlfc_env* E, const int* env_ids, int n, int reset_accumulator
     int e = env_ids ? env_ids[k] : k;
     CU(cudaMemsetAsync(sp.sc.xi + 2 * e, 0, 2 * sizeof(float), E->stream));
     CU(cudaMemsetAsync(sp.sc.t + e, 0, sizeof(float), E->stream));
+    CU(cudaMemcpyAsync(sp.sc.flow_t + e, &E->init_t, sizeof(float), cudaMemcpyHostToDevice, E->stream));   // BDIM.resume: t = stuff[0]
     CU(cudaMemsetAsync(sp.sc.force + 2 * e, 0, 2 * sizeof(float), E->stream));
     CU(cudaMemsetAsync(sp.sc.frozen + e, 0, sizeof(int), E->stream));
     CU(cudaMemsetAsync(sp.sc.non_finite + e, 0, sizeof(int), E->stream));
@@ -1020,13 +1026,15 @@ int rlfc_env_set_fields(rlfc_env* E, int e, const float* ux, const float* uy, co
 int rlfc_env_save_bdim(rlfc_env* E, int e, const char* path) {
   if (!E || !path || e < 0 || e >= E->sp.B) return fail(RLFC_EINVAL, "bad argument");
   const size_t N = (size_t)E->sp.n * E->sp.m;
-  std::vector<float> ux(N), uy(N), p(N), t(E->sp.B);
+  std::vector<float> ux(N), uy(N), p(N);
   int rc = rlfc_env_get_fields(E, e, ux.data(), uy.data(), p.data());
   if (rc) return rc;
-  if ((rc = rlfc_env_get_time(E, t.data()))) return rc;
+  // BDIM.t counts grid-unit time: set by resume, += dt per solver step (AFCCylinder.t advances by dt/resolution instead)
+  float flow_t = 0;
+  CU(cudaMemcpyAsync(&flow_t, E->sp.sc.flow_t + e, sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaStreamSynchronize(E->stream));
   std::string err;
-  // BDIM.t counts grid-unit time: flow.t advances by dt per step while AFCCylinder.t advances by dt/resolution
-  rc = write_bdim_text(path, E->sp.n, E->sp.m, E->init_t + t[e] * E->sp.resolution, E->sp.dt, ux.data(), uy.data(), p.data(), err);
+  rc = write_bdim_text(path, E->sp.n, E->sp.m, flow_t, E->sp.dt, ux.data(), uy.data(), p.data(), err);
   return rc ? fail(rc, err) : RLFC_OK;
 }
 
@@ -1037,6 +1045,11 @@ int rlfc_env_load_bdim(rlfc_env* E, int e, const char* path) {
   std::string err;
   int rc = read_checkpoint(path, E->sp.n, E->sp.m, t, dt, ux, uy, p, err);
   if (rc) return fail(rc, err);
+  if (dt != E->sp.dt && !(std::fabs(dt - E->sp.dt) <= 1e-6f * E->sp.dt))
+    return fail(RLFC_EIO, "checkpoint dt " + std::to_string(dt) + " does not match the handle's " + std::to_string(E->sp.dt));
+  CU(cudaSetDevice(E->device));
+  CU(cudaMemcpyAsync(E->sp.sc.flow_t + e, &t, sizeof(float), cudaMemcpyHostToDevice, E->stream));   // BDIM.resume: t = stuff[0]
+  CU(cudaStreamSynchronize(E->stream));
   return rlfc_env_set_fields(E, e, ux.data(), uy.data(), p.data());
 }
 
@@ -1071,6 +1084,17 @@ int rlfc_env_get_flags(rlfc_env* E, int* flags) {
   CU(cudaMemcpyAsync(E->h_done, E->sp.sc.non_finite, E->sp.B * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
   CU(cudaStreamSynchronize(E->stream));
   for (int e = 0; e < E->sp.B; e++) flags[e] = E->h_done[e] ? 1 : 0;
+  return RLFC_OK;
+}
+
+int rlfc_env_check_cfl(rlfc_env* E, float* dt) {
+  if (!E || !dt) return fail(RLFC_EINVAL, "null argument");
+  CU(cudaSetDevice(E->device));
+  E->launches += launch_check_cfl(E->sp, E->uAx, E->uAy, E->d_reward, E->stream);      // (d_reward: a [B] float scratch)
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(E->h_reward, E->d_reward, E->sp.B * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+  CU(cudaStreamSynchronize(E->stream));
+  std::memcpy(dt, E->h_reward, E->sp.B * sizeof(float));
   return RLFC_OK;
 }
 

@@ -77,6 +77,7 @@ struct ForcePt { int i, j; float s, t, l, nx, ny; };
 struct EnvScalars {
   float *xi;        // [B][2] current action (xi1, xi2)
   float *t;         // [B]    AFCCylinder.t
+  float *flow_t;    // [B]    BDIM.t: grid-unit time, += dt per solver step (BDIM.pde:106), set from the checkpoint
   float *force;     // [B][2] last raw force (-pressForce)
   float *probes;    // [B][32]
   int   *callLearn; // [B]    draw() accumulators (clientCFD.pde:11-13)
@@ -186,6 +187,8 @@ int launch_heun(const SolverParams& P, const float* ucx, const float* ucy, const
                 float* uax, float* uay, cudaStream_t st);
 // force + probes + time advance; accumulate != 0 applies the clientCFD.draw() accumulation
 int launch_force(const SolverParams& P, int accumulate, cudaStream_t st);
+// BDIM.checkCFL of every environment's current velocity: d_dt[B] = min(1/(max(|ux|+|uy|) + 3 nu), 1)
+int launch_check_cfl(const SolverParams& P, const float* ux, const float* uy, float* d_dt, cudaStream_t st);
 // mode 0 (single solver steps): xi = actions (NULL keeps xi), every env runs.  mode 1 (RL step): an env takes its
 // action only where the reference would have asked for one (t > init_time and at a callLearn boundary); envs whose
 // episode is over (t >= episode_time) are frozen for the call

@@ -1129,6 +1129,7 @@ k_force(const __grid_constant__ SolverParams q, int accumulate) {
     q.sc.force[2 * e + 1] = fy;
     const float t = q.sc.t[e] + q.dt_over_res;                                    // AFCCylinder.pde:56
     q.sc.t[e] = t;
+    q.sc.flow_t[e] += q.dt;                                                       // BDIM.update2: t += dt (BDIM.pde:106)
     if (!isfinite(fx) || !isfinite(fy)) q.sc.non_finite[e] = 1;                   // diverged environment (sticky flag)
     if (accumulate && t >= q.episode_time) q.sc.frozen[e] = 1;                    // clientCFD.pde:36: no frame past Time
     if (accumulate && t > q.init_time) {                                          // clientCFD.pde:39-47
@@ -1153,6 +1154,34 @@ k_force(const __grid_constant__ SolverParams q, int accumulate) {
 // changes xi only when callAction returns, i.e. right after an observation was emitted (clientCFD.pde:44-54): an env
 // that has not reached its first callLearn boundary yet (t <= initTime after a reset, or mid-window after an episode
 // change with the sketch-global accumulators kept) keeps its xi.  An env past the episode end takes no more steps.
+// BDIM.checkCFL (BDIM.pde:217-219) = min(u.CFL(nu), 1), VectorField.CFL (VectorField.pde:225-235): 1/(b + 3 nu) with
+// b = max(|ux|+|uy|) over the interior, started from cell [0][0].  A maximum does not depend on the order it is taken in,
+// so the reduction is parallel and still exact.  One CTA per environment (a diagnostic / adaptive-dt read-out, not on
+// the fixed-dt step path).
+__global__ void __launch_bounds__(1024)
+k_check_cfl(const __grid_constant__ SolverParams q, const float* __restrict__ ux_all, const float* __restrict__ uy_all,
+            float* __restrict__ dt_out) {
+  __shared__ float wmax[32];
+  const int e = blockIdx.x, P = q.P, ni = q.n - 2, mj = q.m - 2;
+  const float* ux = ux_all + (size_t)e * q.stride;
+  const float* uy = uy_all + (size_t)e * q.stride;
+  float b = fabsf(ux[0]) + fabsf(uy[0]);
+  for (int k = threadIdx.x; k < ni * mj; k += blockDim.x) {
+    const int i = 1 + k / mj, j = 1 + k - (k / mj) * mj;
+    const float c = fabsf(ux[IDX(i, j)]) + fabsf(uy[IDX(i, j)]);
+    if (c > b) b = c;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const float v = __shfl_down_sync(0xffffffffu, b, o); if (v > b) b = v; }
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = b;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) if (wmax[w] > b) b = wmax[w];
+    const float cfl = 1.f / (b + 3.f * q.nu);
+    dt_out[e] = cfl < 1.f ? cfl : 1.f;                                      // PApplet.min(u.CFL(nu), 1)
+  }
+}
+
 __global__ void k_set_actions(const __grid_constant__ SolverParams q, const float* __restrict__ act, int mode) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= q.B) return;
@@ -1476,6 +1505,11 @@ int launch_heun(const SolverParams& q, const float* ucx, const float* ucy, const
 
 int launch_force(const SolverParams& q, int accumulate, cudaStream_t st) {
   k_force<<<q.B, 64, 0, st>>>(q, accumulate);
+  return 1;
+}
+
+int launch_check_cfl(const SolverParams& q, const float* ux, const float* uy, float* d_dt, cudaStream_t st) {
+  k_check_cfl<<<q.B, 1024, 0, st>>>(q, ux, uy, d_dt);
   return 1;
 }
 

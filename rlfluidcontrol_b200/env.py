@@ -73,6 +73,7 @@ def load_library():
     L.rlfc_env_dims.argtypes = [vp, ip, ip, ip]
     L.rlfc_env_get_time.argtypes = [vp, fp]
     L.rlfc_env_get_mg_iters.argtypes = [vp, ip]
+    L.rlfc_env_check_cfl.argtypes = [vp, fp]
     L.rlfc_env_running.argtypes = [vp, ip]
     L.rlfc_env_get_flags.argtypes = [vp, ip]
     L.rlfc_env_field_sum.argtypes = [vp, fp]
@@ -211,6 +212,12 @@ class AFCCylinderBatch:
         t = np.empty(self.n_envs, np.float32)
         self._check(self._L.rlfc_env_get_time(self._h, _fp(t)), "rlfc_env_get_time")
         return t
+
+    def check_cfl(self):
+        """BDIM.checkCFL per environment: min(1/(max(|ux|+|uy|) + 3 nu), 1)."""
+        dt = np.empty(self.n_envs, np.float32)
+        self._check(self._L.rlfc_env_check_cfl(self._h, _fp(dt)), "rlfc_env_check_cfl")
+        return dt
 
     def running(self):
         """Environments that had not emitted their observation when the last RL-step round ended."""

@@ -144,6 +144,17 @@ def test_reset_and_field_roundtrip(rlfc, init_state, tmp_path):
             assert_same(y, x, f"{nm} text checkpoint round trip")
         lines = path.read_text().splitlines()
         assert len(lines) == 2 + env.n * env.m and lines[2].count(",") == 2
+        # BDIM.t round trip: resume sets t = line 0, every solver step adds dt (BDIM.pde:106,242); one step was taken
+        t_file = np.float32(lines[0])
+        assert t_file == np.float32(np.float32(init_state["t"]) + np.float32(init_state["dt"]))
+        env.update2()
+        env.save_bdim(2, path)                       # env 2 resumed from the file: its clock continues from the file's
+        assert np.float32(path.read_text().splitlines()[0]) == np.float32(t_file + np.float32(init_state["dt"]))
+        # a checkpoint of another grid is rejected, not reinterpreted
+        bad = tmp_path / "bad.bdim"
+        bad.write_text("\n".join(lines + ["1.0, 0.0, 0.0"]) + "\n")
+        with pytest.raises(rlfc.RlfcError):
+            env.load_bdim(0, bad)
 
 
 @pytest.mark.parametrize("resolution,xl,yl", [(16, 16, 8), (8, 16, 8), (12, 8, 4), (24, 8, 4)])
@@ -165,13 +176,15 @@ def test_other_grids(rlfc, oracle, resolution, xl, yl):
 
 
 @pytest.mark.parametrize("envvar,value", [("RLFC_SMOOTHER", "strip"), ("RLFC_SMOOTHER", "wave"), ("RLFC_SMOOTHER", "chain"),
-                                          ("RLFC_NO_GRAPH", "1"),
+                                          ("RLFC_NO_GRAPH", "1"), ("RLFC_FUSED", "0"),
                                           ("RLFC_GROUPS", "3"), ("RLFC_FAST_BC", "0"), ("RLFC_PSUM", "serial")])
 def test_alternative_execution_paths(rlfc, oracle, init_state, monkeypatch, envvar, value):
     """The strip smoother, the wavefront fallback smoother, eager launches, odd env-group splits, the literal setBC kernels and the plain
     serial Field.sum chain are different
     schedules of the same arithmetic: all must reproduce the oracle bit for bit."""
     monkeypatch.setenv(envvar, value)
+    if envvar == "RLFC_FUSED":                     # the unfused kernels only exist on the eager path
+        monkeypatch.setenv("RLFC_NO_GRAPH", "1")
     ref = make_oracle(oracle, init_state)
     ref.set_xi(-0.6, 0.9)
     B = 7
@@ -206,3 +219,17 @@ def test_wide_grid(rlfc, oracle, resolution, dims):
             assert tuple(env.mg_iters()[0]) == ref.mg_iters()
         for nm, a, b in zip(("ux", "uy", "p"), env.get_fields(0), ref.get_state()):
             assert_same(a, b, nm)
+
+
+def test_check_cfl(rlfc, oracle, init_state):
+    """BDIM.checkCFL (adaptive-dt variant of the reference, BDIM.pde:217-219): the device maximum == the oracle's, on the
+    developed wake and after a few steps of two differently driven environments."""
+    refs = [make_oracle(oracle, init_state) for _ in range(2)]
+    refs[1].set_xi(0.9, -0.9)
+    with rlfc.AFCCylinderBatch(2) as env:
+        assert_same(env.check_cfl(), np.array([r.check_cfl() for r in refs], np.float32), "checkCFL at t = 0")
+        for k in range(3):
+            env.update2(np.array([[0, 0], [0.9, -0.9]], np.float32) if k == 0 else None)
+            for r in refs:
+                r.update2()
+        assert_same(env.check_cfl(), np.array([r.check_cfl() for r in refs], np.float32), "checkCFL after 3 steps")

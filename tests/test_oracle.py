@@ -152,3 +152,33 @@ def test_probes_and_linear(oracle, init_state):
 def test_reward_restatement(oracle):
     r = oracle.reference_reward(1.2, (0.5, -1.0))
     assert abs(r - (-1.2 - np.pi / 8 * 0.0097 * 3.66 ** 3 * (0.125 + 1.0))) < 1e-12
+
+
+def test_adaptive_dt_variant(oracle, init_state):
+    """AFCCylinder.update() (AFCCylinder.pde:63-84): dt = min(u.CFL(nu), 1) before every step (BDIM.pde:217-219,
+    VectorField.pde:225-235).  On the developed wake max(|ux|+|uy|) is about 1.8, so dt is about 0.51 grid units --
+    larger than the fixed 0.18 -- and t advances by dt/resolution."""
+    e = oracle.OracleEnv(literal=False)
+    e.set_state(init_state["ux"], init_state["uy"], init_state["p"])
+    ux, uy = init_state["ux"], init_state["uy"]
+    b = max(np.float32(abs(ux[0, 0]) + abs(uy[0, 0])), (np.abs(ux[1:-1, 1:-1]) + np.abs(uy[1:-1, 1:-1])).max())
+    expect = np.float32(1) / (np.float32(b) + np.float32(3) * np.float32(np.float32(24) / np.float32(500)))
+    assert e.check_cfl() == min(expect, np.float32(1))
+    assert 0.3 < float(e.check_cfl()) < 0.8
+    t0 = e.t
+    e.set_xi(0.3, -0.3)
+    for _ in range(3):
+        dt = e.check_cfl()
+        t_before = e.t
+        e.update_adaptive()
+        assert e.dt == dt and abs((e.t - t_before) - float(dt) / 24) < 1e-6
+        assert np.isfinite(e.force()).all() and e.mg_iters()[0] >= 1
+    assert e.t > t0
+    # a fixed-dt step afterwards is NOT what the adaptive one did (dt really entered the step)
+    f_adaptive = e.force()
+    e2 = oracle.OracleEnv(literal=True)
+    e2.set_state(init_state["ux"], init_state["uy"], init_state["p"])
+    e2.set_xi(0.3, -0.3)
+    for _ in range(3):
+        e2.update2()
+    assert e2.force()[0] != f_adaptive[0]
