@@ -893,7 +893,7 @@ int rlfc_env_reset(rlfc_env* E, const int* env_ids, int n, int reset_accumulator
   if ((rc = broadcast_field(E, E->uAx, E->init_ux, env_ids, n))) return rc;
   if ((rc = broadcast_field(E, E->uAy, E->init_uy, env_ids, n))) return rc;
   if ((rc = broadcast_field(E, sp.lev[0].x, E->init_p, env_ids, n))) return rc;
-  const int one16 = 16;
+  const int one16 = E->cfg.substeps;      // callLearn starts at the sketch's constant (clientCFD.pde:12), here `substeps`
   for (int k = 0; k < n; k++) {
     int e = env_ids ? env_ids[k] : k;
     CU(cudaMemsetAsync(sp.sc.xi + 2 * e, 0, 2 * sizeof(float), E->stream));

@@ -156,6 +156,11 @@ __device__ __forceinline__ void st_block(float* p, const float (&in)[C]) {
   if (C & 1) p[C - 1] = in[C - 1];
 }
 
+// The per-step barrier of the warp-specialised pipeline: every warp arrives from its OWN role loop (different call
+// sites), which is what a NAMED barrier with an explicit thread count is for (bar.sync id, count; __syncthreads in
+// role-divergent code is formally undefined and is what compute-sanitizer's synccheck reports).
+__device__ __forceinline__ void step_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kRowsThreads) : "memory"); }
+
 __device__ __forceinline__ int ring_inc(int s) { return (s + 1 == kRowRing) ? 0 : s + 1; }
 __host__ __device__ constexpr int ring_mod(int row) { return ((row % kRowRing) + kRowRing) % kRowRing; }
 
@@ -230,9 +235,9 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
 
 #ifdef RLFC_ROWS_TIMING        // per-warp busy time between two step barriers (tools: which stage does a step wait for?)
   long long busy_ = 0, tk_ = clock64();
-#define RLFC_STEP_SYNC() do { busy_ += clock64() - tk_; __syncthreads(); tk_ = clock64(); } while (0)
+#define RLFC_STEP_SYNC() do { busy_ += clock64() - tk_; rows_detail::step_barrier(); tk_ = clock64(); } while (0)
 #else
-#define RLFC_STEP_SYNC() __syncthreads()
+#define RLFC_STEP_SYNC() rows_detail::step_barrier()
 #endif
   double rr = 0.0;
   if (warp < 4) {
