@@ -560,6 +560,9 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   if (const char* ev = std::getenv("RLFC_CHAIN_MIN_COLS")) chain_min_cols = std::max(1, std::atoi(ev));
   int chain_wpb = 1;
   if (const char* ev = std::getenv("RLFC_CHAIN_WPB")) chain_wpb = std::min(3, std::max(1, std::atoi(ev)));
+  sp.chain_v = 3;                      // RLFC_CHAIN_V=1: the first generation of the sweep kernel (A/B, cross-check tests)
+  if (const char* ev = std::getenv("RLFC_CHAIN_V")) sp.chain_v = std::atoi(ev) == 1 ? 1 : 3;
+  if (sp.chain_v == 3) chain_wpb = 1;  // (one compute warp + one loader warp per CTA)
   sp.nlevels = (int)g.levels.size();
   sp.resolution = cfg->resolution; sp.substeps = cfg->substeps; sp.mg_max_iters = cfg->mg_max_iters;
   sp.init_time = cfg->init_time; sp.episode_time = cfg->episode_time;
@@ -623,7 +626,8 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
       if (sp.use_rows && !force_wave && l < sp.nlevels - 1 && (force_chain || L.wave || prefer_chain) && sp.chain_levels == l) {
         // chained strip smoother: static coefficient table in the strip-skewed layout (solver.h ChainLevel)
         ChainLevel& ch = L.ch;
-        ch.on = 1; ch.NS = (mj + 31) / 32; ch.T = ni + 34;
+        ch.on = 1; ch.NS = (mj + 31) / 32; ch.T = round_up(ni + 33, 32) + 32;   // (>= ni + 34; whole batches of up to 32 steps stay inside a strip)
+        ch.s0 = 0; ch.ns_loc = ch.NS;
         ch.wpb = std::min(chain_wpb, ch.NS); ch.nb = (ch.NS + ch.wpb - 1) / ch.wpb;
         ch.sk_stride = (size_t)ch.NS * ch.T * 32;
         // (the sweeps form addresses up to kChPFS entries past a strip's end for copies of zero bytes: pad the arrays)
@@ -646,6 +650,9 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
         TRY(upload_vec(E, ct, &ch.ct));
         TRY(E->dmalloc(&ch.rsk, ch.sk_stride * B + pad));
         for (int gsw = 0; gsw < 5; gsw++) TRY(E->dmalloc(&ch.dsk[gsw], ch.sk_stride * B + pad));
+        ch.TE = ch.T + 72;               // smooth_chain3.cuh: consumer steps 0 .. T-1 behind kC2EdgePad, producer indices up to T + 62
+        ch.edge_arr = (size_t)B * ch.NS * ch.TE;
+        TRY(E->dmalloc(&ch.edge, ch.edge_arr * 10 + 64));
         L.wave = 0;
         sp.chain_levels = l + 1;
       }
@@ -819,6 +826,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
       ChainLevel& ch = v.lev[l].ch;
       ch.rsk += (size_t)e0 * ch.sk_stride;
       for (int gsw = 0; gsw < 5; gsw++) ch.dsk[gsw] += (size_t)e0 * ch.sk_stride;
+      ch.edge += (size_t)e0 * ch.NS * ch.TE;
       ch.ticket = E->chain_tickets + (size_t)g * kMaxLevels + l;
       ch.tag_hi = (unsigned)(g + 1) << 26;
     }

@@ -84,6 +84,13 @@ __device__ __forceinline__ size_t ch_index(int T, int i, int j) {
   return ((size_t)s * T + (i + L)) * 32 + L;
 }
 
+constexpr int kC2EdgePad = 32;       // front padding of the edge arrays (smooth_chain3.cuh), entries
+// edge array `which` (0 = S edges: lane 31's results, 1 = N edges: lane 0's results) of sweep g, environment e, strip s;
+// the element a consumer needs at its step t sits at index t + kC2EdgePad
+__device__ __forceinline__ uint2* c2_edge(const ChainLevel& ch, int g, int which, int e, int s) {
+  return ch.edge + (size_t)(2 * g + which) * ch.edge_arr + ((size_t)e * ch.NS + s) * ch.TE;
+}
+
 // ------------------------------------------------------------------------------------------------
 // the four sweeps of one level: grid = B * 4 * nb CTAs of 32*wpb threads
 // ------------------------------------------------------------------------------------------------
@@ -361,7 +368,10 @@ k_chain_up(const __grid_constant__ SolverParams q, int level, const float* __res
       const float rn = ro[a][b] - Ad;
       const size_t o = ch_index(ch.T, i, j);
       rsk[o] = rn;
-      d0[o] = make_uint2(__float_as_uint(rn * L0.inv[k]), 0u);                  // MG.pde:80
+      const uint2 d0v = make_uint2(__float_as_uint(rn * L0.inv[k]), 0u);        // MG.pde:80
+      d0[o] = d0v;
+      // lane-0 columns: the N operand of the previous strip's lane 31 in sweep 1 (consumer step = row + 31)
+      if (((j - 1) & 31) == 0) c2_edge(ch, 0, 1, e, (j - 1) >> 5)[i + 31 + kC2EdgePad] = d0v;
       if (LEVEL0) {
         const int di = (i == 1) ? -1 : (i == n - 2 ? 1 : 0), dj = (j == 1) ? -1 : (j == m - 2 ? 1 : 0);
         if (di) x[IDX(i + di, j)] += dc;

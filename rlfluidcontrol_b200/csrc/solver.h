@@ -51,6 +51,12 @@ struct ChainLevel {
   uint2* dsk[5];            // [B] iterate after sweep g = 0..4 as {value bits, launch tag}         (8 B / element)
   unsigned long long* ticket;   // [1] CTA tickets of this level's sweep launches (role order = start order)
   unsigned tag_hi;          // high bits of the launch tag (unique per ticket counter)
+  // smooth_chain3.cuh: compact copies of every strip's lane-31 (S edge) and lane-0 (N edge) results, indexed by the
+  // CONSUMER's step (+ kC2EdgePad), array (2 g + which) of sweep g at edge + (2 g + which) * edge_arr, [B][NS][TE]
+  uint2* edge;
+  size_t edge_arr;
+  int TE;
+  int s0, ns_loc;           // strips s0 .. s0 + ns_loc - 1 are swept by this device (slab mode; otherwise 0, NS)
 };
 
 struct DevLevel {
@@ -105,6 +111,7 @@ struct SolverParams {
   float mg_tol;
   int   nlevels;
   int   coarse_strips;      // max strip count over levels >= 1 (warps of k_mg_coarse)
+  int   chain_v;            // sweep kernel generation: 1 = smooth_chain.cuh, 3 (default) = smooth_chain3.cuh
   int   chain_levels;       // levels 0 .. chain_levels-1 run as grid-wide kernels with the chained strip smoother; the
                             // one-CTA-per-env coarse kernel starts at level max(chain_levels, 1)
   double *rr_chain;         // [B][rr_chain_n] per-CTA partial sums of r.r of the level-0 chain increment

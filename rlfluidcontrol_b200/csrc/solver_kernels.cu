@@ -975,6 +975,7 @@ k_psum(const __grid_constant__ SolverParams q) {
 
 #include "exact_sum_kernels.cuh"
 #include "smooth_chain.cuh"
+#include "smooth_chain3.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // projection tail (VectorField.pde:136-139): p += -sum/N on all cells; dp = grad p with its setBC
@@ -1341,7 +1342,8 @@ int configure_kernels(const SolverParams& q) {
   if (cudaFuncSetAttribute(k_xsum_chain_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kXsBlocksSmem) != cudaSuccess) return -1;
   cudaError_t e3 = cudaFuncSetAttribute(k_mg_coarse_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coarse_rows_smem(q));
   if (q.chain_levels > 0 &&
-      cudaFuncSetAttribute(k_chain_sweeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kChMaxWpb * sizeof(ChainRing))) != cudaSuccess)
+      (cudaFuncSetAttribute(k_chain_sweeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kChMaxWpb * sizeof(ChainRing))) != cudaSuccess ||
+       cudaFuncSetAttribute(k_chain_sweeps3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Chain3Smem)) != cudaSuccess))
     return -1;
   cudaError_t e4 = cudaSuccess;
   if (!q.lev[0].wave && !q.lev[0].ch.on) switch (q.lev[0].rt.C) {
@@ -1360,7 +1362,8 @@ int configure_kernels(const SolverParams& q) {
 // chained strip smoother (smooth_chain.cuh): the pieces of one level, individually launchable (profiling) ...
 int launch_chain_sweeps(const SolverParams& q, int l, cudaStream_t st) {
   const ChainLevel& ch = q.lev[l].ch;
-  k_chain_sweeps<<<q.B * 4 * ch.nb, 32 * ch.wpb, ch.wpb * sizeof(ChainRing), st>>>(q, l);
+  if (q.chain_v == 1) k_chain_sweeps<<<q.B * 4 * ch.nb, 32 * ch.wpb, ch.wpb * sizeof(ChainRing), st>>>(q, l);
+  else k_chain_sweeps3<<<q.B * 4 * ch.ns_loc, 96, sizeof(Chain3Smem), st>>>(q, l);
   return 1;
 }
 int launch_chain_incr(const SolverParams& q, int l, float* r_out, int which, cudaStream_t st) {

@@ -199,12 +199,13 @@ def test_alternative_execution_paths(rlfc, oracle, init_state, monkeypatch, envv
             assert_same(a, b, nm)
 
 
-@pytest.mark.parametrize("resolution,dims", [(64, (1026, 514)), (128, (2050, 1026))])
-def test_wide_grid(rlfc, oracle, resolution, dims):
+@pytest.mark.parametrize("resolution,dims,chain_v", [(64, (1026, 514), 3), (128, (2050, 1026), 3), (64, (1026, 514), 1)])
+def test_wide_grid(rlfc, oracle, monkeypatch, resolution, dims, chain_v):
     """Single-domain-style grids wider than the row pipeline's 256 columns: BASELINE config 3 (2048x1024, SURVEY 8d:
     resolution 128, t_step = 0.18/128 so dt stays 0.18 grid units) and its half-scale version.  The wide levels fall
     back to the wavefront smoother, setBC to the literal kernels.  Impulsive start, a non-zero action, every float
-    equal to the oracle's."""
+    equal to the oracle's.  chain_v: the two generations of the chained sweep kernel (smooth_chain.cuh, smooth_chain3.cuh)."""
+    monkeypatch.setenv("RLFC_CHAIN_V", str(chain_v))
     kw = dict(resolution=resolution, x_lengths=16, y_lengths=8)
     t_step = np.float32(0.18) / np.float32(resolution)
     ref = oracle.OracleEnv(literal=False, resolution=resolution, xLengths=16, yLengths=8, tStep=float(t_step))
