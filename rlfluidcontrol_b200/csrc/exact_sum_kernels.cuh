@@ -379,18 +379,59 @@ k_xsum_chain(const __grid_constant__ SolverParams q) {
 #undef XS_TICK
 }
 
+// Large domains: blocks of 32 consecutive batch records condensed IN PARALLEL (one warp per block), ahead of the serial
+// pass: a segmented scan of table compositions over the lanes, runs broken at the records that are more than one table.
+// Lane l of block k ends up with the composition of the tables of records (start of its run) .. l; the serial pass
+// (k_xsum_chain_blocks) crosses a whole run with one checked application of the run's last lane.  Output layout
+// xs_blk[e][block][8][32]: words 0..6 the composed table, word 7 the block's mask of one-table records.
+__global__ void __launch_bounds__(32)
+k_xsum_condense(const __grid_constant__ SolverParams q) {
+  const int e = blockIdx.y, bk = blockIdx.x, lane = threadIdx.x;
+  if (q.sc.frozen[e]) return;
+  const int nb = q.xs_nbatches, b0 = bk * 32;
+  const int kend = min(32, nb - b0);
+  const uint32_t* mine = q.xs_recs + ((size_t)e * nb + b0 + lane) * kXsRecWords;
+  const uint32_t ident[7] = {xsum::kAnyKey, 0u, 0u, (uint32_t)INT32_MIN, (uint32_t)INT32_MAX, (uint32_t)INT32_MIN, (uint32_t)INT32_MAX};
+  uint32_t cnt = 0xffffffffu;
+  uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = w0;
+  if (lane < kend) {
+    cnt = mine[0];
+    w0 = *reinterpret_cast<const uint4*>(mine + 8);
+    w1 = *reinterpret_cast<const uint4*>(mine + 12);
+  }
+  const bool pure = cnt == 1u;                                    // the whole batch is one table (no float additions, no serial run)
+  uint32_t acc[7] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z};
+  if (!pure)
+#pragma unroll
+    for (int w = 0; w < 7; w++) acc[w] = ident[w];
+  const uint32_t puremask = __ballot_sync(0xffffffffu, pure);
+  const uint32_t headmask = ~puremask;
+  const uint32_t upto = headmask & ((2u << lane) - 1u);
+  const int dist = upto ? lane - (31 - __clz(upto)) : lane + 1;    // lanes since the last non-table record (itself: 0)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t prev[7];
+#pragma unroll
+    for (int w = 0; w < 7; w++) prev[w] = __shfl_up_sync(0xffffffffu, acc[w], o);
+    if (dist > o && lane >= o) xsum::compose_tables(prev, acc);    // (the partner is inside this lane's run)
+  }
+  uint32_t* out = q.xs_blk + (((size_t)e * gridDim.x + bk) * 8) * 32 + lane;
+#pragma unroll
+  for (int w = 0; w < 7; w++) out[w * 32] = acc[w];
+  out[7 * 32] = puremask;
+}
+
 // Serial pass for LARGE domains (thousands of batches per environment, e.g. 2048 for a 2048 x 1024 grid): there almost
-// every batch record is ONE table (no binade change inside 1024 additions), and tables compose, so the warp first
-// condenses every block of 32 consecutive batch records -- a segmented scan of table compositions over the lanes, runs
-// broken at the records that are more than one table -- and then crosses a whole run with one checked table
-// application.  Records with float additions or serial segments are walked entry by entry as in k_xsum_chain; a run whose
+// every batch record is ONE table (no binade change inside 1024 additions), and tables compose, so every block of 32
+// consecutive batch records is condensed first (k_xsum_condense, in parallel: a segmented scan of table compositions
+// over the lanes, runs broken at the records that are more than one table) and this warp crosses a whole run with one
+// checked table application.  Records with float additions or serial segments are walked entry by entry as in k_xsum_chain; a run whose
 // composed table does not provably apply is walked record by record.  Exactness is unchanged: a table is only applied
 // when its validity condition holds for the true accumulator.
 __global__ void __launch_bounds__(32)
 k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
-  extern __shared__ __align__(16) uint32_t xs_dyn[];               // [2][32][kXsRecWords] record blocks | [32][32] float stage
-  uint32_t (*blk)[32][kXsRecWords] = reinterpret_cast<uint32_t (*)[32][kXsRecWords]>(xs_dyn);
-  float (*stage)[32] = reinterpret_cast<float (*)[32]>(xs_dyn + 2 * 32 * kXsRecWords);
+  extern __shared__ __align__(16) uint32_t xs_dyn[];               // [32][32] float stage
+  float (*stage)[32] = reinterpret_cast<float (*)[32]>(xs_dyn);
   const int e = blockIdx.x, lane = threadIdx.x;
   if (q.sc.frozen[e]) return;
   const unsigned len = (unsigned)(q.m - 2), P = (unsigned)q.P;
@@ -436,7 +477,7 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");          // (also drains the record block in flight: rare path)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     {
       float s = xsum::u2f(bits);
@@ -476,40 +517,23 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
     if (ok) { st_rec++; st_ent += count; }
     else { bits = start; st_redo = st_redo0; redo_batch(b); }
   };
-  // record blocks land in shared memory by cp.async, one block ahead
-  auto fetch = [&](int b0, int buf) {
-    const int n16 = min(32, nb - b0) * (kXsRecWords / 4);
-    if (n16 > 0) {
-      uint32_t* dst = blk[buf][0];
-      const uint32_t* src = recs + (size_t)b0 * kXsRecWords;
-      for (int k = lane; k < n16; k += 32) xs_cp16(dst + 4 * k, src + 4 * k);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  const uint32_t ident[7] = {xsum::kAnyKey, 0u, 0u, (uint32_t)INT32_MIN, (uint32_t)INT32_MAX, (uint32_t)INT32_MIN, (uint32_t)INT32_MAX};
-  fetch(0, 0);
-  for (int b0 = 0, buf = 0; b0 < nb; b0 += 32, buf ^= 1) {
-    __syncwarp();
-    fetch(b0 + 32, buf ^ 1);
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncwarp();
+  const uint32_t* cblk = q.xs_blk + (size_t)e * ((nb + 31) / 32) * 8 * 32;
+  uint32_t nxt[8];
+#pragma unroll
+  for (int w = 0; w < 8; w++) nxt[w] = cblk[w * 32 + lane];
+  // (the records themselves are only read where a run does not apply or a record is more than one table: straight from
+  // global memory, a few dozen per pass)
+  for (int b0 = 0; b0 < nb; b0 += 32) {
     const int kend = min(32, nb - b0);
-    const uint32_t* mine = blk[buf][lane];
-    const uint32_t cnt = lane < kend ? mine[0] : 0xffffffffu;
-    const bool pure = cnt == 1u;                                  // the whole batch is one table (no float additions, no serial run)
+    // this block's condensed tables (k_xsum_condense), fetched one block ahead
     uint32_t acc[7];
 #pragma unroll
-    for (int w = 0; w < 7; w++) acc[w] = pure ? mine[8 + w] : ident[w];
-    const uint32_t puremask = __ballot_sync(0xffffffffu, pure);
-    const uint32_t headmask = ~puremask;
-    const uint32_t upto = headmask & ((2u << lane) - 1u);
-    const int dist = upto ? lane - (31 - __clz(upto)) : lane + 1;  // lanes since the last non-table record (itself: 0)
+    for (int w = 0; w < 7; w++) acc[w] = nxt[w];
+    const uint32_t puremask = nxt[7];
+    if (b0 + 32 < nb) {
+      const uint32_t* src = cblk + ((size_t)(b0 / 32 + 1) * 8) * 32 + lane;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t prev[7];
-#pragma unroll
-      for (int w = 0; w < 7; w++) prev[w] = __shfl_up_sync(0xffffffffu, acc[w], o);
-      if (dist > o && lane >= o) xsum::compose_tables(prev, acc);  // (the partner is inside this lane's run)
+      for (int w = 0; w < 8; w++) nxt[w] = src[w * 32];
     }
     int k = 0;
     XSB_TICK(0);
@@ -525,11 +549,11 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
         const uint32_t nb_bits = xsum::apply_table(bits, tbl[0], (int32_t)tbl[1], (int32_t)tbl[2], (int32_t)tbl[3], (int32_t)tbl[4],
                                                    (int32_t)tbl[5], (int32_t)tbl[6], ok);
         if (ok) { bits = nb_bits; st_rec += run; st_ent++; }
-        else for (int j = 0; j < run; j++) walk_batch(b0 + k + j, blk[buf][k + j]);
+        else for (int j = 0; j < run; j++) walk_batch(b0 + k + j, recs + (size_t)(b0 + k + j) * kXsRecWords);
         k += run;
         XSB_TICK(1);
       } else {
-        walk_batch(b0 + k, blk[buf][k]);
+        walk_batch(b0 + k, recs + (size_t)(b0 + k) * kXsRecWords);
         k++;
         XSB_TICK(2);
       }
@@ -545,4 +569,4 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
   }
 #undef XSB_TICK
 }
-constexpr size_t kXsBlocksSmem = (size_t)(2 * 32 * kXsRecWords + 32 * 32) * 4;
+constexpr size_t kXsBlocksSmem = (size_t)(32 * 32) * 4;

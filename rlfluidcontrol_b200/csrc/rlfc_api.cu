@@ -781,6 +781,8 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
       TRY(E->dmalloc(&sp.xs_rflag, (size_t)sp.xs_nchunks * B));
       TRY(E->dmalloc(&sp.xs_epoch, (size_t)B));
       TRY(E->dmalloc(&sp.xs_recs, (size_t)sp.xs_nbatches * 192 * B));
+      sp.xs_blk = nullptr;
+      if (sp.xs_nbatches >= 256) TRY(E->dmalloc(&sp.xs_blk, (size_t)((sp.xs_nbatches + 31) / 32) * 256 * B));
     }
   }
   TRY(E->dmalloc(&sp.sc.any_active, n_groups));
@@ -842,6 +844,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
       v.xs_ctot += (size_t)e0 * v.xs_nchunks;
       v.xs_cflag += (size_t)e0 * v.xs_nchunks; v.xs_rflag += (size_t)e0 * v.xs_nchunks; v.xs_epoch += e0;
       v.xs_recs += (size_t)e0 * v.xs_nbatches * 192;
+      if (v.xs_blk) v.xs_blk += (size_t)e0 * ((v.xs_nbatches + 31) / 32) * 256;
     }
     v.xs_stats += 8 * e0;
     const size_t o = (size_t)e0 * sp.stride;

@@ -389,6 +389,7 @@ k_chain_up(const __grid_constant__ SolverParams q, int level, const float* __res
 // environment adds the per-CTA partial sums in index order and takes the MGsolver loop decision (MG.pde:32-35).
 // ------------------------------------------------------------------------------------------------
 constexpr int kChIncEntries = 32;
+constexpr int kChIncChunk = 8;
 constexpr int kChIncWarps = 4;
 
 template <bool LEVEL0>
@@ -406,46 +407,67 @@ k_chain_incr(const __grid_constant__ SolverParams q, int level, float* __restric
   const size_t eo = (size_t)e * ch.sk_stride;
   const uint2* __restrict__ d4 = ch.dsk[4] + eo;
   const uint2* dcol = d4 + (size_t)s * T * 32 + lane;
-  float* __restrict__ x = Lv.x + (size_t)e * Lv.stride;
+  float* x = Lv.x + (size_t)e * Lv.stride;
   double rr = 0.0;
   if (t0 <= ni + 31) {
-    const float4* ct = ch.ct + (size_t)s * T * 32 + lane;
-    const float* rsk = ch.rsk + eo + (size_t)s * T * 32 + lane;
+    const float4* __restrict__ ct = ch.ct + (size_t)s * T * 32 + lane;
+    const float* __restrict__ rsk = ch.rsk + eo + (size_t)s * T * 32 + lane;
     float* __restrict__ r_out = LEVEL0 ? r_out_all + (size_t)e * Lv.stride : nullptr;
     float dW = __uint_as_float(dcol[(size_t)(t0 - 1) * 32].x), dC = __uint_as_float(dcol[(size_t)t0 * 32].x);
     float cxW = LEVEL0 ? ct[(size_t)(t0 - 1) * 32].x : 0.f;
     const int t1 = min(t0 + kChIncEntries - 1, ni + 31);
-    for (int t = t0; t <= t1; t++) {
-      const int i = t - lane;
-      const bool ok = i >= 1 && i <= ni && j <= mj;
-      const float dE = __uint_as_float(dcol[(size_t)(t + 1) * 32].x);
-      if (LEVEL0) {
-        const float4 c = ct[(size_t)t * 32];
-        // S = (i, j-1): lane L-1 of entry t-1 = what that lane holds as dW; N = (i, j+1): lane L+1 of entry t+1 = its dE
-        float dS = __shfl_up_sync(0xffffffffu, dW, 1), dN = __shfl_down_sync(0xffffffffu, dE, 1);
-        if (lane == 0 && s > 0 && ok) dS = __uint_as_float(d4[((size_t)(s - 1) * T + t + 31) * 32 + 31].x);
-        if (lane == 31 && s + 1 < NS && ok) dN = __uint_as_float(d4[((size_t)(s + 1) * T + t - 31) * 32].x);
-        if (ok) {
-          const float w_ = (i == 1) ? dC : dW, e_ = (i == ni) ? dC : dE;          // d.setBC: ghost = adjacent interior
-          const float s_ = (j == 1) ? dC : dS, n_ = (j == mj) ? dC : dN;
-          const float dg = -(cxW + c.x + c.y + c.z);                              // PoissonMatrix.pde:46-48
-          const float Ad = dC * dg + w_ * cxW + e_ * c.x + s_ * c.y + n_ * c.z;   // PoissonMatrix.pde:56-61
-          const float rN = rsk[(size_t)t * 32] - Ad;
-          const int k = IDX(i, j);
-          r_out[k] = rN;
-          const float prod = rN * rN;                    // float product, double accumulation (Field.pde:304-307)
-          rr += (double)prod;
-          x[k] += dC;
-          const int di = (i == 1) ? -1 : (i == ni ? 1 : 0), dj = (j == 1) ? -1 : (j == mj ? 1 : 0);
-          if (di) x[IDX(i + di, j)] += dC;
-          if (dj) x[IDX(i, j + dj)] += dC;
-          if (di && dj) x[IDX(i + di, j + dj)] += dC;
+    // chunks of kChIncChunk entries: every load of a chunk is issued before its first store (the read-modify-write of x
+    // would otherwise serialise the loop on one memory round trip per entry)
+    for (int tb = t0; tb <= t1; tb += kChIncChunk) {
+      float dEv[kChIncChunk], xv[kChIncChunk], rsv[kChIncChunk], dSx[kChIncChunk], dNx[kChIncChunk];
+      float4 cv[kChIncChunk];
+#pragma unroll
+      for (int k = 0; k < kChIncChunk; k++) {
+        const int t = tb + k, i = t - lane;
+        const bool in = t <= t1, ok = in && i >= 1 && i <= ni && j <= mj;
+        dEv[k] = in ? __uint_as_float(dcol[(size_t)(t + 1) * 32].x) : 0.f;
+        xv[k] = ok ? x[IDX(i, j)] : 0.f;
+        if (LEVEL0) {
+          cv[k] = in ? ct[(size_t)t * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+          rsv[k] = ok ? rsk[(size_t)t * 32] : 0.f;
+          dSx[k] = (lane == 0 && s > 0 && ok) ? __uint_as_float(d4[((size_t)(s - 1) * T + t + 31) * 32 + 31].x) : 0.f;
+          dNx[k] = (lane == 31 && s + 1 < NS && ok) ? __uint_as_float(d4[((size_t)(s + 1) * T + t - 31) * 32].x) : 0.f;
         }
-        cxW = c.x;
-      } else if (ok) {
-        x[IDX(i, j)] += dC;                              // x.plusEq(d), MG.pde:95
       }
-      dW = dC; dC = dE;
+#pragma unroll
+      for (int k = 0; k < kChIncChunk; k++) {
+        const int t = tb + k, i = t - lane;
+        if (t > t1) break;
+        const bool ok = i >= 1 && i <= ni && j <= mj;
+        const float dE = dEv[k];
+        if (LEVEL0) {
+          const float4 c = cv[k];
+          // S = (i, j-1): lane L-1 of entry t-1 = what that lane holds as dW; N = (i, j+1): lane L+1 of entry t+1 = its dE
+          float dS = __shfl_up_sync(0xffffffffu, dW, 1), dN = __shfl_down_sync(0xffffffffu, dE, 1);
+          if (lane == 0 && s > 0 && ok) dS = dSx[k];
+          if (lane == 31 && s + 1 < NS && ok) dN = dNx[k];
+          if (ok) {
+            const float w_ = (i == 1) ? dC : dW, e_ = (i == ni) ? dC : dE;          // d.setBC: ghost = adjacent interior
+            const float s_ = (j == 1) ? dC : dS, n_ = (j == mj) ? dC : dN;
+            const float dg = -(cxW + c.x + c.y + c.z);                              // PoissonMatrix.pde:46-48
+            const float Ad = dC * dg + w_ * cxW + e_ * c.x + s_ * c.y + n_ * c.z;   // PoissonMatrix.pde:56-61
+            const float rN = rsv[k] - Ad;
+            const int kk = IDX(i, j);
+            r_out[kk] = rN;
+            const float prod = rN * rN;                  // float product, double accumulation (Field.pde:304-307)
+            rr += (double)prod;
+            x[kk] = xv[k] + dC;
+            const int di = (i == 1) ? -1 : (i == ni ? 1 : 0), dj = (j == 1) ? -1 : (j == mj ? 1 : 0);
+            if (di) x[IDX(i + di, j)] += dC;
+            if (dj) x[IDX(i, j + dj)] += dC;
+            if (di && dj) x[IDX(i + di, j + dj)] += dC;
+          }
+          cxW = c.x;
+        } else if (ok) {
+          x[IDX(i, j)] = xv[k] + dC;                     // x.plusEq(d), MG.pde:95
+        }
+        dW = dC; dC = dE;
+      }
     }
   }
   if (LEVEL0) {

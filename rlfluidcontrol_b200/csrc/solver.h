@@ -139,6 +139,7 @@ struct SolverParams {
   unsigned *xs_rflag;       // [B][xs_nchunks] == xs_epoch + 1 once the chunk's batch records are written
   unsigned *xs_epoch;       // [B] passes completed
   unsigned *xs_recs;        // [B][xs_nbatches][192] batch records (32 summaries condensed)
+  unsigned *xs_blk;         // [B][ceil(xs_nbatches/32)][8][32] blocks of 32 records condensed (large domains; else nullptr)
   int xs_nseg, xs_nchunks, xs_nbatches;
   int *xs_stats;            // [B][8] counters of the last serial pass (rlfc_env_field_sum_stats)
   EnvScalars sc;

@@ -1463,8 +1463,12 @@ int launch_psum_tables(const SolverParams& q, cudaStream_t st) {
   return 1;
 }
 int launch_psum_pass(const SolverParams& q, cudaStream_t st) {
-  if (q.xs_nbatches >= 256) k_xsum_chain_blocks<<<q.B, 32, kXsBlocksSmem, st>>>(q);   // large domains: runs of records condensed first
-  else k_xsum_chain<false><<<q.B, 32, 0, st>>>(q);
+  if (q.xs_blk) {                       // large domains: runs of records condensed first (in parallel), then crossed
+    k_xsum_condense<<<dim3((q.xs_nbatches + 31) / 32, q.B), 32, 0, st>>>(q);
+    k_xsum_chain_blocks<<<q.B, 32, kXsBlocksSmem, st>>>(q);
+    return 2;
+  }
+  k_xsum_chain<false><<<q.B, 32, 0, st>>>(q);
   return 1;
 }
 int launch_psum(const SolverParams& q, cudaStream_t st) {
