@@ -69,6 +69,12 @@ typedef struct {
                                  checkpoint (BDIM.write format) or a .bdimb binary one */
   void *stream;         /* cudaStream_t to run on; NULL = the library creates its own */
   int   n_groups;       /* env groups advanced concurrently on separate streams; 0 = auto    */
+  int   n_devices;      /* 1 (default) = the handle lives on `device`.  > 1 = SLAB MODE (n_envs must be 1): ONE domain
+                           advanced by devices device .. device + n_devices - 1 of this process, which share every
+                           field through one address range (CUDA virtual memory management + peer access over
+                           NVLink): rows / strips are distributed, halo operands are ordinary peer loads, the
+                           lexicographic Gauss-Seidel sweeps cross devices strip to strip, results are bit-identical
+                           to the single-device run (BASELINE config 5)                         */
 } rlfc_config;
 
 void rlfc_default_config(rlfc_config *cfg);

@@ -16,6 +16,7 @@
 #include "geometry.h"
 #include "solver.h"
 #include "smooth_rows.cuh"
+#include "vmm.h"
 
 using namespace rlfc;
 
@@ -74,6 +75,20 @@ struct rlfc_env {
   };
   std::vector<Group> groups;
   Group whole;                               // the entire batch on the handle's stream (eager / profiled path)
+  // Slab mode (cfg.n_devices > 1, BASELINE config 5): one domain advanced by several devices over one shared address
+  // range (vmm.h); every device runs the same kernel sequence on its row blocks / strips, a barrier between kernels
+  struct SlabDev {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    SolverParams sp{}, spB{};                // this device's view (slab_rank, its strips, its ticket counters); B: lev[0].x = pressure buffer B
+    SlabBarrier bar{};
+    void* local[2] = {nullptr, nullptr};     // cudaMalloc'd on this device: ticket counters, barrier epoch
+  };
+  std::vector<SlabDev> slab;
+  SolverParams solo{}, soloB{};              // the whole domain as ONE device sees it (kernels that run on device 0 only)
+  VmmPool vmm;
+  bool home_only = false;                    // dmalloc: keep the next allocations on device 0 (data only it touches)
+  long long slab_barriers = 0;
   cudaStream_t aux_stream = nullptr;         // used to capture the bodies of the conditional nodes
   cudaEvent_t fork_ev = nullptr;
   cudaStream_t psum_stream = nullptr;        // side branch of the step graphs: Field.sum's serial pass (launch_psum_overlapped)
@@ -140,9 +155,16 @@ struct rlfc_env {
   template <typename T>
   int dmalloc(T** p, size_t count, bool zero = true) {
     void* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
-    if (e != cudaSuccess) return fail(RLFC_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-    allocs.push_back(q);
+    cudaError_t e;
+    if (cfg.n_devices > 1) {                 // slab mode: visible to every device at this address, striped over them
+      std::string err;
+      int rc = vmm.alloc(&q, std::max<size_t>(count, 1) * sizeof(T), !home_only, 0, err);
+      if (rc) return fail(rc, err);
+    } else {
+      e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+      if (e != cudaSuccess) return fail(RLFC_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+      allocs.push_back(q);
+    }
     if (zero) {
       e = cudaMemsetAsync(q, 0, std::max<size_t>(count, 1) * sizeof(T), stream);
       if (e != cudaSuccess) return fail(RLFC_ECUDA, std::string("cudaMemset: ") + cudaGetErrorString(e));
@@ -399,9 +421,128 @@ int join_groups(rlfc_env* E) {
   return RLFC_OK;
 }
 
+// ---- slab mode: one solver step (AFCCylinder.update2) of ONE domain on several devices, eager launches ----
+// Grid-wide kernels are launched with their full grid on every device (blocks of other devices' rows / strips exit at
+// once); kernels that are one CTA per environment (setBC, the coarsest levels, Field.sum, the force read-out) run on
+// device 0; a barrier separates dependent kernels.  Halo operands and the few remote results travel as ordinary
+// loads and stores through the shared address range; the Gauss-Seidel sweeps cross device boundaries strip to strip
+// through the tagged edge arrays (smooth_chain3.cuh).
+using SlabDev = rlfc_env::SlabDev;
+
+template <typename F>
+void slab_all(rlfc_env* E, const char* name, double fpc, F&& launch) {
+  for (size_t d = 0; d < E->slab.size(); d++) {
+    SlabDev& D = E->slab[d];
+    cudaSetDevice(D.device);
+    if (d == 0) E->run(name, fpc, [&] { return launch(D); }, D.st, 0);
+    else E->launches += launch(D);
+  }
+}
+template <typename F>
+void slab_first(rlfc_env* E, const char* name, double fpc, F&& launch) {
+  SlabDev& D = E->slab[0];
+  cudaSetDevice(D.device);
+  E->run(name, fpc, [&] { return launch(D); }, D.st, 0);
+}
+void slab_barrier(rlfc_env* E) {
+  slab_all(E, "k_slab_barrier", 0, [&](SlabDev& D) { return launch_slab_barrier(D.bar, D.st); });
+  E->slab_barriers++;
+}
+
+int slab_project(rlfc_env* E, float* Ux, float* Uy, int which) {
+  const SolverParams& s0 = E->slab[0].sp;
+  float* r = s0.lev[0].r;
+  float* rs = s0.lev[0].d;
+  float* pA = s0.lev[0].x;
+  float* pB = E->slab[0].spB.lev[0].x;
+  const int first = std::max(1, s0.chain_levels);
+  static const char* nm[4][4] = {{"k_chain_down_L1", "k_chain_up_L1", "k_chain_sweeps_L1", "k_chain_incr_L1"},
+                                 {"k_chain_down_L2", "k_chain_up_L2", "k_chain_sweeps_L2", "k_chain_incr_L2"},
+                                 {"k_chain_down_L3", "k_chain_up_L3", "k_chain_sweeps_L3", "k_chain_incr_L3"},
+                                 {"k_chain_down_L4+", "k_chain_up_L4+", "k_chain_sweeps_L4+", "k_chain_incr_L4+"}};
+  for (int it = 0; it < s0.mg_max_iters; it++) {
+    cudaSetDevice(E->slab[0].device);
+    CU(cudaMemsetAsync(s0.sc.any_active, 0, sizeof(int), E->slab[0].st));
+    if (it == 0) slab_all(E, "k_resid_down0", 5.25, [&](SlabDev& D) { return launch_resid_down0(D.sp, Ux, Uy, pA, pB, rs, which, D.st); });
+    else slab_all(E, "k_mg_down0", 4.25, [&](SlabDev& D) { return launch_mg_down0(D.spB, r, rs, D.st); });
+    slab_barrier(E);
+    for (int l = 1; l < first; l++) {
+      slab_all(E, nm[std::min(l, 4) - 1][0], 0, [&](SlabDev& D) { return launch_chain_down(D.spB, l, D.st); });
+      slab_barrier(E);
+    }
+    slab_first(E, "k_mg_coarse_cta", 0.5, [&](SlabDev& D) { return launch_coarse_cta(E->soloB, D.st); });
+    slab_barrier(E);
+    for (int l = first - 1; l >= 0; l--) {
+      const int k = std::min(std::max(l, 1), 4) - 1;
+      slab_all(E, l ? nm[k][1] : "k_chain_up_L0", l ? 0 : 4.25, [&](SlabDev& D) { return launch_chain_up(D.spB, l, l ? nullptr : rs, D.st); });
+      slab_barrier(E);
+      slab_all(E, l ? nm[k][2] : "k_chain_sweeps_L0", l ? 0 : 3, [&](SlabDev& D) { return launch_chain_sweeps(D.spB, l, D.st); });
+      slab_barrier(E);
+      slab_all(E, l ? nm[k][3] : "k_chain_incr_L0", l ? 0 : 4, [&](SlabDev& D) { return launch_chain_incr(D.spB, l, l ? nullptr : r, l ? 0 : which, D.st); });
+      slab_barrier(E);
+    }
+    E->mg_iter_launch_rounds++;
+    cudaSetDevice(E->slab[0].device);
+    CU(cudaMemcpyAsync(E->h_any, s0.sc.any_active, sizeof(int), cudaMemcpyDeviceToHost, E->slab[0].st));
+    CU(cudaStreamSynchronize(E->slab[0].st));
+    if (!*E->h_any) break;
+  }
+  // projection tail: Field.sum on device 0 (a serial float chain over the whole field), then the grid-wide correction
+  if (E->soloB.xs_recs) {
+    slab_first(E, "k_xsum_tables", 1, [&](SlabDev& D) { return launch_psum_tables(E->soloB, D.st); });
+    slab_first(E, "k_xsum_pass", 0, [&](SlabDev& D) { return launch_psum_pass(E->soloB, D.st); });
+  } else {
+    slab_first(E, "k_psum", 1, [&](SlabDev& D) { return launch_psum(E->soloB, D.st); });
+  }
+  slab_barrier(E);
+  if (which == 1 && s0.fast_bc) {
+    Group& G = E->whole;
+    slab_all(E, "k_project_shift_heun", 8, [&](SlabDev& D) { return launch_project_shift_heun(D.sp, pB, pA, Ux, Uy, G.uBx, G.uBy, G.uAx, G.uAy, D.st); });
+    slab_barrier(E);
+    slab_first(E, "k_bc_heun", 0, [&](SlabDev& D) { return launch_bc_heun(E->solo, Ux, Uy, G.uBx, G.uBy, G.uAx, G.uAy, D.st); });
+    slab_barrier(E);
+    return RLFC_OK;
+  }
+  slab_all(E, "k_project_shift", 6, [&](SlabDev& D) { return launch_project_shift(D.sp, pB, pA, Ux, Uy, D.st); });
+  slab_barrier(E);
+  slab_first(E, "k_bc", 0, [&](SlabDev& D) { return launch_bc(E->solo, Ux, Uy, D.st); });
+  slab_barrier(E);
+  return RLFC_OK;
+}
+
+int slab_step(rlfc_env* E, int accumulate) {
+  Group& G = E->whole;
+  int rc;
+  slab_barrier(E);   // (whatever device 0 enqueued since the last step -- actions, resets, field uploads -- is visible to all)
+  slab_all(E, "k_advdif", 5, [&](SlabDev& D) { return launch_advdif(D.sp, G.uAx, G.uAy, G.uAx, G.uAy, G.uBx, G.uBy, D.st); });
+  slab_barrier(E);
+  slab_first(E, "k_band_bc", 0, [&](SlabDev& D) { return launch_band_bc(E->solo, G.uBx, G.uBy, D.st); });
+  slab_barrier(E);
+  if ((rc = slab_project(E, G.uBx, G.uBy, 0))) return rc;
+  slab_all(E, "k_advdif", 5, [&](SlabDev& D) { return launch_advdif(D.sp, G.uBx, G.uBy, G.uAx, G.uAy, G.uCx, G.uCy, D.st); });
+  slab_barrier(E);
+  slab_first(E, "k_band_bc", 0, [&](SlabDev& D) { return launch_band_bc(E->solo, G.uCx, G.uCy, D.st); });
+  slab_barrier(E);
+  if ((rc = slab_project(E, G.uCx, G.uCy, 1))) return rc;
+  if (!E->slab[0].sp.fast_bc) {
+    slab_all(E, "k_heun", 6, [&](SlabDev& D) { return launch_heun(D.sp, G.uCx, G.uCy, G.uBx, G.uBy, G.uAx, G.uAy, D.st); });
+    slab_barrier(E);
+  }
+  slab_first(E, "k_force", 0, [&](SlabDev& D) { return launch_force(E->solo, accumulate, D.st); });
+  slab_barrier(E);
+  cudaSetDevice(E->slab[0].device);
+  CU(cudaGetLastError());
+  return RLFC_OK;
+}
+
 // `nsteps` solver steps (AFCCylinder.update2) for the whole batch
 int solver_steps(rlfc_env* E, int nsteps, int accumulate) {
   int rc;
+  if (!E->slab.empty()) {
+    for (int s = 0; s < nsteps; s++)
+      if ((rc = slab_step(E, accumulate))) return rc;
+    return RLFC_OK;
+  }
   const bool graph = E->use_graph && !E->profiling;
   if (!graph && !(E->fixed_iters > 0 && E->eager_groups)) {
     for (int s = 0; s < nsteps; s++)
@@ -465,7 +606,7 @@ void rlfc_default_config(rlfc_config* c) {
   c->dR = .125f; c->gR = .2f; c->theta = 3.1415927f / 3; c->t_step = .0075f;   // clientCFD.pde:9,95-96
   c->action_scale = 5.f;                                                       // clientCFD.pde:53-54
   c->substeps = 16; c->init_time = 1.f; c->episode_time = 50.f;                // clientCFD.pde:5-6,12
-  c->n_envs = 1; c->device = -1; c->exact = 1; c->mg_max_iters = 20; c->n_groups = 0;
+  c->n_envs = 1; c->device = -1; c->exact = 1; c->mg_max_iters = 20; c->n_groups = 0; c->n_devices = 1;
   c->init_bdim_path = nullptr; c->stream = nullptr;
 }
 
@@ -484,6 +625,14 @@ void rlfc_env_destroy(rlfc_env* E) {
     if (G.done) cudaEventDestroy(G.done);
     if (g > 0 && G.st) { cudaStreamSynchronize(G.st); cudaStreamDestroy(G.st); }
   }
+  for (size_t d = 0; d < E->slab.size(); d++) {
+    auto& D = E->slab[d];
+    cudaSetDevice(D.device);
+    if (D.st) cudaStreamSynchronize(D.st);
+    if (d > 0 && D.st) cudaStreamDestroy(D.st);
+    for (void* q : D.local) if (q) cudaFree(q);
+  }
+  cudaSetDevice(E->device);
   if (E->aux_stream) cudaStreamDestroy(E->aux_stream);
   if (E->psum_stream) cudaStreamDestroy(E->psum_stream);
   if (E->psum_fork) cudaEventDestroy(E->psum_fork);
@@ -523,6 +672,19 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     return fail(RLFC_ENODEV, "cudaGetDevice failed");
   }
   if (cudaSetDevice(E->device) != cudaSuccess) { delete E; return fail(RLFC_ENODEV, "cudaSetDevice failed"); }
+  if (E->cfg.n_devices < 1) E->cfg.n_devices = 1;
+  if (E->cfg.n_devices > 1) {
+    // slab mode: ONE domain on devices device .. device + n_devices - 1 (BASELINE config 5)
+    if (cfg->n_envs != 1) { delete E; return fail(RLFC_EINVAL, "slab mode (n_devices > 1) advances one environment"); }
+    if (E->device + E->cfg.n_devices > ndev) { delete E; return fail(RLFC_ENODEV, "n_devices exceeds the devices present"); }
+    if (cfg->stream) { delete E; return fail(RLFC_EINVAL, "slab mode creates its own streams"); }
+    std::vector<int> devs;
+    for (int d = 0; d < E->cfg.n_devices; d++) devs.push_back(E->device + d);
+    std::string err;
+    int vrc = E->vmm.init(devs, err);
+    if (vrc) { delete E; return fail(vrc, err); }
+    cudaSetDevice(E->device);
+  }
   if (cfg->stream) {
     E->stream = (cudaStream_t)cfg->stream;
   } else {
@@ -556,12 +718,14 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   // RLFC_SMOOTHER=chain: the chained strip smoother (smooth_chain.cuh) on every level but the coarsest (tests); by default it
   // takes the levels that are too wide for the row pipeline
   const bool force_chain = std::getenv("RLFC_SMOOTHER") && std::string(std::getenv("RLFC_SMOOTHER")) == "chain";
+  const bool slab = E->cfg.n_devices > 1;   // slab mode: level 0 always runs the chained smoother (its sweeps span devices)
   int chain_min_cols = 32;            // RLFC_CHAIN_MIN_COLS: coarse levels at least this wide follow a chained level 0
   if (const char* ev = std::getenv("RLFC_CHAIN_MIN_COLS")) chain_min_cols = std::max(1, std::atoi(ev));
   int chain_wpb = 1;
   if (const char* ev = std::getenv("RLFC_CHAIN_WPB")) chain_wpb = std::min(3, std::max(1, std::atoi(ev)));
   sp.chain_v = 3;                      // RLFC_CHAIN_V=1: the first generation of the sweep kernel (A/B, cross-check tests)
   if (const char* ev = std::getenv("RLFC_CHAIN_V")) sp.chain_v = std::atoi(ev) == 1 ? 1 : 3;
+  if (slab) sp.chain_v = 3;
   if (sp.chain_v == 3) chain_wpb = 1;  // (one compute warp + one loader warp per CTA)
   sp.nlevels = (int)g.levels.size();
   sp.resolution = cfg->resolution; sp.substeps = cfg->substeps; sp.mg_max_iters = cfg->mg_max_iters;
@@ -623,7 +787,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
       L.ch = ChainLevel{};
       // levels the row pipeline could take, but which are faster chained when one domain has the GPU to itself
       const bool prefer_chain = sp.chain_levels > 0 && l >= 1 && mj >= chain_min_cols;
-      if (sp.use_rows && !force_wave && l < sp.nlevels - 1 && (force_chain || L.wave || prefer_chain) && sp.chain_levels == l) {
+      if (sp.use_rows && !force_wave && l < sp.nlevels - 1 && (force_chain || L.wave || prefer_chain || (slab && l == 0)) && sp.chain_levels == l) {
         // chained strip smoother: static coefficient table in the strip-skewed layout (solver.h ChainLevel)
         ChainLevel& ch = L.ch;
         ch.on = 1; ch.NS = (mj + 31) / 32; ch.T = round_up(ni + 33, 32) + 32;   // (>= ni + 34; whole batches of up to 32 steps stay inside a strip)
@@ -746,6 +910,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   if (const char* ev = std::getenv("RLFC_GROUPS")) n_groups = std::atoi(ev);
   if (n_groups <= 0) n_groups = B >= 128 ? 4 : (B >= 32 ? 2 : 1);
   n_groups = std::min(n_groups, B);
+  if (slab) n_groups = 1;
   if (const char* ev = std::getenv("RLFC_NO_GRAPH")) E->use_graph = std::atoi(ev) == 0;
   if (const char* ev = std::getenv("RLFC_FIXED_ITERS")) E->fixed_iters = std::atoi(ev);
   if (const char* ev = std::getenv("RLFC_EAGER_GROUPS")) E->eager_groups = std::atoi(ev) != 0;
@@ -772,7 +937,8 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     sp.xs_nbatches = (sp.xs_nseg + 31) / 32;
     sp.xs_ctot = nullptr; sp.xs_recs = nullptr;
     TRY(E->dmalloc(&sp.xs_stats, (size_t)8 * B));
-    bool summaries = N * B <= 24000000ll;
+    bool summaries = N * B <= 24000000ll || slab;   // (one large domain: the plain chain would be tens of milliseconds)
+    E->home_only = true;                            // Field.sum runs on device 0 only
     if (ev && std::strcmp(ev, "serial") == 0) summaries = false;
     if (ev && std::strcmp(ev, "parallel") == 0) summaries = true;
     if (summaries) {
@@ -784,6 +950,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
       sp.xs_blk = nullptr;
       if (sp.xs_nbatches >= 256) TRY(E->dmalloc(&sp.xs_blk, (size_t)((sp.xs_nbatches + 31) / 32) * 256 * B));
     }
+    E->home_only = false;
   }
   TRY(E->dmalloc(&sp.sc.any_active, n_groups));
   if (sp.chain_levels > 0) {
@@ -877,6 +1044,51 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   E->whole.spB = E->whole.sp; E->whole.spB.lev[0].x = E->pB;
   E->whole.uAx = E->uAx; E->whole.uAy = E->uAy; E->whole.uBx = E->uBx; E->whole.uBy = E->uBy;
   E->whole.uCx = E->uCx; E->whole.uCy = E->uCy;
+  if (slab) {
+    // per-device views: the same arrays (one address range), each device its row blocks / strips, its own streams,
+    // ticket counters and barrier epoch in its own memory
+    if (!sp.lev[0].ch.on) return bail(fail(RLFC_EGRID, "slab mode needs the chained smoother on level 0"));
+    const int nd = E->cfg.n_devices;
+    unsigned* bar_count = nullptr;
+    E->home_only = true;
+    if ((rc = E->dmalloc(&bar_count, 1))) return bail(rc);
+    E->home_only = false;
+    if (cudaStreamSynchronize(E->stream) != cudaSuccess) return bail(fail(RLFC_ECUDA, "initialisation failed"));
+    E->solo = E->whole.sp; E->soloB = E->whole.spB;
+    E->slab.resize(nd);
+    for (int d = 0; d < nd; d++) {
+      rlfc_env::SlabDev& D = E->slab[d];
+      D.device = E->device + d;
+      if (cudaSetDevice(D.device) != cudaSuccess) return bail(fail(RLFC_ENODEV, "cudaSetDevice failed"));
+      if (d == 0) D.st = E->stream;
+      else if (cudaStreamCreateWithFlags(&D.st, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(RLFC_ECUDA, "cudaStreamCreate failed"));
+      if (d > 0 && configure_kernels(sp)) return bail(fail(RLFC_ECUDA, "kernel attribute configuration failed"));
+      unsigned long long* tickets = nullptr;
+      unsigned* epoch = nullptr;
+      if (cudaMalloc(&tickets, sizeof(unsigned long long) * kMaxLevels) != cudaSuccess || cudaMalloc(&epoch, sizeof(unsigned)) != cudaSuccess)
+        return bail(fail(RLFC_ENOMEM, "cudaMalloc failed"));
+      D.local[0] = tickets; D.local[1] = epoch;
+      D.sp = E->whole.sp;
+      D.sp.slab_n = nd; D.sp.slab_rank = d;
+      std::vector<unsigned long long> init(kMaxLevels, 0ull);
+      for (int l = 0; l < sp.chain_levels; l++) {
+        ChainLevel& ch = D.sp.lev[l].ch;
+        ch.s0 = (int)((long long)ch.NS * d / nd);
+        ch.ns_loc = (int)((long long)ch.NS * (d + 1) / nd) - ch.s0;
+        ch.wpb = 1; ch.nb = ch.ns_loc;
+        ch.ticket = tickets + l;
+        ch.tag_hi = 1u << 26;                                  // the same launch tags on every device
+        init[l] = (unsigned long long)B * 4ull * (unsigned)std::max(ch.ns_loc, 1);
+      }
+      if (cudaMemcpy(tickets, init.data(), sizeof(unsigned long long) * kMaxLevels, cudaMemcpyHostToDevice) != cudaSuccess ||
+          cudaMemset(epoch, 0, sizeof(unsigned)) != cudaSuccess)
+        return bail(fail(RLFC_ECUDA, "slab initialisation failed"));
+      D.spB = D.sp;
+      D.spB.lev[0].x = E->pB;
+      D.bar.count = bar_count; D.bar.epoch = epoch; D.bar.n = (unsigned)nd;
+    }
+    cudaSetDevice(E->device);
+  }
   if (const char* ev = std::getenv("RLFC_PSUM_OVERLAP")) E->psum_overlap = std::atoi(ev) != 0;
   if (cudaStreamCreateWithFlags(&E->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&E->psum_stream, cudaStreamNonBlocking) != cudaSuccess ||

@@ -313,7 +313,7 @@ k_chain_sweeps(const __grid_constant__ SolverParams q, int level) {
 __global__ void __launch_bounds__(256)
 k_chain_down(const __grid_constant__ SolverParams q, int level) {
   const int e = blockIdx.z;
-  if (!q.sc.active[e]) return;
+  if (!q.sc.active[e] || slab_skip(blockIdx.y, gridDim.y, q.slab_rank, q.slab_n)) return;
   const DevLevel& L = q.lev[level];
   const DevLevel& C = q.lev[level + 1];
   const int J = blockIdx.x * blockDim.x + threadIdx.x + 1;
@@ -333,7 +333,7 @@ template <bool LEVEL0>
 __global__ void __launch_bounds__(256)
 k_chain_up(const __grid_constant__ SolverParams q, int level, const float* __restrict__ r_all) {
   const int e = blockIdx.z;
-  if (!q.sc.active[e]) return;
+  if (!q.sc.active[e] || slab_skip(blockIdx.y, gridDim.y, q.slab_rank, q.slab_n)) return;
   const DevLevel& L0 = q.lev[level];
   const DevLevel& L1 = q.lev[level + 1];
   const ChainLevel& ch = L0.ch;
@@ -402,6 +402,7 @@ k_chain_incr(const __grid_constant__ SolverParams q, int level, float* __restric
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = Lv.n, m = Lv.m, P = Lv.P, ni = n - 2, mj = m - 2, T = ch.T, NS = ch.NS;
   const int s = blockIdx.y;
+  if (q.slab_n > 1 && (s < ch.s0 || s >= ch.s0 + ch.ns_loc)) return;          // slab mode: the strips this device sweeps
   const int t0 = (blockIdx.x * kChIncWarps + warp) * kChIncEntries + 1;        // first entry of this warp's run
   const int j = 32 * s + lane + 1;
   const size_t eo = (size_t)e * ch.sk_stride;
@@ -483,12 +484,13 @@ k_chain_incr(const __grid_constant__ SolverParams q, int level, float* __restric
       double sblk = 0;
       for (int w = 0; w < kChIncWarps; w++) sblk += wsum[w];
       q.rr_chain[(size_t)e * q.rr_chain_n + blk] = sblk;
-      __threadfence();
-      s_last = atomicAdd(q.rr_count + e, 1u) == (unsigned)nblk - 1u;
+      // (slab mode: the blocks of one environment run on several devices)
+      if (q.slab_n > 1) { __threadfence_system(); s_last = atomicAdd_system(q.rr_count + e, 1u) == (unsigned)nblk - 1u; }
+      else { __threadfence(); s_last = atomicAdd(q.rr_count + e, 1u) == (unsigned)nblk - 1u; }
     }
     __syncthreads();
     if (s_last) {
-      __threadfence();
+      if (q.slab_n > 1) __threadfence_system(); else __threadfence();
       const volatile double* part = q.rr_chain + (size_t)e * q.rr_chain_n;
       double acc = 0;
       for (int k = threadIdx.x; k < nblk; k += blockDim.x) acc += part[k];   // fixed assignment of partial sums to threads
@@ -502,7 +504,7 @@ k_chain_incr(const __grid_constant__ SolverParams q, int level, float* __restric
         q.rr_count[e] = 0u;
         const int it = ++q.sc.iters[2 * e + which];
         if ((float)sum < q.mg_tol || it >= q.mg_max_iters) q.sc.active[e] = 0;
-        else atomicExch(q.sc.any_active, 1);
+        else if (q.slab_n > 1) atomicExch_system(q.sc.any_active, 1); else atomicExch(q.sc.any_active, 1);
       }
     }
   }

@@ -60,15 +60,17 @@ __device__ __forceinline__ float4 c3_lds128v(unsigned a) {
   asm volatile("ld.volatile.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
   return v;
 }
-#ifndef RLFC_C3_SCOPE
-#define RLFC_C3_SCOPE "relaxed.gpu"
-#endif
+// {value, tag} hand-offs: device scope on one GPU; system scope when strips of one sweep run on several devices (slab mode)
+template <bool SYS>
 __device__ __forceinline__ void c3_st64(uint2* p, unsigned v, unsigned tag) {
-  asm volatile("st." RLFC_C3_SCOPE ".global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v), "r"(tag) : "memory");
+  if (SYS) asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v), "r"(tag) : "memory");
+  else asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v), "r"(tag) : "memory");
 }
+template <bool SYS>
 __device__ __forceinline__ uint2 c3_ld64(const uint2* p) {
   uint2 v;
-  asm volatile("ld." RLFC_C3_SCOPE ".global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  if (SYS) asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  else asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void c3_mbar_arrive(unsigned long long* bar) {
@@ -85,6 +87,7 @@ __device__ __forceinline__ bool c3_mbar_test(unsigned long long* bar, unsigned p
   return ok != 0;
 }
 
+template <bool SYS>
 __global__ void __launch_bounds__(96)
 k_chain_sweeps3(const __grid_constant__ SolverParams q, int level) {
   using namespace rows_detail;           // mbarrier / bulk-copy wrappers (smooth_rows.cuh)
@@ -145,8 +148,8 @@ k_chain_sweeps3(const __grid_constant__ SolverParams q, int level) {
       }
       const int te = efill + lane;
       uint2 vs = make_uint2(0u, tag), vn = make_uint2(0u, tagp);
-      if (hasS && te >= 1 && te <= ni) vs = c3_ld64(g_es + te);
-      if (hasN && te >= 32 && te <= ni + 31) vn = c3_ld64(g_en + te);
+      if (hasS && te >= 1 && te <= ni) vs = c3_ld64<SYS>(g_es + te);
+      if (hasN && te >= 32 && te <= ni + 31) vn = c3_ld64<SYS>(g_en + te);
       const unsigned okm = __ballot_sync(0xffffffffu, vs.y == tag && vn.y == tagp);
       const int cnt = (okm == 0xffffffffu) ? 32 : (__ffs(~okm) - 1);            // leading run of current entries
       const int lim = min(cnt, nsteps - efill);
@@ -187,7 +190,7 @@ k_chain_sweeps3(const __grid_constant__ SolverParams q, int level) {
       bool progress = false;
       if (settling) {
         const int tl = min(b_issue * kC3B - 1, Tend - 1);     // last step in flight whose E operand is checked
-        const bool ok = c3_ld64(reinterpret_cast<const uint2*>(g_e + (size_t)tl * 256) + lane).y == tagp;
+        const bool ok = c3_ld64<SYS>(reinterpret_cast<const uint2*>(g_e + (size_t)tl * 256) + lane).y == tagp;
         if (__all_sync(0xffffffffu, ok)) {
           for (int bb = b_valid + 1; bb < b_issue; bb++) {    // drain the copies in flight (stale), ...
             const int sl = bb % kC3Slots;
@@ -301,8 +304,8 @@ k_chain_sweeps3(const __grid_constant__ SolverParams q, int level) {
         if (l31) N = axv;
         if (l0) S = axv;
         const float res = (W * cxW + E * c.x + S * c.y + N * c.z - rv) * c.w;      // MG.pde:85-86
-        if (edge_lane) c3_st64(eout + t0 + k, __float_as_uint(res), tag);
-        c3_st64(out + (size_t)k * 32, __float_as_uint(res), tag);
+        if (edge_lane) c3_st64<SYS>(eout + t0 + k, __float_as_uint(res), tag);
+        c3_st64<SYS>(out + (size_t)k * 32, __float_as_uint(res), tag);
         W = res;
         cxW = c.x;
       }

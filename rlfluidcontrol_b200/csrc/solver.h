@@ -100,7 +100,17 @@ struct EnvScalars {
   int   *any_active;// [1]
 };
 
+// Slab mode (BASELINE config 5): one domain advanced by several devices that share every array through one virtual
+// address range (vmm.h).  A device owns a contiguous range of a kernel's row blocks (plain arrays) or strips (skewed
+// arrays); kernels are launched with their full grid on every device and blocks outside the device's range exit.
+struct SlabBarrier {
+  unsigned* count;          // [1] arrivals of all devices, all barriers (memory of device 0, mapped everywhere)
+  unsigned* epoch;          // [1] this device's barrier count (its own memory)
+  unsigned n;               // devices
+};
+
 struct SolverParams {
+  int slab_n, slab_rank;    // devices sharing the domain (0/1 = not in slab mode), this device's index
   int B;                    // environments in the batch
   int n, m, P;              // level-0 dims
   size_t stride;            // level-0 per-env stride
@@ -144,6 +154,19 @@ struct SolverParams {
   int *xs_stats;            // [B][8] counters of the last serial pass (rlfc_env_field_sum_stats)
   EnvScalars sc;
 };
+
+#ifdef __CUDACC__
+// true = block `blk` of `nblk` (a kernel's row-block or strip index) belongs to another device
+__device__ __forceinline__ bool slab_skip(unsigned blk, unsigned nblk, int rank, int n) {
+  if (n <= 1) return false;
+  const unsigned lo = (unsigned)((unsigned long long)nblk * (unsigned)rank / (unsigned)n);
+  const unsigned hi = (unsigned)((unsigned long long)nblk * (unsigned)(rank + 1) / (unsigned)n);
+  return blk < lo || blk >= hi;
+}
+#endif
+
+// every device of a slab-mode handle waits here for all the others (between dependent kernels)
+int launch_slab_barrier(const SlabBarrier& b, cudaStream_t st);
 
 // opt-in shared-memory attributes of the strip kernels; call once per handle before the first launch / capture
 int configure_kernels(const SolverParams& P);

@@ -89,8 +89,8 @@ template <bool PREDICTOR>
 __global__ void __launch_bounds__(128)
 k_advdif(const float* __restrict__ srcx, const float* __restrict__ srcy, const float* __restrict__ u0x,
          const float* __restrict__ u0y, float* __restrict__ dstx, float* __restrict__ dsty, int n, int m, int P,
-         size_t stride, float dt, float nu, const int* __restrict__ frozen) {
-  if (frozen[blockIdx.z]) return;
+         size_t stride, float dt, float nu, const int* __restrict__ frozen, int slab_rank, int slab_n) {
+  if (frozen[blockIdx.z] || slab_skip(blockIdx.y, gridDim.y, slab_rank, slab_n)) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ni = n - 2, mj = m - 2;
   const int jw0 = 1 + blockIdx.x * kAdvCols;                         // first output column of this warp
@@ -240,7 +240,7 @@ __device__ __forceinline__ float band_face(const SolverParams& q, const float* u
 __global__ void __launch_bounds__(256)
 k_band_blend(const __grid_constant__ SolverParams q, const float* ux_all, const float* uy_all) {
   const int e = blockIdx.y, b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= q.nband_x + q.nband_y || q.sc.frozen[e]) return;
+  if (b >= q.nband_x + q.nband_y || q.sc.frozen[e] || slab_skip(blockIdx.x, gridDim.x, q.slab_rank, q.slab_n)) return;
   const float* ux = ux_all + (size_t)e * q.stride;
   const float* uy = uy_all + (size_t)e * q.stride;
   float* tmp = q.band_tmp + (size_t)e * (q.nband_x + q.nband_y);
@@ -494,7 +494,7 @@ __device__ __forceinline__ void down_block(const DevLevel& L, const DevLevel& C,
 __global__ void __launch_bounds__(256)
 k_mg_down0(const __grid_constant__ SolverParams q, const float* __restrict__ rin_all, float* __restrict__ rout_all) {
   const int e = blockIdx.z;
-  if (!q.sc.active[e]) return;
+  if (!q.sc.active[e] || slab_skip(blockIdx.y, gridDim.y, q.slab_rank, q.slab_n)) return;
   const DevLevel& L0 = q.lev[0];
   const DevLevel& L1 = q.lev[1];
   const int J = blockIdx.x * blockDim.x + threadIdx.x + 1;   // coarse interior indices
@@ -526,6 +526,7 @@ k_resid_down0(const __grid_constant__ SolverParams q, const float* __restrict__ 
   const int P = L.P, n = L.n, m = L.m;
   const int e = blockIdx.z;
   if (q.sc.frozen[e]) return;                          // (active[e] is 0 after every completed solve: the MG kernels skip it too)
+  if (slab_skip(blockIdx.y, gridDim.y, q.slab_rank, q.slab_n)) return;
   const int tid = threadIdx.y * kRdJ + threadIdx.x;
   if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) { q.sc.active[e] = 1; q.sc.iters[2 * e + which] = 0; }
   const size_t eo = (size_t)e * L.stride;
@@ -1034,7 +1035,7 @@ k_project_shift(const __grid_constant__ SolverParams q, const float* __restrict_
   const int P = q.P, n = q.n, m = q.m, nv = P >> 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int e = blockIdx.y;
-  if (idx >= n * nv || q.sc.frozen[e]) return;
+  if (idx >= n * nv || q.sc.frozen[e] || slab_skip(blockIdx.x, gridDim.x, q.slab_rank, q.slab_n)) return;
   const int i = idx / nv, j4 = (idx - i * nv) << 2;
   const size_t eo = (size_t)e * q.stride;
   const float shift = -1 * q.sc.psum[e] / q.inv_cells;
@@ -1088,10 +1089,10 @@ k_project_shift(const __grid_constant__ SolverParams q, const float* __restrict_
 __global__ void __launch_bounds__(256)
 k_heun(const float* __restrict__ ucx, const float* __restrict__ ucy, const float* __restrict__ ubx,
        const float* __restrict__ uby, float* __restrict__ uax, float* __restrict__ uay, int n, int m, int P,
-       size_t stride, const int* __restrict__ frozen) {
+       size_t stride, const int* __restrict__ frozen, int slab_rank, int slab_n) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y * blockDim.y + threadIdx.y;
-  if (i >= n || j >= m || frozen[blockIdx.z]) return;
+  if (i >= n || j >= m || frozen[blockIdx.z] || slab_skip(blockIdx.y, gridDim.y, slab_rank, slab_n)) return;
   const size_t k = (size_t)blockIdx.z * stride + IDX(i, j);
   uax[k] = (ucx[k] + ubx[k]) * 0.5f;
   uay[k] = (ucy[k] + uby[k]) * 0.5f;
@@ -1213,6 +1214,25 @@ __global__ void k_emit_obs(const __grid_constant__ SolverParams q, const float* 
 }
 
 // end of one MGsolver iteration inside a CUDA-graph WHILE node: continue while any env is still active
+// Slab mode: all devices meet here between dependent kernels.  One arrival counter (device 0's memory) counts every
+// device's every barrier; a device has passed its k-th barrier when the counter has reached k * n.
+__global__ void k_slab_barrier(SlabBarrier b) {
+  __threadfence_system();
+  const unsigned ep = *b.epoch + 1u;
+  *b.epoch = ep;
+  atomicAdd_system(b.count, 1u);
+  const unsigned target = ep * b.n;
+  unsigned spins = 0;
+  while (true) {
+    unsigned v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(b.count) : "memory");
+    if ((int)(v - target) >= 0) break;
+    if (++spins > (1u << 26)) __trap();          // a device that never arrives is a bug, and a trap beats a hung box
+    __nanosleep(100);
+  }
+  __threadfence_system();
+}
+
 __global__ void k_loopcond(cudaGraphConditionalHandle h, int* any_active) {
   if (threadIdx.x == 0) {
     const unsigned v = *any_active ? 1u : 0u;
@@ -1233,9 +1253,9 @@ int launch_advdif(const SolverParams& q, const float* srcx, const float* srcy, c
   const int ni = q.n - 2, mj = q.m - 2;
   dim3 grid((mj + kAdvCols - 1) / kAdvCols, ((ni + kAdvRows - 1) / kAdvRows + 3) / 4, q.B);
   if (srcx == u0x && srcy == u0y)
-    k_advdif<true><<<grid, 128, 0, st>>>(srcx, srcy, u0x, u0y, dstx, dsty, q.n, q.m, q.P, q.stride, q.dt, q.nu, q.sc.frozen);
+    k_advdif<true><<<grid, 128, 0, st>>>(srcx, srcy, u0x, u0y, dstx, dsty, q.n, q.m, q.P, q.stride, q.dt, q.nu, q.sc.frozen, q.slab_rank, q.slab_n);
   else
-    k_advdif<false><<<grid, 128, 0, st>>>(srcx, srcy, u0x, u0y, dstx, dsty, q.n, q.m, q.P, q.stride, q.dt, q.nu, q.sc.frozen);
+    k_advdif<false><<<grid, 128, 0, st>>>(srcx, srcy, u0x, u0y, dstx, dsty, q.n, q.m, q.P, q.stride, q.dt, q.nu, q.sc.frozen, q.slab_rank, q.slab_n);
   return 1;
 }
 
@@ -1293,6 +1313,11 @@ int launch_bc_heun(const SolverParams& q, float* ux, float* uy, const float* usx
   return 1;
 }
 
+int launch_slab_barrier(const SlabBarrier& b, cudaStream_t st) {
+  k_slab_barrier<<<1, 1, 0, st>>>(b);
+  return 1;
+}
+
 int launch_loopcond(const SolverParams& q, unsigned long long handle, cudaStream_t st) {
   k_loopcond<<<1, 32, 0, st>>>((cudaGraphConditionalHandle)handle, q.sc.any_active);
   return 1;
@@ -1343,7 +1368,8 @@ int configure_kernels(const SolverParams& q) {
   cudaError_t e3 = cudaFuncSetAttribute(k_mg_coarse_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coarse_rows_smem(q));
   if (q.chain_levels > 0 &&
       (cudaFuncSetAttribute(k_chain_sweeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kChMaxWpb * sizeof(ChainRing))) != cudaSuccess ||
-       cudaFuncSetAttribute(k_chain_sweeps3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Chain3Smem)) != cudaSuccess))
+       cudaFuncSetAttribute(k_chain_sweeps3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Chain3Smem)) != cudaSuccess ||
+       cudaFuncSetAttribute(k_chain_sweeps3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Chain3Smem)) != cudaSuccess))
     return -1;
   cudaError_t e4 = cudaSuccess;
   if (!q.lev[0].wave && !q.lev[0].ch.on) switch (q.lev[0].rt.C) {
@@ -1363,7 +1389,11 @@ int configure_kernels(const SolverParams& q) {
 int launch_chain_sweeps(const SolverParams& q, int l, cudaStream_t st) {
   const ChainLevel& ch = q.lev[l].ch;
   if (q.chain_v == 1) k_chain_sweeps<<<q.B * 4 * ch.nb, 32 * ch.wpb, ch.wpb * sizeof(ChainRing), st>>>(q, l);
-  else k_chain_sweeps3<<<q.B * 4 * ch.ns_loc, 96, sizeof(Chain3Smem), st>>>(q, l);
+  else if (ch.ns_loc > 0) {
+    // (slab mode: strips on other devices hand their edge operands over through peer memory: system-scope accesses)
+    if (q.slab_n > 1) k_chain_sweeps3<true><<<q.B * 4 * ch.ns_loc, 96, sizeof(Chain3Smem), st>>>(q, l);
+    else k_chain_sweeps3<false><<<q.B * 4 * ch.ns_loc, 96, sizeof(Chain3Smem), st>>>(q, l);
+  }
   return 1;
 }
 int launch_chain_incr(const SolverParams& q, int l, float* r_out, int which, cudaStream_t st) {
@@ -1506,7 +1536,7 @@ int launch_shift_p(const SolverParams& q, cudaStream_t st) {
 int launch_heun(const SolverParams& q, const float* ucx, const float* ucy, const float* ubx, const float* uby,
                 float* uax, float* uay, cudaStream_t st) {
   dim3 blk(32, 8);
-  k_heun<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(ucx, ucy, ubx, uby, uax, uay, q.n, q.m, q.P, q.stride, q.sc.frozen);
+  k_heun<<<grid2d(q.m, q.n, q.B, blk), blk, 0, st>>>(ucx, ucy, ubx, uby, uax, uay, q.n, q.m, q.P, q.stride, q.sc.frozen, q.slab_rank, q.slab_n);
   return 1;
 }
 

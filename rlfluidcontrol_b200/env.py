@@ -29,7 +29,7 @@ class Config(C.Structure):
         ("action_scale", C.c_float), ("substeps", C.c_int), ("init_time", C.c_float),
         ("episode_time", C.c_float), ("n_envs", C.c_int), ("device", C.c_int), ("exact", C.c_int),
         ("mg_max_iters", C.c_int), ("init_bdim_path", C.c_char_p), ("stream", C.c_void_p),
-        ("n_groups", C.c_int),
+        ("n_groups", C.c_int), ("n_devices", C.c_int),
     ]
 
 
