@@ -14,7 +14,9 @@
                         8d), a step = one solver step (AFCCylinder.update2); metric solver-steps/s; roofline against the
                         240 B/cell model.  N > 1 runs N independent replicas (the path does not shard on one domain
                         without the slab decomposition of config 5).
-  --config 5            BASELINE configs[4] (8192x4096 over 8 GPUs): not built; prints {"unavailable": ...}.
+  --config 5            BASELINE configs[4]: ONE 8192x4096 domain (--resolution 512) slab-decomposed over --gpus devices of
+                        one box (rlfc_config.n_devices: shared address range + NVLink peer access, one host process);
+                        metric solver-steps/s, scaling "strong"; reports barriers (exchanges) per step and NVLink bytes.
 
 `value`  : device-resident throughput (inputs already in HBM, *_device entry points, CUDA events on the handle's stream).
 `e2e`    : the same metric through the host-pointer C-ABI call (pinned host buffers, H2D actions + D2H results inside the
@@ -588,6 +590,121 @@ def run_wide(args):
         dist.destroy_process_group()
 
 
+METRIC5 = "solver-steps/sec (single BDIM domain, slab-decomposed over the GPUs of one box)"
+
+
+def nvlink_counters(n):
+    """Cumulative NVLink data bytes (tx + rx) of devices 0..n-1 from NVML, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        tot = 0
+        for d in range(n):
+            h = pynvml.nvmlDeviceGetHandleByIndex(d)
+            vals = pynvml.nvmlDeviceGetFieldValues(h, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xFFFFFFFF),
+                                                       (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])
+            for v in vals:
+                if v.nvmlReturn != 0:
+                    return None
+                tot += int(v.value.ullVal) * 1024          # KiB
+        return tot
+    except Exception:
+        return None
+
+
+def run_slab(args):
+    """Config 5: ONE domain (default 8192x4096, resolution 512) advanced by --gpus devices through the library's slab mode
+    (rlfc_config.n_devices): the devices are driven by ONE host process -- rank 0 -- which owns all of them (shared address
+    range + peer access); under torchrun the other ranks only take part in the rendezvous."""
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        dist.init_process_group("gloo", init_method="env://")
+    nd = args.gpus
+    if rank == 0:
+        import rlfluidcontrol_b200 as R
+
+        K, W = args.steps, max(args.warmup, 3)
+        res = args.resolution
+        t_step = float(np.float32(0.18) / np.float32(res))
+        env = R.AFCCylinderBatch(1, init_state=None, device=0, resolution=res, x_lengths=16, y_lengths=8, t_step=t_step, n_devices=nd)
+        cells = (env.n - 2) * (env.m - 2)
+        act_host = np.array([[0.5, -0.5]], np.float32)
+        torch.cuda.set_device(0)
+        ext = torch.cuda.ExternalStream(env.stream, device=0)
+        act_dev = torch.tensor([[0.5, -0.5]], dtype=torch.float32, device="cuda:0")
+        torch.cuda.synchronize()
+        for _ in range(args.settle_steps):
+            env.update2_device()
+        env.update2_device(act_dev.data_ptr())
+        for _ in range(W):
+            env.update2_device()
+        _ = env.t                                            # (synchronises)
+        clocks = ClockSampler(0)
+        clocks.start()
+        l0, (_, b0, shared) = env.launch_count, env.slab_info()
+        nv0 = nvlink_counters(nd)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(K):
+            env.update2_device()                             # (the last kernel of a step runs behind a barrier of all devices)
+        e1.record(ext)
+        _ = env.t
+        ms = e0.elapsed_time(e1)
+        nv1 = nvlink_counters(nd)
+        launches, barriers = env.launch_count - l0, env.slab_info()[1] - b0
+        clk = clocks.stop()
+        for _ in range(W):
+            env.update2(act_host, want_probes=True)
+        t0 = time.perf_counter()
+        for _ in range(K):
+            f, pr = env.update2(act_host, want_probes=True)
+        e2e_s = time.perf_counter() - t0
+        assert np.isfinite(f).all() and not env.flags().any()
+        prof, its = [], []
+        if args.profile_steps > 0:
+            env.set_profiling(True)
+            for _ in range(args.profile_steps):
+                env.update2()
+                its.append(env.mg_iters()[0].tolist())
+            prof = env.get_profile()
+            env.set_profiling(False)
+        env.close()
+        peak, peak_src = measured_peak()
+        kern, tot_ms, table = kernel_table(prof, args.profile_steps, peak, clk.get("sm_mhz") if clk else None, {})
+        k_sum = float(np.sum(its, axis=1).mean()) if its else 2.0
+        model_bytes = 4.0 * cells * (28 + 16 * k_sum)
+        ach = model_bytes / (ms / K * 1e-3) / 1e9
+        line = {
+            "metric": METRIC5, "value": K / (ms / 1e3), "unit": UNIT3, "n_gpus": nd, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"BASELINE config 5: ONE {env.n - 2}x{env.m - 2} cylinder-wake domain (resolution {res}, 16x8 lengths, "
+                                   f"Re=500, dt = 0.18 grid units, uniform start, actions 0 then (0.5,-0.5)) slab-decomposed over {nd} "
+                                   "GPU(s) of one box; one step = one solver step (AFCCylinder.update2)",
+                       "baseline_config": 5, "grid": f"{env.n - 2}x{env.m - 2}", "mode": "exact (bit-identical to the single-device run)",
+                       "l2": "working set >> 126 MB L2 per device (inputs larger than L2)",
+                       "parallelism": f"slab x{nd}: rows / strips distributed over one shared address range (VMM + NVLink peer access), "
+                                      "one host process drives all devices"},
+            "clocks": clk,
+            "e2e": {"value": K / e2e_s, "unit": UNIT3, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": int((2 + 32) * 4)},
+            "gpu_launches": int(launches),
+            "slab": {"devices": nd, "barriers_per_step": barriers / K, "shared_address_range_bytes": shared,
+                     "nvlink_bytes_per_step_measured": (None if nv0 is None or nv1 is None else (nv1 - nv0) / K)},
+            "roofline": {"bound": "hbm", "kernel": "whole solver step", "achieved": ach, "peak": peak * nd, "unit": "GB/s",
+                         "frac": ach / (peak * nd), "traffic": None, "peak_source": peak_src + f" x {nd} devices",
+                         "algorithmic_bytes_per_launch": model_bytes, "avg_launch_ms": ms / K,
+                         "model": "4 B x N_int x (28 + 16 (kP + kC)) = 240 B/cell at one MG iteration per solve (SURVEY 8d)"},
+            "kernels": table, "mg_iters_per_solve": k_sum / 2,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -601,20 +718,21 @@ def main():
     ap.add_argument("--cpu-sample-env-steps", type=int, default=4)
     ap.add_argument("--cpu-sample-wide-steps", type=int, default=2)
     ap.add_argument("--ref-env-steps", type=int, default=2, help="env-steps per core per step in --impl reference")
-    ap.add_argument("--resolution", type=int, default=128, help="config 3: cells per diameter (128 = the 2048x1024 domain)")
+    ap.add_argument("--resolution", type=int, default=None,
+                    help="configs 3 / 5: cells per diameter (default 128 = the 2048x1024 domain / 512 = the 8192x4096 domain)")
     ap.add_argument("--settle-steps", type=int, default=12, help="config 3: untimed solver steps after the impulsive start")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.resolution is None:
+        args.resolution = 512 if args.config == 5 else 128
     if args.steps is None:
-        args.steps = 200 if (args.config == 3 and args.impl == "b200") else 8
+        args.steps = 200 if (args.config == 3 and args.impl == "b200") else (20 if args.config == 5 else 8)
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
     elif args.config == 5:
-        if int(os.environ.get("RANK", "0")) == 0:
-            print(json.dumps({"metric": "solver-steps/sec (single 8192x4096 BDIM domain, slab-decomposed)", "unavailable":
-                              "config 5 (slab decomposition over 8 GPUs with NVLink halo exchange) is not built; see DESIGN.md section 5"}))
+        run_slab(args)
     elif args.config == 3:
         run_wide(args)
     else:

@@ -181,6 +181,10 @@ int  rlfc_env_get_profile(rlfc_env *env, int idx, char *name, int name_cap, doub
                           long long *launches, double *algorithmic_bytes_per_launch);
 /* The stream the handle enqueues on (cudaStream_t), for event timing by the caller. */
 void *rlfc_env_stream(rlfc_env *env);
+/* Slab mode (rlfc_config.n_devices > 1): the devices sharing the domain, the device-wide barriers executed so far (one
+   between any two dependent kernels: the exchange count), and the bytes of the shared address range.  n_devices = 1,
+   0, 0 for an ordinary handle. */
+int  rlfc_env_slab_info(const rlfc_env *env, int *n_devices, long long *barriers, long long *bytes_shared);
 /* Number of kernel launches (incl. those inside replayed CUDA graphs) issued so far. */
 long long rlfc_env_launch_count(const rlfc_env *env);
 /* Algorithmic bytes moved per solver step per env (SURVEY section 8d model) given the MG iteration

@@ -47,6 +47,13 @@ __device__ __forceinline__ void xs_fill(const SolverParams& q, const float* p, l
   }
 }
 
+// PASS (large domains only; 0 otherwise): 1 = first of two passes -- also records, per batch, the predicted accumulator at
+// its start and what the batch really does to a float accumulator (its table's increment: the rounding BIAS of a long run
+// of small addends against a large accumulator is systematic, thousands of ulps per million additions, and the exact
+// prefix sums the prediction is made of know nothing about it); k_xsum_refine turns these into a per-batch correction;
+// 2 = second pass: the prediction includes that correction, so the records are built for the binade the accumulator is
+// really in.  A prediction is only a prediction: exactness rests on the validity checks of the serial pass alone.
+template <int PASS>
 __global__ void __launch_bounds__(kXsThreads)
 k_xsum_tables(const __grid_constant__ SolverParams q) {
   __shared__ float buf[kXsThreads * kXsPad];
@@ -114,6 +121,9 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
   __syncthreads();
   double pred = base_pred;
   for (int w = 0; w < warp; w++) pred += wsum[w];
+  const long long batch_ = (long long)c * (kXsThreads / 32) + warp;
+  if (PASS == 1 && lane == 0 && batch_ < q.xs_nbatches) q.xs_pred[(size_t)e * q.xs_nbatches + batch_] = pred;
+  if (PASS == 2 && batch_ < q.xs_nbatches) pred += q.xs_corr[(size_t)e * q.xs_nbatches + batch_];
   pred += incl - ssum;
   uint32_t slot[xsum::kSlotWords];
   if (cnt > 0) {
@@ -165,12 +175,15 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
     const uint32_t emitmask = __ballot_sync(0xffffffffu, head && !absorbed);
     const int idx = __popc(emitmask & ((1u << lane) - 1u));       // entry index of an emitting head lane
     const int count = __popc(emitmask) + 1;
-    const int run = type == xsum::kSerial ? __ffs(~(sermask >> lane)) - 1 : 0;   // serial summaries from this lane on
+    // serial summaries from this lane on (all the way to lane 31: the shifted mask has no zero bit left when lane == 0)
+    const uint32_t nser = ~(sermask >> lane);
+    const int run = type == xsum::kSerial ? (nser ? __ffs(nser) - 1 : 32 - lane) : 0;
     const long long batch = (long long)c * (kXsThreads / 32) + warp;
     if (batch < q.xs_nbatches) {
       uint32_t* rec = q.xs_recs + ((size_t)e * q.xs_nbatches + batch) * kXsRecWords;
       if (lane == 0)
         *reinterpret_cast<uint4*>(rec) = make_uint4(count <= kXsRecEntries ? (uint32_t)count : 0xffffffffu, sermask, 0u, 0u);
+      if (PASS == 1 && lane == 31 && count > kXsRecEntries) q.xs_inc[(size_t)e * q.xs_nbatches + batch] = incl;
       if (count <= kXsRecEntries) {
         const uint32_t nz = xsum::kNegZero;                        // serial heads and the last entry add nothing
         if (head && !absorbed) {
@@ -179,6 +192,17 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
           ent[0] = make_uint4(X[0], X[1], X[2], X[3]);
           ent[1] = make_uint4(X[4], X[5], X[6], sp ? slot[xsum::kSlotRaw] : nz);
           ent[2] = make_uint4(sp ? slot[xsum::kSlotRaw + 1] : nz, sp ? slot[xsum::kSlotRaw + 2] : nz, (uint32_t)run, (uint32_t)lane);
+        }
+        if (PASS == 1 && lane == 31) {
+          // the batch's effect on a float accumulator: the table's increment where the batch is one valid table,
+          // otherwise its exact sum
+          double inc = incl;
+          if (count == 1 && acc[0] != xsum::kAnyKey && (int32_t)acc[3] != xsum::kNever) {
+            const int ex = (int)(acc[0] & 255u);
+            inc = ldexp((double)(int32_t)acc[1], ex - 150);
+            if (acc[0] >> 8) inc = -inc;
+          }
+          q.xs_inc[(size_t)e * q.xs_nbatches + batch] = inc;
         }
         if (lane == 31) {
           uint4* ent = reinterpret_cast<uint4*>(rec + 8 + kXsEntWords * (count - 1));
@@ -194,6 +218,36 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
   if (t == 0) {
     __threadfence();
     *(volatile unsigned*)(q.xs_rflag + (size_t)e * q.xs_nchunks + c) = q.xs_epoch[e] + 1u;
+  }
+}
+
+// Between the two table passes of a large domain: prefix sums of the batches' float increments = the refined prediction
+// of the accumulator at every batch start; its difference from the first pass's prediction is the correction.
+__global__ void __launch_bounds__(1024)
+k_xsum_refine(const __grid_constant__ SolverParams q) {
+  __shared__ double wtot[32];
+  const int e = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (q.sc.frozen[e]) return;
+  const int nb = q.xs_nbatches, per = (nb + 1023) / 1024;
+  const double* inc = q.xs_inc + (size_t)e * nb;
+  const double* pred = q.xs_pred + (size_t)e * nb;
+  double* corr = q.xs_corr + (size_t)e * nb;
+  const int b0 = t * per, b1 = min(b0 + per, nb);
+  double mine = 0.0;
+  for (int b = b0; b < b1; b++) mine += inc[b];
+  double incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) wtot[warp] = incl;
+  __syncthreads();
+  double run = incl - mine;
+  for (int w = 0; w < warp; w++) run += wtot[w];
+  for (int b = b0; b < b1; b++) {
+    corr[b] = run - pred[b];
+    run += inc[b];
   }
 }
 
@@ -430,8 +484,9 @@ k_xsum_condense(const __grid_constant__ SolverParams q) {
 // when its validity condition holds for the true accumulator.
 __global__ void __launch_bounds__(32)
 k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
-  extern __shared__ __align__(16) uint32_t xs_dyn[];               // [32][32] float stage
+  extern __shared__ __align__(16) uint32_t xs_dyn[];               // [32][32] float stage | [32][33] float stage (redo)
   float (*stage)[32] = reinterpret_cast<float (*)[32]>(xs_dyn);
+  float (*stageP)[33] = reinterpret_cast<float (*)[33]>(xs_dyn + 32 * 32);
   const int e = blockIdx.x, lane = threadIdx.x;
   if (q.sc.frozen[e]) return;
   const unsigned len = (unsigned)(q.m - 2), P = (unsigned)q.P;
@@ -439,7 +494,7 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
   const int nb = q.xs_nbatches;
   const float* p = q.lev[0].x + (size_t)e * q.stride;
   const uint32_t* recs = q.xs_recs + (size_t)e * nb * kXsRecWords;
-  int st_rec = 0, st_walk = 0, st_ent = 0, st_redo = 0;
+  int st_rec = 0, st_walk = 0, st_ent = 0, st_redo = 0, st_km = 0;
   long long tk = clock64(), tacc[4] = {0, 0, 0, 0};                // cycles: [0] block set-up + scan, [1] table runs, [2] record walks, [3] batches redone
 #define XSB_TICK(i) do { const long long n_ = clock64(); tacc[i] += n_ - tk; tk = n_; } while (0)
   uint32_t bits = 0u;                                             // s = +0.f
@@ -459,7 +514,13 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
     }
     bits = xsum::f2u(s);
   };
-  auto redo_batch = [&](int b) {                                  // the whole batch as 1024 genuine additions
+  // A batch whose record does not apply -- in practice: the accumulator sits in the other binade than predicted, or
+  // comes closer to a binade boundary than the prediction did -- is redone with tables built for the TRUE accumulator:
+  // lane L summarises segment L for the accumulator's actual key, a scan composes the prefixes, every lane checks its
+  // prefix against the accumulator, the longest valid prefix is applied in one step, the segment behind it (the real
+  // binade change) is added element by element, and the rest is rebuilt for the new key.  Exact for the same reason as
+  // everywhere else: a table is applied only where its validity condition holds for the true accumulator.
+  auto redo_batch = [&](int b) {
     st_walk++;
     XSB_TICK(2);
     __syncwarp();
@@ -470,8 +531,8 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
       const float* src = p + (size_t)(1u + row) * P + 1u + col;
 #pragma unroll 4
       for (int k = 0; k < 32; k++) {
-        if (K < N) xs_cp4(&stage[k][lane], src);
-        else stage[k][lane] = -0.f;
+        if (K < N) xs_cp4(&stageP[k][lane], src);
+        else stageP[k][lane] = -0.f;
         K += 32u; col += 32u; src += 32;
         while (col >= len) { col -= len; src += P - len; }
       }
@@ -479,27 +540,63 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    {
+    auto add_row = [&](int k) {                                   // 32 genuine additions (every lane the same chain, broadcast loads)
       float s = xsum::u2f(bits);
-      const float4* v4 = reinterpret_cast<const float4*>(&stage[0][0]);
 #pragma unroll 8
-      for (int k = 0; k < 256; k++) {                              // every lane runs the same chain on broadcast loads
-        const float4 v = v4[k];
-        s += v.x; s += v.y; s += v.z; s += v.w;
-      }
+      for (int j = 0; j < 32; j++) s += stageP[k][j];
       bits = xsum::f2u(s);
-      st_redo += 32;
+      st_redo++;
+    };
+    int done = 0;
+    if (q.xs_flags & 1) {                                         // RLFC_XS_REDO=serial: plain genuine additions (cross-check)
+      for (int k = 0; k < 32; k++) add_row(k);
+      done = 32;
+    }
+    while (done < 32) {
+      const uint32_t key = bits >> 23;
+      if (!xsum::key_ok(key)) { add_row(done); done++; continue; }
+      uint32_t w[7] = {xsum::kAnyKey, 0u, 0u, (uint32_t)INT32_MIN, (uint32_t)INT32_MAX, (uint32_t)INT32_MIN, (uint32_t)INT32_MAX};
+      if (lane >= done) {
+        xsum::Run run;
+        run.start(key);
+#pragma unroll 8
+        for (int j = 0; j < 32; j++) run.add(stageP[lane][j]);    // (row pitch 33: conflict-free)
+        if (run.good) { run.store(w); xsum::normalise_table(w); }
+        else { w[0] = key; w[1] = w[2] = 0u; w[3] = w[5] = (uint32_t)xsum::kNever; w[4] = w[6] = (uint32_t)(-xsum::kNever); }
+      }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t prev[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) prev[k] = __shfl_up_sync(0xffffffffu, w[k], o);
+        if (lane >= o) xsum::compose_tables(prev, w);
+      }
+      bool ok = true;
+      const uint32_t nbits = xsum::apply_table(bits, w[0], (int32_t)w[1], (int32_t)w[2], (int32_t)w[3], (int32_t)w[4], (int32_t)w[5],
+                                               (int32_t)w[6], ok);
+      const uint32_t okm = __ballot_sync(0xffffffffu, ok || lane < done);
+      const int f = (okm == 0xffffffffu) ? 32 : (__ffs(~okm) - 1);               // first segment whose prefix does not apply
+      if (f > done) bits = __shfl_sync(0xffffffffu, nbits, f - 1);
+      if (f < 32) { add_row(f); done = f + 1; } else done = 32;
     }
     __syncwarp();
     XSB_TICK(3);
   };
   auto walk_batch = [&](int b, const uint32_t* rec) {              // one record, entry by entry (as k_xsum_chain)
     const uint4 hdr = *reinterpret_cast<const uint4*>(rec);
+#ifdef RLFC_XS_DIAG
+    if (lane == 0 && b >= 503 && b <= 505) printf("xswalk %d hdr %08x %08x bits %08x\n", b, hdr.x, hdr.y, bits);
+#endif
     if (hdr.x == 0xffffffffu) { st_walk += 1 << 16; redo_batch(b); return; }
     const uint32_t start = bits;
     const int st_redo0 = st_redo;
     bool ok = true;
     const int count = (int)hdr.x;
+    if (count > 0 && rec[8] != xsum::kAnyKey && rec[8] != (bits >> 23)) st_km++;   // (diagnostic: the record was built for another binade)
+#ifdef RLFC_XS_DIAG
+    if (lane == 0 && count > 0 && rec[8] != xsum::kAnyKey && rec[8] != (bits >> 23) && (st_km % 16) == 1)
+      printf("xs miss batch %d of %d: accumulator %.9g (key %u), record key %u\n", b, nb, xsum::u2f(bits), bits >> 23, rec[8]);
+#endif
     for (int i = 0; i < count; i++) {
       const uint4 t0 = *reinterpret_cast<const uint4*>(rec + 8 + kXsEntWords * i);
       const uint4 t1 = *reinterpret_cast<const uint4*>(rec + 12 + kXsEntWords * i);
@@ -537,7 +634,13 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
     }
     int k = 0;
     XSB_TICK(0);
+#ifdef RLFC_XS_DIAG
+    if (lane == 0) printf("xsblk %d bits %08x puremask %08x\n", b0, bits, puremask);
+#endif
     while (k < kend) {
+#ifdef RLFC_XS_DIAG
+      if (lane == 0) printf("xsbat %d bits %08x\n", b0 + k, bits);
+#endif
       if ((puremask >> k) & 1u) {
         const uint32_t rest = ~(puremask >> k);                    // first non-table record at or after k
         int run = rest ? __ffs(rest) - 1 : 32 - k;
@@ -548,6 +651,9 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
         bool ok = true;
         const uint32_t nb_bits = xsum::apply_table(bits, tbl[0], (int32_t)tbl[1], (int32_t)tbl[2], (int32_t)tbl[3], (int32_t)tbl[4],
                                                    (int32_t)tbl[5], (int32_t)tbl[6], ok);
+#ifdef RLFC_XS_DIAG
+        if (lane == 0 && b0 + k <= 505 && b0 + k + run > 503) printf("xsrun %d..%d key %08x D0 %d ok %d\n", b0 + k, b0 + k + run - 1, tbl[0], (int)tbl[1], (int)ok);
+#endif
         if (ok) { bits = nb_bits; st_rec += run; st_ent++; }
         else for (int j = 0; j < run; j++) walk_batch(b0 + k + j, recs + (size_t)(b0 + k + j) * kXsRecWords);
         k += run;
@@ -564,9 +670,9 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
     q.sc.psum[e] = xsum::u2f(bits);
     q.xs_epoch[e] += 1u;
     int* st = q.xs_stats + 8 * e;
-    st[0] = st_rec; st[1] = st_walk; st[2] = st_ent; st[3] = st_redo;
+    st[0] = st_rec; st[1] = st_walk; st[2] = st_ent | (st_km << 16); st[3] = st_redo;
     for (int k = 0; k < 4; k++) st[4 + k] = (int)tacc[k];
   }
 #undef XSB_TICK
 }
-constexpr size_t kXsBlocksSmem = (size_t)(32 * 32) * 4;
+constexpr size_t kXsBlocksSmem = (size_t)(32 * 32 + 32 * 33) * 4;

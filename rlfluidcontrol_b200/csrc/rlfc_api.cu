@@ -936,6 +936,8 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     sp.xs_nchunks = (sp.xs_nseg + 255) / 256;
     sp.xs_nbatches = (sp.xs_nseg + 31) / 32;
     sp.xs_ctot = nullptr; sp.xs_recs = nullptr;
+    if (const char* ev2 = std::getenv("RLFC_XS_REDO")) sp.xs_flags |= std::strcmp(ev2, "serial") == 0 ? 1 : 0;
+    const bool xs_refine = !(std::getenv("RLFC_XS_REFINE") && std::atoi(std::getenv("RLFC_XS_REFINE")) == 0);
     TRY(E->dmalloc(&sp.xs_stats, (size_t)8 * B));
     bool summaries = N * B <= 24000000ll || slab;   // (one large domain: the plain chain would be tens of milliseconds)
     E->home_only = true;                            // Field.sum runs on device 0 only
@@ -948,7 +950,14 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
       TRY(E->dmalloc(&sp.xs_epoch, (size_t)B));
       TRY(E->dmalloc(&sp.xs_recs, (size_t)sp.xs_nbatches * 192 * B));
       sp.xs_blk = nullptr;
-      if (sp.xs_nbatches >= 256) TRY(E->dmalloc(&sp.xs_blk, (size_t)((sp.xs_nbatches + 31) / 32) * 256 * B));
+      if (sp.xs_nbatches >= 256) {
+        TRY(E->dmalloc(&sp.xs_blk, (size_t)((sp.xs_nbatches + 31) / 32) * 256 * B));
+        if (xs_refine) {
+        TRY(E->dmalloc(&sp.xs_pred, (size_t)sp.xs_nbatches * B));
+        TRY(E->dmalloc(&sp.xs_inc, (size_t)sp.xs_nbatches * B));
+        TRY(E->dmalloc(&sp.xs_corr, (size_t)sp.xs_nbatches * B));
+        }
+      }
     }
     E->home_only = false;
   }
@@ -1011,7 +1020,10 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
       v.xs_ctot += (size_t)e0 * v.xs_nchunks;
       v.xs_cflag += (size_t)e0 * v.xs_nchunks; v.xs_rflag += (size_t)e0 * v.xs_nchunks; v.xs_epoch += e0;
       v.xs_recs += (size_t)e0 * v.xs_nbatches * 192;
-      if (v.xs_blk) v.xs_blk += (size_t)e0 * ((v.xs_nbatches + 31) / 32) * 256;
+      if (v.xs_blk) {
+        v.xs_blk += (size_t)e0 * ((v.xs_nbatches + 31) / 32) * 256;
+        if (v.xs_corr) { v.xs_pred += (size_t)e0 * v.xs_nbatches; v.xs_inc += (size_t)e0 * v.xs_nbatches; v.xs_corr += (size_t)e0 * v.xs_nbatches; }
+      }
     }
     v.xs_stats += 8 * e0;
     const size_t o = (size_t)e0 * sp.stride;
@@ -1423,6 +1435,14 @@ int rlfc_format_float_java(float v, char* buf, int cap) {
 }
 
 void* rlfc_env_stream(rlfc_env* E) { return E ? (void*)E->stream : nullptr; }
+int rlfc_env_slab_info(const rlfc_env* E, int* n_devices, long long* barriers, long long* bytes_shared) {
+  if (!E) return fail(RLFC_EINVAL, "null handle");
+  if (n_devices) *n_devices = E->slab.empty() ? 1 : (int)E->slab.size();
+  if (barriers) *barriers = E->slab_barriers;
+  if (bytes_shared) *bytes_shared = (long long)E->vmm.bytes_mapped();
+  return RLFC_OK;
+}
+
 long long rlfc_env_launch_count(const rlfc_env* E) { return E ? E->launches : 0; }
 
 double rlfc_env_model_bytes_per_solver_step(const rlfc_env* E) {

@@ -150,7 +150,10 @@ struct SolverParams {
   unsigned *xs_epoch;       // [B] passes completed
   unsigned *xs_recs;        // [B][xs_nbatches][192] batch records (32 summaries condensed)
   unsigned *xs_blk;         // [B][ceil(xs_nbatches/32)][8][32] blocks of 32 records condensed (large domains; else nullptr)
+  double *xs_pred, *xs_inc, *xs_corr;   // [B][xs_nbatches] large domains: first-pass prediction at every batch start, the batches'
+                            // float increments, and the correction the second table pass adds (k_xsum_refine)
   int xs_nseg, xs_nchunks, xs_nbatches;
+  int xs_flags;             // cross-check switches: bit 0 = redo batches as plain additions (RLFC_XS_REDO=serial)
   int *xs_stats;            // [B][8] counters of the last serial pass (rlfc_env_field_sum_stats)
   EnvScalars sc;
 };

@@ -1489,7 +1489,13 @@ int launch_smooth0(const SolverParams& q, const float* r_in, float* r_out, int w
 // Field.sum as segment summaries: the table kernel, then the serial pass (individually launchable for profiling)
 int launch_psum_tables(const SolverParams& q, cudaStream_t st) {
   const dim3 grid(q.B, q.xs_nchunks);     // chunk index slow: see the look-back in k_xsum_tables
-  k_xsum_tables<<<grid, kXsThreads, 0, st>>>(q);
+  if (q.xs_corr) {                        // large domains: two passes, the second with the refined prediction
+    k_xsum_tables<1><<<grid, kXsThreads, 0, st>>>(q);
+    k_xsum_refine<<<q.B, 1024, 0, st>>>(q);
+    k_xsum_tables<2><<<grid, kXsThreads, 0, st>>>(q);
+    return 3;
+  }
+  k_xsum_tables<0><<<grid, kXsThreads, 0, st>>>(q);
   return 1;
 }
 int launch_psum_pass(const SolverParams& q, cudaStream_t st) {
@@ -1514,7 +1520,7 @@ int launch_psum_overlapped(const SolverParams& q, cudaStream_t st, cudaStream_t 
   cudaEventRecord(fork, st);
   cudaStreamWaitEvent(side, fork, 0);
   const dim3 grid(q.B, q.xs_nchunks);
-  k_xsum_tables<<<grid, kXsThreads, 0, st>>>(q);
+  k_xsum_tables<0><<<grid, kXsThreads, 0, st>>>(q);
   k_xsum_chain<true><<<q.B, 32, 0, side>>>(q);       // waits for each chunk's record flag (bounded), see the kernel
   cudaEventRecord(join, side);
   cudaStreamWaitEvent(st, join, 0);

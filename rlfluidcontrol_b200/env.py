@@ -86,6 +86,7 @@ def load_library():
                                        C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
     L.rlfc_env_stream.argtypes = [vp]
     L.rlfc_env_stream.restype = vp
+    L.rlfc_env_slab_info.argtypes = [vp, ip, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.rlfc_env_launch_count.argtypes = [vp]
     L.rlfc_env_launch_count.restype = C.c_longlong
     L.rlfc_env_model_bytes_per_solver_step.argtypes = [vp]
@@ -283,6 +284,12 @@ class AFCCylinderBatch:
     @property
     def launch_count(self):
         return int(self._L.rlfc_env_launch_count(self._h))
+
+    def slab_info(self):
+        """(devices sharing the domain, device-wide barriers executed so far, bytes of the shared address range)."""
+        n, b, by = C.c_int(), C.c_longlong(), C.c_longlong()
+        self._check(self._L.rlfc_env_slab_info(self._h, C.byref(n), C.byref(b), C.byref(by)), "rlfc_env_slab_info")
+        return n.value, b.value, by.value
 
     def model_bytes_per_solver_step(self):
         return float(self._L.rlfc_env_model_bytes_per_solver_step(self._h))

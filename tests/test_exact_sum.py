@@ -69,6 +69,14 @@ def adversarial(kind, n, rng):
         a[0] = 512.0
         a[rng.integers(1, max(2, n), n // 7)] *= -1
         return a
+    if kind == 11:                                                            # +1, -1, +1, ...: the accumulator changes binade at
+        return np.where(np.arange(n) % 2 == 0, 1.0, -1.0)                     # every addition, whole batches of serial segments
+    if kind == 12:                                                            # long cancelling stretch inside an ordinary field
+        a = rng.standard_normal(n) * 0.01
+        k0, ln = n // 3, min(5000, n // 3)
+        a[k0:k0 + ln] = np.where(np.arange(ln) % 2 == 0, 0.75, -0.75)
+        a[k0 - 1] = -np.sum(a[:k0 - 1])
+        return a
     a = rng.standard_normal(n)                                                # Inf / NaN somewhere
     a[rng.integers(0, n)] = [np.inf, -np.inf, np.nan][int(rng.integers(0, 3))]
     return a
@@ -128,15 +136,46 @@ def test_device_field_sum(rlfc, oracle, resolution, xl, yl):
     """rlfc_env_field_sum on adversarial pressure fields == the oracle's Field.sum, bit for bit (also with the plain
     serial chain, RLFC_PSUM=serial, through test_alternative_execution_paths)."""
     rng = np.random.default_rng(5)
-    B = 11
+    B = 13
     with rlfc.AFCCylinderBatch(B, init_state=None, resolution=resolution, x_lengths=xl, y_lengths=yl) as env:
         n, m = env.n, env.m
         fields = []
         for e in range(B):
-            p = adversarial(e % 11, n * m, rng).astype(np.float32).reshape(n, m)
+            p = adversarial(e % 13, n * m, rng).astype(np.float32).reshape(n, m)
             fields.append(p)
             env.set_fields(e, None, None, p)
         got = env.field_sum()
         for e in range(B):
             want = np.float32(oracle.Field(n, m, values=fields[e]).sum())
             assert got[e].tobytes() == want.tobytes() or (np.isnan(got[e]) and np.isnan(want)), (e, got[e], want)
+
+
+@pytest.mark.gpu
+def test_device_field_sum_large_domain(rlfc, oracle):
+    """The large-domain path (record blocks condensed in parallel, batches that miss their prediction redone with tables
+    built for the true accumulator): 2048x1024 fields with the accumulator hovering around binade boundaries, crossing
+    zero, meeting large and tiny addends == the oracle's serial float loop, bit for bit."""
+    rng = np.random.default_rng(11)
+    res = 128
+    with rlfc.AFCCylinderBatch(1, init_state=None, resolution=res, x_lengths=16, y_lengths=8,
+                               t_step=float(np.float32(0.18) / np.float32(res))) as env:
+        n, m = env.n, env.m
+        N = n * m
+        for case in range(10):
+            if case < 5:
+                p = adversarial(case * 2 + 1, N, rng).astype(np.float32)
+            elif case >= 8:
+                p = adversarial(case + 3, N, rng).astype(np.float32)
+            elif case == 5:      # zero-mean smooth field: the sum wanders around 0 and the binade boundaries near it
+                x = np.linspace(0, 40 * np.pi, N)
+                p = (1e-3 * np.sin(x) + 1e-5 * rng.standard_normal(N)).astype(np.float32)
+            elif case == 6:      # accumulator parked next to 2.0 by a constant offset, then tiny signed addends
+                p = (1e-6 * rng.standard_normal(N)).astype(np.float32)
+                p[m + 1] = 2.0
+            else:                # long stretches of one sign followed by cancellation
+                p = np.where((np.arange(N) // 50000) % 2 == 0, 3e-4, -3e-4).astype(np.float32) * (1 + 1e-3 * rng.standard_normal(N).astype(np.float32))
+            p = p.reshape(n, m)
+            env.set_fields(0, None, None, p)
+            got = env.field_sum()[0]
+            want = np.float32(oracle.Field(n, m, values=p).sum())
+            assert got.tobytes() == want.tobytes() or (np.isnan(got) and np.isnan(want)), (case, got, want, env.field_sum_stats()[0].tolist())
