@@ -29,6 +29,12 @@
 #endif
 constexpr int kC3B = RLFC_C3B;           // steps per batch (multiple of 8)
 constexpr int kC3Slots = RLFC_C3SLOTS;   // batches in flight
+#ifndef RLFC_C3_LSLEEP
+#define RLFC_C3_LSLEEP 0
+#endif
+#ifndef RLFC_C3_FSLEEP
+#define RLFC_C3_FSLEEP 0
+#endif
 constexpr int kC3EdgeRing = 128;         // entries of the edge ring (power of two, >= 64)
 
 struct __align__(128) Chain3Smem {
@@ -168,7 +174,12 @@ k_chain_sweeps3(const __grid_constant__ SolverParams q, int level) {
         efill += lim;
         if (lane == 0) c3_sts_volatile(&R.edge_ready, efill);
         idle = 0;
-      } else if (++idle > kChSpinMax) __trap();               // a tag that never comes is a bug, and a trap beats a hung GPU
+      } else {
+        if (++idle > kChSpinMax) __trap();                    // a tag that never comes is a bug, and a trap beats a hung GPU
+#if RLFC_C3_FSLEEP > 0
+        __nanosleep(RLFC_C3_FSLEEP);
+#endif
+      }
     }
 #ifdef RLFC_CHAIN_STATS
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(fw_t1));
@@ -247,7 +258,12 @@ k_chain_sweeps3(const __grid_constant__ SolverParams q, int level) {
         }
       }
       if (progress) idle = 0;
-      else if (++idle > kChSpinMax) __trap();
+      else {
+        if (++idle > kChSpinMax) __trap();
+#if RLFC_C3_LSLEEP > 0
+        __nanosleep(RLFC_C3_LSLEEP);                          // (do not hammer the shared-memory port the compute warp loads through)
+#endif
+      }
     }
     return;
   }
