@@ -780,7 +780,7 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     {  // pre-skewed coefficient table for the row-pipelined smoother (layout: solver.h RowTab)
       const int ni = H.n - 2, mj = H.m - 2;
       const int C = (mj + 31) / 32, K = (3 * C + 1 + 3) / 4, nl = (mj + C - 1) / C;
-      const int front = 10 /*kTabFront*/, entries = front + ni + nl + 10 /*kStageLag*/ + 5 /*kPF*/ + 6;
+      const int front = 10 /*kTabFront*/, entries = rows_table_entries(ni, nl);
       // levels too wide for the row pipeline (more than 8 columns per lane on level 0, 4 on coarse levels) are smoothed by
       // the wavefront fallback (smooth_wave.cuh); RLFC_SMOOTHER=wave forces it everywhere (tests)
       L.wave = (C > (l == 0 ? 8 : 4)) || force_wave;

@@ -43,8 +43,22 @@
 
 namespace rlfc {
 
-constexpr int kRowsWarps = 8;
+constexpr int kRowsWarps = 7;
 constexpr int kRowsThreads = 32 * kRowsWarps;
+#ifndef RLFC_ROWS_BULK_WO
+#define RLFC_ROWS_BULK_WO 3        // x rows leave through one shared->global bulk copy in modes >= this (2: also the coarse levels)
+#endif
+#ifndef RLFC_ROWS_RES_SPLIT
+#define RLFC_ROWS_RES_SPLIT 1      // level 0: the residual stage as two warps (lower / upper half of every lane's columns)
+#endif
+constexpr int kRows0Threads = kRowsThreads;
+// warp roles of the row pipeline (a warp's scheduler is warp id mod 4)
+//   level 0 (mode 3):  {residual A, x increment} {residual B, loader} {sweeps 1+2, stage 0} {sweeps 3+4}
+//   modes 1, 2:        {loader, -} {x increment, -} {sweeps 3+4, stage 0} {sweeps 1+2}      (no residual stage)
+template <bool SKEW> struct rows_detail_roles {
+  static constexpr int ResA = SKEW ? 0 : 4, ResB = SKEW ? 1 : 5, SweepA = SKEW ? 2 : 3, SweepB = SKEW ? 3 : 2,
+                       Xinc = SKEW ? 4 : 1, Loader = SKEW ? 5 : 0, Stage0 = 6;
+};
 #ifndef RLFC_KPF
 #define RLFC_KPF 5
 #endif
@@ -59,7 +73,7 @@ constexpr int kSLanes = 33;        // stage buffers carry a zero 33rd lane (righ
 
 __host__ __device__ constexpr int rows_K(int C) { return (3 * C + 1 + 3) / 4; }   // float4 vectors per lane-entry
 __host__ __device__ constexpr int rows_CP(int C) { return (C + 1) & ~1; }          // lane block of the stage buffers (even)
-__host__ __device__ inline int rows_table_entries(int ni, int nl) { return kTabFront + ni + nl + kStageLag + kPF + 6; }
+__host__ __device__ inline int rows_table_entries(int ni, int nl) { return kTabFront + ni + nl + kStageLag + kPF + 12; }
 
 // dynamic shared memory of one rows_smooth call (bytes): [coef ring | r ring (plain-r modes) | x ring | R ring |
 // stage buffers | mbarriers]; `skewed_r` = level-0 mode, where r arrives pre-skewed and needs no row ring
@@ -70,7 +84,7 @@ __host__ __device__ inline size_t rows_smem_bytes(int C, int P, bool skewed_r) {
 // skewed residual array of one environment (level 0): entry tau = i + l holds row i of lane l's columns,
 // [tau][32][CP] floats; entries the smoother touches: 1 .. ni + nl + kStageLag + kPF + 2
 __host__ __device__ inline size_t rows_skew_floats(int C, int ni, int nl) {
-  return (size_t)(ni + nl + kStageLag + kPF + 8) * 32 * rows_CP(C);
+  return (size_t)(ni + nl + kStageLag + kPF + 14) * 32 * rows_CP(C);
 }
 
 namespace rows_detail {
@@ -122,6 +136,14 @@ __device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned 
                : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// shared -> global bulk copy (bulk async-group completion): the write-out of a finished row by ONE thread
+__device__ __forceinline__ void bulk_s2g(void* gmem, const void* smem, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem), "r"(sm_addr(smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // floats [A, B) of a lane-entry (float4 vectors, lane-contiguous: vector k of lane l sits at ent[k*32 + l])
 template <int A, int B>
@@ -159,7 +181,8 @@ __device__ __forceinline__ void st_block(float* p, const float (&in)[C]) {
 // The per-step barrier of the warp-specialised pipeline: every warp arrives from its OWN role loop (different call
 // sites), which is what a NAMED barrier with an explicit thread count is for (bar.sync id, count; __syncthreads in
 // role-divergent code is formally undefined and is what compute-sanitizer's synccheck reports).
-__device__ __forceinline__ void step_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kRowsThreads) : "memory"); }
+template <int NT>
+__device__ __forceinline__ void step_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
 __device__ __forceinline__ int ring_inc(int s) { return (s + 1 == kRowRing) ? 0 : s + 1; }
 __host__ __device__ constexpr int ring_mod(int row) { return ((row % kRowRing) + kRowRing) % kRowRing; }
@@ -174,7 +197,14 @@ __host__ __device__ constexpr int ring_mod(int row) { return ((row % kRowRing) +
 //      floats) for the ghost cells of x.  In this mode `r` is the environment's SKEWED residual array
 //      (rows_skew_floats; written by k_mg_up0): entry tau is one contiguous block that is bulk-copied straight into
 //      the step-indexed ring, and the new residual is written back in place, skewed, as coalesced stores.
-// Called by ALL kRowsThreads threads of the CTA.  x (and r in modes 1, 2) are this environment's row-major pitched
+// Warp roles (kRowsThreads = 7 warps, ids in rows_detail_roles): sweeps 1+2, sweeps 3+4, the residual increment of the lower /
+// upper half of every lane's columns (mode 3; idle otherwise), x increment, loader, stage 0.  The pipeline is bound by the
+// SM's shared-memory pipe (ncu: 71-76 % of its wavefront peak with one sweep per warp, profiles/r02_rows_balance.md), so a
+// warp runs TWO consecutive sweeps: the second one works two rows behind the first, i.e. on the row the first one
+// finished two steps earlier, so its coefficients are the first one's of two steps ago (kept in registers) and its
+// operands from the previous sweep are the first one's last two results (registers, one shuffle for the neighbouring
+// lane's column): no shared-memory traffic at all for every second sweep.
+// Called by ALL threads of the CTA.  x (and r in modes 1, 2) are this environment's row-major pitched
 // arrays of the level.  Returns this thread's share of r.r (XMODE 3; non-zero only in the residual warp).
 template <int C, int XMODE>
 __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restrict__ r, float* __restrict__ x,
@@ -184,12 +214,18 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
   // float offsets inside a lane-entry
   constexpr int F_CY = 0, F_NINV = C + 1, F_CX = 2 * C + 1, F_END = 3 * C + 1;
   constexpr bool SKEW = (XMODE == 3);
+  constexpr int NT = kRowsThreads;
+  using Roles = rows_detail_roles<SKEW>;
+  constexpr int kWResA = Roles::ResA, kWResB = Roles::ResB, kWSweepA = Roles::SweepA, kWSweepB = Roles::SweepB,
+                kWXinc = Roles::Xinc, kWLoader = Roles::Loader, kWStage0 = Roles::Stage0;
+  constexpr bool BULK_WO = XMODE >= RLFC_ROWS_BULK_WO;   // finished x rows: one bulk copy by the loader / per-lane stores by warp 6
   constexpr int ES = K * 32;                       // float4s per entry
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ni = L.n - 2, mj = L.m - 2, P = L.P;
   const int nl = (mj + C - 1) / C;                 // lanes that own at least one column
   const int lag = nl + kStageLag;                  // row w is complete after step w + nl - 1 + kStageLag
-  const int t_end = (ni + lag + 1) & ~1;           // last step (even count; the last write-out is at step ni + lag)
+  const int t_end = (ni + lag + 5) / 6 * 6;        // last step (a multiple of 6: the sweep warps' unrolled period; the last
+                                                   // write-out is at step ni + lag; later steps only see zero table entries)
   float4* coef = reinterpret_cast<float4*>(smem_raw);
   float* rring = reinterpret_cast<float*>(smem_raw + (size_t)kCoefSlots * ES * 16);   // plain-r modes only
   float* xring = rring + (SKEW ? 0 : (size_t)kRowRing * P);
@@ -199,8 +235,8 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
   const int j0 = C * lane + 1;                     // first column of this lane
 
   // zero the coefficient ring (entries tau <= 0), the R ring and the stage buffers (incl. the 33rd lane)
-  for (int k = threadIdx.x; k < kCoefSlots * ES; k += kRowsThreads) coef[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int k = threadIdx.x; k < (kRSlots * 32 + 5 * 2 * kSLanes) * CP; k += kRowsThreads) R[k] = 0.f;
+  for (int k = threadIdx.x; k < kCoefSlots * ES; k += NT) coef[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = threadIdx.x; k < (kRSlots * 32 + 5 * 2 * kSLanes) * CP; k += NT) R[k] = 0.f;
   __syncthreads();
 
   // loader (one lane of warp 5): row q of r (and x) and table entry q as bulk copies completing on bars[(q-1) & 15]
@@ -224,7 +260,7 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
     if (SKEW) bulk_g2s(R + (size_t)(q & (kRSlots - 1)) * 32 * CP, r + (size_t)q * 32 * CP, rsk_bytes, bar);
     bulk_g2s(coef + (size_t)(q & (kCoefSlots - 1)) * ES, tab + (size_t)(q + kTabFront) * ES, ent_bytes, bar);
   };
-  if (warp == 7) {
+  if (warp == kWLoader) {
     if (lane == 0) {
       fence_proxy_async();
       for (int q = 1; q <= kPF; q++) issue(q);
@@ -235,117 +271,165 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
 
 #ifdef RLFC_ROWS_TIMING        // per-warp busy time between two step barriers (tools: which stage does a step wait for?)
   long long busy_ = 0, tk_ = clock64();
-#define RLFC_STEP_SYNC() do { busy_ += clock64() - tk_; rows_detail::step_barrier(); tk_ = clock64(); } while (0)
+#define RLFC_STEP_SYNC() do { busy_ += clock64() - tk_; rows_detail::step_barrier<NT>(); tk_ = clock64(); } while (0)
 #else
-#define RLFC_STEP_SYNC() rows_detail::step_barrier()
+#define RLFC_STEP_SYNC() rows_detail::step_barrier<NT>()
 #endif
   double rr = 0.0;
-  if (warp < 4) {
-    // ------------------------------------------------------------------ sweep g = warp + 1, row t - L - 2g
-    const int g = warp + 1;
-    float prev[C], Ep[C], cxW[C];
-#pragma unroll
-    for (int c = 0; c < C; c++) { prev[c] = 0.f; Ep[c] = 0.f; cxW[c] = 0.f; }
-    const float* Sin = S + ((size_t)(g - 1) * 2 * kSLanes + lane) * CP;
-    float* Sout = S + ((size_t)g * 2 * kSLanes + lane) * CP;
+  if (warp == kWSweepA || warp == kWSweepB) {
+    // ------------------------------------------------------------------ sweeps gA = 2 warp + 1 (row t - L - 2 gA) and
+    //                                                                    gB = gA + 1 (row t - L - 2 gA - 2)
+    const int gA = (warp == kWSweepA) ? 1 : 3;
+    const float* Sin = S + ((size_t)(gA - 1) * 2 * kSLanes + lane) * CP;
+    float* Sout = S + ((size_t)(gA + 1) * 2 * kSLanes + lane) * CP;
     const float* Rl = R + (size_t)lane * CP;
     const float4* cl = coef + lane;
-    int e0 = (1 - 2 * g) & (kCoefSlots - 1);       // slot of entry t - 2g at t = 1 (same index for the R ring)
-    // operands that do not depend on the previous step are fetched BEFORE the step's barrier (entries <= t and the
-    // R slots <= t - 1 are complete by then), so only the previous stage's row is loaded on the critical path
-    float cxE[C], cyn[2 * C + 1], rv[C];           // cyn = [cy(C+1) | ninv(C)]
-    auto fetch = [&]() {
+    int e0 = (1 - 2 * gA) & (kCoefSlots - 1);      // slot of entry t - 2 gA at t = 1 (same index for the R ring)
+    // Register rings, indexed by compile-time step phases so that nothing is ever moved (the loop is unrolled over the
+    // common period 6):
+    //   set[q], q = t mod 3: coefficient set sweep A uses at step t -- [cy(C+1) | ninv(C)], cx of the row below, r --
+    //     fetched BEFORE the previous step's barrier (entries <= t and the R slots <= t - 1 are complete by then), so only
+    //     the previous stage's row is loaded on the critical path; sweep B at step t uses A's set of step t - 2 =
+    //     set[(q+1) mod 3] (entries tau <= 0 are zero, so the ring starts as zeros);
+    //   rA[q]: sweep A's result of step t; rA[(q+2) mod 3] = of step t - 1 (A's W operand, B's E operand),
+    //     rA[(q+1) mod 3] = of step t - 2 (B's N operands);
+    //   EA[p], rB[p], p = t mod 2: the previous stage's row loaded at step t (this step's E, next step's N operands) and
+    //     sweep B's result (next step's W operand).
+    float cyn[3][2 * C + 1], cxE[3][C], rv[3][C], rA[3][C], EA[2][C], rB[2][C], cxWB[C];
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+#pragma unroll
+      for (int c = 0; c < C; c++) { cxE[q][c] = 0.f; rv[q][c] = 0.f; rA[q][c] = 0.f; }
+#pragma unroll
+      for (int c = 0; c < 2 * C + 1; c++) cyn[q][c] = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++) { EA[0][c] = 0.f; EA[1][c] = 0.f; rB[0][c] = 0.f; rB[1][c] = 0.f; cxWB[c] = 0.f; }
+    auto fetch = [&](auto q_c) {                    // the set of the step with phase q
+      constexpr int q = decltype(q_c)::value;
       const int e1 = (e0 + 1) & (kCoefSlots - 1);
-      ld_entry<F_CY, F_CX>(cl + e0 * ES, cyn);
-      ld_entry<F_CX, F_END>(cl + e1 * ES, cxE);
-      ld_block<C>(Rl + e0 * 32 * CP, rv);
+      ld_entry<F_CY, F_CX>(cl + e0 * ES, cyn[q]);
+      ld_entry<F_CX, F_END>(cl + e1 * ES, cxE[q]);
+      ld_block<C>(Rl + e0 * 32 * CP, rv[q]);
     };
-    fetch();
-    auto step = [&](auto par_c) {
-      constexpr int par = decltype(par_c)::value;
-      float E[C];
-      float Sl = __shfl_up_sync(0xffffffffu, prev[C - 1], 1);
+    fetch(std::integral_constant<int, 1>{});        // t = 1
+    auto step = [&](auto t_c) {
+      constexpr int tt = decltype(t_c)::value;      // t mod 6
+      constexpr int par = tt & 1, q = tt % 3, q1 = (q + 2) % 3, q2 = (q + 1) % 3;
+      float SlA = __shfl_up_sync(0xffffffffu, rA[q1][C - 1], 1);
+      float SlB = __shfl_up_sync(0xffffffffu, rB[par ^ 1][C - 1], 1);
+      float NxB = __shfl_down_sync(0xffffffffu, rA[q1][0], 1);   // A's row t - L - 2 gA - 2, column 0 of lane L+1 (its last step's result)
       const float* Sp = Sin + (par ^ 1) * kSLanes * CP;
-      ld_block<C>(Sp, E);
-      const float Nx = Sp[CP];                      // column 0 of lane L+1 (lane 32 = zero pad)
-      Sl = (lane == 0) ? 0.f : Sl;
-      float res[C];
+      ld_block<C>(Sp, EA[par]);
+      const float NxA = Sp[CP];                     // column 0 of lane L+1 (lane 32 = zero pad)
+      SlA = (lane == 0) ? 0.f : SlA;
+      SlB = (lane == 0) ? 0.f : SlB;
+      NxB = (lane == 31) ? 0.f : NxB;               // (the zero pad of the stage buffers)
+      float resA[C];
 #pragma unroll
       for (int c = 0; c < C; c++) {
-        const float Sop = (c == 0) ? Sl : res[c == 0 ? 0 : c - 1];
-        const float Nop = (c == C - 1) ? Nx : Ep[c == C - 1 ? c : c + 1];
-        res[c] = (prev[c] * cxW[c] + E[c] * cxE[c] + Sop * cyn[c] + Nop * cyn[c + 1] - rv[c]) * cyn[C + 1 + c];
+        const float Sop = (c == 0) ? SlA : resA[c == 0 ? 0 : c - 1];
+        const float Nop = (c == C - 1) ? NxA : EA[par ^ 1][c == C - 1 ? c : c + 1];
+        resA[c] = (rA[q1][c] * cxE[q1][c] + EA[par][c] * cxE[q][c] + Sop * cyn[q][c] + Nop * cyn[q][c + 1] - rv[q][c]) * cyn[q][C + 1 + c];
       }
-      st_block<C>(Sout + par * kSLanes * CP, res);
+      float resB[C];
 #pragma unroll
-      for (int c = 0; c < C; c++) { prev[c] = res[c]; Ep[c] = E[c]; cxW[c] = cxE[c]; }
+      for (int c = 0; c < C; c++) {                 // sweep B: E = A's result of the last step, N = A's result of two steps ago
+        const float Sop = (c == 0) ? SlB : resB[c == 0 ? 0 : c - 1];
+        const float Nop = (c == C - 1) ? NxB : rA[q2][c == C - 1 ? c : c + 1];
+        resB[c] = (rB[par ^ 1][c] * cxWB[c] + rA[q1][c] * cxE[q2][c] + Sop * cyn[q2][c] + Nop * cyn[q2][c + 1] - rv[q2][c]) * cyn[q2][C + 1 + c];
+      }
+      st_block<C>(Sout + par * kSLanes * CP, resB);
+#pragma unroll
+      for (int c = 0; c < C; c++) { rA[q][c] = resA[c]; rB[par][c] = resB[c]; cxWB[c] = cxE[q2][c]; }
       e0 = (e0 + 1) & (kCoefSlots - 1);
-      fetch();
+      fetch(std::integral_constant<int, q2>{});     // (phase of step t + 1; its old content was sweep B's set of this step)
       RLFC_STEP_SYNC();
     };
-    for (int t = 1; t <= t_end; t += 2) {
+    for (int t = 1; t <= t_end; t += 6) {
       step(std::integral_constant<int, 1>{});
+      step(std::integral_constant<int, 2>{});
+      step(std::integral_constant<int, 3>{});
+      step(std::integral_constant<int, 4>{});
+      step(std::integral_constant<int, 5>{});
       step(std::integral_constant<int, 0>{});
     }
-  } else if (warp == 4) {
+  } else if (warp == kWResA || warp == kWResB) {
     // ------------------------------------------------------------------ residual increment, row i5 = t - L - 10
+    // (mode 3: warp kWResA takes columns [0, CA) of every lane's block, warp kWResB columns [CA, C))
     if (XMODE == 3) {
-      float dC[C], dW[C], dEp[C], cxW[C];
+      constexpr int CA = RLFC_ROWS_RES_SPLIT ? (C + 1) / 2 : C;
+      auto run = [&](auto half_c) {
+        constexpr int CLO = decltype(half_c)::value ? CA : 0, CHI = decltype(half_c)::value ? C : CA;
+        float dC[C], dW[C], dEp[C], cxW[C];
 #pragma unroll
-      for (int c = 0; c < C; c++) { dC[c] = 0.f; dW[c] = 0.f; dEp[c] = 0.f; cxW[c] = 0.f; }
-      int i5 = 1 - lane - kStageLag;
-      const float* Sin = S + ((size_t)4 * 2 * kSLanes + lane) * CP;
-      const float* Rl = R + (size_t)lane * CP;
-      const float4* cl = coef + lane;
-      int e0 = (1 - kStageLag) & (kCoefSlots - 1);
-      float* rout = r + ((ptrdiff_t)(1 - kStageLag) * 32 + lane) * CP;   // skewed entry t - 10 of this lane
-      // which of this lane's columns are the first / last column of the level
-      const int cfirst = (lane == 0) ? 0 : -1;
-      const int clast = (lane == nl - 1) ? (mj - 1) - C * lane : -1;
-      auto step = [&](auto par_c) {
-        constexpr int par = decltype(par_c)::value;
-        const int e1 = (e0 + 1) & (kCoefSlots - 1);
-        const float* Sp = Sin + (par ^ 1) * kSLanes * CP;
-        float dE[C], cxE[C], cy[C + 1], rv[C], rN[C];
-        ld_block<C>(Sp, dE);
-        const float Nx = Sp[CP];
+        for (int c = 0; c < C; c++) { dC[c] = 0.f; dW[c] = 0.f; dEp[c] = 0.f; cxW[c] = 0.f; }
+        int i5 = 1 - lane - kStageLag;
+        const float* Sin = S + ((size_t)4 * 2 * kSLanes + lane) * CP;
+        const float* Rl = R + (size_t)lane * CP;
+        const float4* cl = coef + lane;
+        int e0 = (1 - kStageLag) & (kCoefSlots - 1);
+        float* rout = r + ((ptrdiff_t)(1 - kStageLag) * 32 + lane) * CP;   // skewed entry t - 10 of this lane
+        // which of this lane's columns are the first / last column of the level
+        const int cfirst = (lane == 0) ? 0 : -1;
+        const int clast = (lane == nl - 1) ? (mj - 1) - C * lane : -1;
+        auto step = [&](auto par_c) {
+          constexpr int par = decltype(par_c)::value;
+          const int e1 = (e0 + 1) & (kCoefSlots - 1);
+          const float* Sp = Sin + (par ^ 1) * kSLanes * CP;
+          float dE[C], cxE[C], cy[C + 1], rv[C], rN[C];
+          ld_block<C>(Sp, dE);
+          const float Nx = Sp[CP];
 #pragma unroll
-        for (int c = 0; c < C; c++) { dW[c] = dC[c]; dC[c] = dEp[c]; dEp[c] = dE[c]; }
-        float Sl = __shfl_up_sync(0xffffffffu, dW[C - 1], 1);
-        ld_entry<F_CY, F_NINV>(cl + e0 * ES, cy);
-        ld_entry<F_CX, F_END>(cl + e1 * ES, cxE);
-        ld_block<C>(Rl + e0 * 32 * CP, rv);
-        const bool rowok = (unsigned)(i5 - 1) < (unsigned)ni;
-        const bool top = i5 == 1, bot = i5 == ni;
+          for (int c = 0; c < C; c++) { dW[c] = dC[c]; dC[c] = dEp[c]; dEp[c] = dE[c]; }
+          float Sl = 0.f;
+          if (CLO == 0) Sl = __shfl_up_sync(0xffffffffu, dW[C - 1], 1);
+          ld_entry<F_CY, F_NINV>(cl + e0 * ES, cy);
+          ld_entry<F_CX, F_END>(cl + e1 * ES, cxE);
+          ld_block<C>(Rl + e0 * 32 * CP, rv);
+          const bool rowok = (unsigned)(i5 - 1) < (unsigned)ni;
+          const bool top = i5 == 1, bot = i5 == ni;
 #pragma unroll
-        for (int c = 0; c < C; c++) {
-          const float d0 = dC[c];
-          const float dg = -(cxW[c] + cxE[c] + cy[c] + cy[c + 1]);   // diagonal = -sumd, PoissonMatrix.pde:46-48
-          const float w_ = top ? d0 : dW[c];
-          const float e_ = bot ? d0 : dE[c];
-          const float s_ = (c == cfirst) ? d0 : ((c == 0) ? Sl : dC[c == 0 ? 0 : c - 1]);
-          const float n_ = (c == clast) ? d0 : ((c == C - 1) ? Nx : dC[c == C - 1 ? c : c + 1]);
-          const float Ad = d0 * dg + w_ * cxW[c] + e_ * cxE[c] + s_ * cy[c] + n_ * cy[c + 1];   // PoissonMatrix.pde:56-61
-          const bool ok = rowok && C * lane + c < mj;
-          rN[c] = ok ? rv[c] - Ad : 0.f;
-          const float prod = rN[c] * rN[c];            // float product, double accumulation (Field.pde:304-307)
-          rr += (double)prod;
-          cxW[c] = cxE[c];
+          for (int c = CLO; c < CHI; c++) {
+            const float d0 = dC[c];
+            const float dg = -(cxW[c] + cxE[c] + cy[c] + cy[c + 1]);   // diagonal = -sumd, PoissonMatrix.pde:46-48
+            const float w_ = top ? d0 : dW[c];
+            const float e_ = bot ? d0 : dE[c];
+            const float s_ = (c == cfirst) ? d0 : ((c == 0) ? Sl : dC[c == 0 ? 0 : c - 1]);
+            const float n_ = (c == clast) ? d0 : ((c == C - 1) ? Nx : dC[c == C - 1 ? c : c + 1]);
+            const float Ad = d0 * dg + w_ * cxW[c] + e_ * cxE[c] + s_ * cy[c] + n_ * cy[c + 1];   // PoissonMatrix.pde:56-61
+            const bool ok = rowok && C * lane + c < mj;
+            rN[c] = ok ? rv[c] - Ad : 0.f;
+            const float prod = rN[c] * rN[c];            // float product, double accumulation (Field.pde:304-307)
+            rr += (double)prod;
+          }
+#pragma unroll
+          for (int c = 0; c < C; c++) cxW[c] = cxE[c];
+          if (rowok) {                                   // this warp's share of the contiguous 32*CP-float block of the step
+#pragma unroll
+            for (int c = CLO; c < CHI; c++) {
+              if (!(c & 1) && c + 1 < CHI) *reinterpret_cast<float2*>(rout + c) = make_float2(rN[c], rN[c + 1]);
+              else if ((c & 1) && c > CLO) {}            // (second half of a pair)
+              else rout[c] = rN[c];
+            }
+          }
+          e0 = e1;
+          i5++;
+          rout += 32 * CP;
+          RLFC_STEP_SYNC();
+        };
+        for (int t = 1; t <= t_end; t += 2) {
+          step(std::integral_constant<int, 1>{});
+          step(std::integral_constant<int, 0>{});
         }
-        if (rowok) st_block<C>(rout, rN);              // one contiguous 32*CP-float block per warp and step
-        e0 = e1;
-        i5++;
-        rout += 32 * CP;
-        RLFC_STEP_SYNC();
       };
-      for (int t = 1; t <= t_end; t += 2) {
-        step(std::integral_constant<int, 1>{});
-        step(std::integral_constant<int, 0>{});
-      }
+      if (warp == kWResA) run(std::integral_constant<int, 0>{});
+      else if (CA < C) run(std::integral_constant<int, 1>{});
+      else { for (int t = 1; t <= t_end; t++) RLFC_STEP_SYNC(); }
     } else {
       for (int t = 1; t <= t_end; t++) RLFC_STEP_SYNC();
     }
-  } else if (warp == 5) {
+  } else if (warp == kWStage0) {
     // ------------------------------------------------------------------ stage 0 (row t - L) + loader
     int i0 = 1 - lane;
     int slot0 = ring_mod(i0);
@@ -374,7 +458,7 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
       slot0 = ring_inc(slot0);
       RLFC_STEP_SYNC();
     }
-  } else if (warp == 6) {
+  } else if (warp == kWXinc) {
     // ------------------------------------------------------------------ x increment: row t - L - 9 (sweep 4's last row)
     int i6 = 1 - lane - 9;
     int slot = ring_mod(i6);
@@ -383,6 +467,7 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
     float* gbot = gbuf + mj;
     float* gleft = gbuf + 2 * mj;
     float* gright = gbuf + 2 * mj + ni;
+    const int clastx = (lane == nl - 1) ? (mj - 1) - C * lane : -1;   // this lane's column that is the level's last one
     for (int t = 1; t <= t_end; t++) {
       const int par = t & 1;
       float d[C], xv[C];
@@ -398,20 +483,24 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
         const float xn = (XMODE == 1) ? 0.f + d[c] : xv[c] + d[c];
         if (rowok && C * lane + c < mj) xrow[c] = xn;
       }
-      if (XMODE == 3 && rowok && (i6 == 1 || i6 == ni || lane == 0 || lane == nl - 1)) {
-        // boundary values of d feed the ghost cells of x after the sweep (x.plusEq(d) runs over all cells)
+      if (XMODE == 3) {
+        // boundary values of d feed the ghost cells of x after the sweep (x.plusEq(d) runs over all cells).  The first and
+        // the last column are one predicated store each; the top / bottom rows are a branch a lane takes twice per call
+        float dl = d[0];
 #pragma unroll
-        for (int c = 0; c < C; c++) {
-          const int j = j0 + c;
-          if (j <= mj) {
-            if (i6 == 1) gtop[j - 1] = d[c];
-            if (i6 == ni) gbot[j - 1] = d[c];
-            if (j == 1) gleft[i6 - 1] = d[c];
-            if (j == mj) gright[i6 - 1] = d[c];
-          }
+        for (int c = 1; c < C; c++) dl = (c == clastx) ? d[c] : dl;
+        if (rowok && lane == 0) gleft[i6 - 1] = d[0];
+        if (rowok && clastx >= 0) gright[i6 - 1] = dl;
+        if (i6 == 1 || i6 == ni) {
+#pragma unroll
+          for (int c = 0; c < C; c++)
+            if (C * lane + c < mj) {
+              if (i6 == 1) gtop[j0 + c - 1] = d[c];
+              if (i6 == ni) gbot[j0 + c - 1] = d[c];
+            }
         }
       }
-      {  // write-out of row t - lag: every lane's x increment passed it at step t - 2
+      if (!BULK_WO) {  // write-out of row t - lag: every lane's x increment passed it at step t - 2
         const int w = t - lag;
         if (w >= 1 && w <= ni) {
           const float* xs = xring + (size_t)ring_mod(w) * P;
@@ -426,23 +515,79 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
           for (int c = 0; c < C; c++)
             if (1 + lane + 32 * c <= mj) xg[32 * c] = xo[c];
         }
+      } else {
+        // (the loader warp writes finished rows out as ONE bulk copy each; make this step's ring writes
+        // visible to the async proxy before the step barrier)
+        fence_proxy_async();
       }
       i6++;
       slot = ring_inc(slot);
       RLFC_STEP_SYNC();
     }
-  } else {
+  } else if (warp == kWLoader) {
     // ------------------------------------------------------------------ loader: bulk copies kPF steps ahead
-    for (int t = 1; t <= t_end; t++) {
-      if (lane == 0) {
+    // ... and (BULK_WO) the write-out of finished x rows: row w = t - lag is complete in the x ring after step t - 2
+    // (every lane's increment has passed it), ghost columns and pitch padding still as loaded, so the whole row goes
+    // back with one shared->global bulk copy.  Its ring slot is refilled with row w + kRowRing at step
+    // w + kRowRing - kPF > w + lag: the copies of earlier steps must have READ their rows before this step's loads.
+    // (everything lane 0 needs per step is kept as running pointers / offsets: the loader shares a scheduler with a sweep warp)
+    {
+      int q = 1 + kPF;                                                  // entry / row fetched at step t: q = t + kPF
+      unsigned qoff = (unsigned)ring_mod(q) * row_bytes;               // byte offset of row q's slot in the row rings
+      unsigned woff = (unsigned)ring_mod(1 - lag) * row_bytes;         // ... of row t - lag's slot
+      const unsigned ring_bytes = (unsigned)kRowRing * row_bytes;
+      const char* g_r = reinterpret_cast<const char*>(r) + (size_t)q * (SKEW ? rsk_bytes : row_bytes);
+      char* g_x = reinterpret_cast<char*>(x) + (size_t)q * row_bytes;
+      char* g_w = reinterpret_cast<char*>(x) + (ptrdiff_t)(1 - lag) * (ptrdiff_t)row_bytes;
+      const char* g_tab = reinterpret_cast<const char*>(tab + (size_t)(q + kTabFront) * ES);
+      char* const s_r = reinterpret_cast<char*>(rring);
+      char* const s_x = reinterpret_cast<char*>(xring);
+      char* const s_R = reinterpret_cast<char*>(R);
+      char* const s_c = reinterpret_cast<char*>(coef);
+      const unsigned tx_norow = ent_bytes + (SKEW ? rsk_bytes : 0u);
+      const unsigned tx_row = tx_norow + ((XMODE != 1 ? 1u : 0u) + (SKEW ? 0u : 1u)) * row_bytes;
+      for (int t = 1; t <= t_end; t++) {
+        if (lane == 0) {
+        if (BULK_WO) bulk_wait_read0();
         fence_proxy_async();
-        issue(t + kPF);
+        {
+          unsigned long long* bar = bars + ((q - 1) & (kCoefSlots - 1));
+          const bool row = q <= ni;
+          mbar_expect_tx(bar, row ? tx_row : tx_norow);
+          if (row) {
+            if (!SKEW) bulk_g2s(s_r + qoff, g_r, row_bytes, bar);
+            if (XMODE != 1) bulk_g2s(s_x + qoff, g_x, row_bytes, bar);
+          }
+          if (SKEW) bulk_g2s(s_R + (size_t)(q & (kRSlots - 1)) * rsk_bytes, g_r, rsk_bytes, bar);
+          bulk_g2s(s_c + (size_t)(q & (kCoefSlots - 1)) * ent_bytes, g_tab, ent_bytes, bar);
+        }
+        if (BULK_WO) {
+          const int w = t - lag;
+          if (w >= 1 && w <= ni) {
+            bulk_s2g(g_w, s_x + woff, row_bytes);
+            bulk_commit();
+          }
+        }
+        }
+        q++;
+        qoff = (qoff + row_bytes == ring_bytes) ? 0u : qoff + row_bytes;
+        woff = (woff + row_bytes == ring_bytes) ? 0u : woff + row_bytes;
+        g_r += SKEW ? rsk_bytes : row_bytes;
+        g_x += row_bytes;
+        g_w += row_bytes;
+        g_tab += ent_bytes;
+        mbar_wait(bars + (t & (kCoefSlots - 1)), ((unsigned)t >> kCoefShift) & 1u);   // entry / row t + 1 has landed
+        RLFC_STEP_SYNC();
       }
-      mbar_wait(bars + (t & (kCoefSlots - 1)), ((unsigned)t >> kCoefShift) & 1u);   // entry / row t + 1 has landed
-      RLFC_STEP_SYNC();
     }
     // drain: every issued copy must have landed before the shared memory is reused
     for (int q = t_end + 2; q <= t_end + kPF; q++) mbar_wait(bars + ((q - 1) & (kCoefSlots - 1)), ((unsigned)(q - 1) >> kCoefShift) & 1u);
+    if (BULK_WO && lane == 0) {   // ... and every written-out row must be in global memory before anybody reads x again
+      bulk_wait0();
+      fence_proxy_async_all();
+    }
+  } else {
+    for (int t = 1; t <= t_end; t++) RLFC_STEP_SYNC();
   }
 #undef RLFC_STEP_SYNC
 #ifdef RLFC_ROWS_TIMING

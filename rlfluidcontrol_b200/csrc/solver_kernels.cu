@@ -868,7 +868,7 @@ k_mg_coarse_rows(const __grid_constant__ SolverParams q, int first) {
 }
 
 template <int C>
-__global__ void __launch_bounds__(kRowsThreads)
+__global__ void __launch_bounds__(kRows0Threads, 2)
 k_smooth0_rows(const __grid_constant__ SolverParams q, int which) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const DevLevel& L = q.lev[0];
@@ -1469,14 +1469,14 @@ int launch_smooth0(const SolverParams& q, const float* r_in, float* r_out, int w
   if (q.use_rows) {
     const size_t sm = smooth0_rows_smem(q);
     switch (q.lev[0].rt.C) {
-      case 1: k_smooth0_rows<1><<<q.B, kRowsThreads, sm, st>>>(q, which); break;
-      case 2: k_smooth0_rows<2><<<q.B, kRowsThreads, sm, st>>>(q, which); break;
-      case 3: k_smooth0_rows<3><<<q.B, kRowsThreads, sm, st>>>(q, which); break;
-      case 4: k_smooth0_rows<4><<<q.B, kRowsThreads, sm, st>>>(q, which); break;
-      case 5: k_smooth0_rows<5><<<q.B, kRowsThreads, sm, st>>>(q, which); break;
-      case 6: k_smooth0_rows<6><<<q.B, kRowsThreads, sm, st>>>(q, which); break;
-      case 7: k_smooth0_rows<7><<<q.B, kRowsThreads, sm, st>>>(q, which); break;
-      default: k_smooth0_rows<8><<<q.B, kRowsThreads, sm, st>>>(q, which); break;
+      case 1: k_smooth0_rows<1><<<q.B, kRows0Threads, sm, st>>>(q, which); break;
+      case 2: k_smooth0_rows<2><<<q.B, kRows0Threads, sm, st>>>(q, which); break;
+      case 3: k_smooth0_rows<3><<<q.B, kRows0Threads, sm, st>>>(q, which); break;
+      case 4: k_smooth0_rows<4><<<q.B, kRows0Threads, sm, st>>>(q, which); break;
+      case 5: k_smooth0_rows<5><<<q.B, kRows0Threads, sm, st>>>(q, which); break;
+      case 6: k_smooth0_rows<6><<<q.B, kRows0Threads, sm, st>>>(q, which); break;
+      case 7: k_smooth0_rows<7><<<q.B, kRows0Threads, sm, st>>>(q, which); break;
+      default: k_smooth0_rows<8><<<q.B, kRows0Threads, sm, st>>>(q, which); break;
     }
     return 1;
   }
