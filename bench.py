@@ -629,7 +629,12 @@ def run_slab(args):
 
         K, W = args.steps, max(args.warmup, 3)
         res = args.resolution
-        t_step = float(np.float32(0.18) / np.float32(res))
+        # SURVEY 8d prescribes t_step = 0.18/resolution (dt = 0.18 grid units).  At resolution 512 (nu = D/Re = 1.024) that violates
+        # the reference's own bound BDIM.checkCFL = 1/(max|u| + 3 nu) (BDIM.pde:217-219) once |u| > 2.5, and the impulsive start
+        # diverges near solver step 41 -- in the CPU oracle exactly as on the device (profiles/r02_config5_stability.md).  From
+        # resolution 512 on the bench therefore runs dt = 0.09 grid units: same work per step, stable.
+        dt_grid = 0.18 if res < 512 else 0.09
+        t_step = float(np.float32(dt_grid) / np.float32(res))
         env = R.AFCCylinderBatch(1, init_state=None, device=0, resolution=res, x_lengths=16, y_lengths=8, t_step=t_step, n_devices=nd)
         cells = (env.n - 2) * (env.m - 2)
         act_host = np.array([[0.5, -0.5]], np.float32)
@@ -682,7 +687,7 @@ def run_slab(args):
             "metric": METRIC5, "value": K / (ms / 1e3), "unit": UNIT3, "n_gpus": nd, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"BASELINE config 5: ONE {env.n - 2}x{env.m - 2} cylinder-wake domain (resolution {res}, 16x8 lengths, "
-                                   f"Re=500, dt = 0.18 grid units, uniform start, actions 0 then (0.5,-0.5)) slab-decomposed over {nd} "
+                                   f"Re=500, dt = {dt_grid} grid units, uniform start, actions 0 then (0.5,-0.5)) slab-decomposed over {nd} "
                                    "GPU(s) of one box; one step = one solver step (AFCCylinder.update2)",
                        "baseline_config": 5, "grid": f"{env.n - 2}x{env.m - 2}", "mode": "exact (bit-identical to the single-device run)",
                        "l2": "working set >> 126 MB L2 per device (inputs larger than L2)",

@@ -123,7 +123,7 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
   for (int w = 0; w < warp; w++) pred += wsum[w];
   const long long batch_ = (long long)c * (kXsThreads / 32) + warp;
   if (PASS == 1 && lane == 0 && batch_ < q.xs_nbatches) q.xs_pred[(size_t)e * q.xs_nbatches + batch_] = pred;
-  if (PASS == 2 && batch_ < q.xs_nbatches) pred += q.xs_corr[(size_t)e * q.xs_nbatches + batch_];
+  if (PASS >= 2 && batch_ < q.xs_nbatches) pred += q.xs_corr[(size_t)e * q.xs_nbatches + batch_];
   pred += incl - ssum;
   uint32_t slot[xsum::kSlotWords];
   if (cnt > 0) {
@@ -183,7 +183,7 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
       uint32_t* rec = q.xs_recs + ((size_t)e * q.xs_nbatches + batch) * kXsRecWords;
       if (lane == 0)
         *reinterpret_cast<uint4*>(rec) = make_uint4(count <= kXsRecEntries ? (uint32_t)count : 0xffffffffu, sermask, 0u, 0u);
-      if (PASS == 1 && lane == 31 && count > kXsRecEntries) q.xs_inc[(size_t)e * q.xs_nbatches + batch] = incl;
+      if ((PASS == 1 || PASS == 3) && lane == 31 && count > kXsRecEntries) q.xs_inc[(size_t)e * q.xs_nbatches + batch] = incl;
       if (count <= kXsRecEntries) {
         const uint32_t nz = xsum::kNegZero;                        // serial heads and the last entry add nothing
         if (head && !absorbed) {
@@ -193,7 +193,7 @@ k_xsum_tables(const __grid_constant__ SolverParams q) {
           ent[1] = make_uint4(X[4], X[5], X[6], sp ? slot[xsum::kSlotRaw] : nz);
           ent[2] = make_uint4(sp ? slot[xsum::kSlotRaw + 1] : nz, sp ? slot[xsum::kSlotRaw + 2] : nz, (uint32_t)run, (uint32_t)lane);
         }
-        if (PASS == 1 && lane == 31) {
+        if ((PASS == 1 || PASS == 3) && lane == 31) {
           // the batch's effect on a float accumulator: the table's increment where the batch is one valid table,
           // otherwise its exact sum
           double inc = incl;

@@ -928,7 +928,9 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     // Field.sum: segment summaries (exact_sum.cuh) or the plain dependent-add chain (k_psum).  The chain costs
     // 6 cycles per cell of pure latency whatever the batch size and next to no issue slots; the summaries cost
     // throughput proportional to batch x cells and a short serial pass.  Measured on B200 (default grid): summaries
-    // +2.5 % step throughput at 256 envs, -8 % at 512, so the default switches on the batch's cell count.
+    // +2.5 % step throughput at 256 envs, -8 % at 512.  Both costs are proportional to the cells per environment (chain: ~3 ns
+    // per cell of latency; summaries: ~8 ps per cell and environment of throughput), so the choice depends on the batch size
+    // alone: summaries up to 320 environments, whatever the grid (one 8192x4096 domain: 88 ms per solve as a chain).
     // RLFC_PSUM=serial | parallel overrides.
     const char* ev = std::getenv("RLFC_PSUM");
     const long long N = (long long)(g.n - 2) * (g.m - 2);
@@ -936,10 +938,14 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
     sp.xs_nchunks = (sp.xs_nseg + 255) / 256;
     sp.xs_nbatches = (sp.xs_nseg + 31) / 32;
     sp.xs_ctot = nullptr; sp.xs_recs = nullptr;
+    // (the prediction of a zero-mean field's running sum misses the accumulator's binade more often the longer the sum: a second
+    // refinement of the prediction pays from about 8 Mi cells on, profiles/r02_field_sum_large.md)
+    sp.xs_passes = sp.xs_nbatches >= 8192 ? 3 : 2;
+    if (const char* ev3 = std::getenv("RLFC_XS_PASSES")) sp.xs_passes = std::atoi(ev3) >= 3 ? 3 : 2;
     if (const char* ev2 = std::getenv("RLFC_XS_REDO")) sp.xs_flags |= std::strcmp(ev2, "serial") == 0 ? 1 : 0;
     const bool xs_refine = !(std::getenv("RLFC_XS_REFINE") && std::atoi(std::getenv("RLFC_XS_REFINE")) == 0);
     TRY(E->dmalloc(&sp.xs_stats, (size_t)8 * B));
-    bool summaries = N * B <= 24000000ll || slab;   // (one large domain: the plain chain would be tens of milliseconds)
+    bool summaries = B <= 320 || slab;
     E->home_only = true;                            // Field.sum runs on device 0 only
     if (ev && std::strcmp(ev, "serial") == 0) summaries = false;
     if (ev && std::strcmp(ev, "parallel") == 0) summaries = true;

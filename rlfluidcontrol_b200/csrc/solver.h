@@ -153,6 +153,7 @@ struct SolverParams {
   double *xs_pred, *xs_inc, *xs_corr;   // [B][xs_nbatches] large domains: first-pass prediction at every batch start, the batches'
                             // float increments, and the correction the second table pass adds (k_xsum_refine)
   int xs_nseg, xs_nchunks, xs_nbatches;
+  int xs_passes;            // table passes of a large domain's Field.sum: 2, or 3 from 8 Mi cells on (RLFC_XS_PASSES)
   int xs_flags;             // cross-check switches: bit 0 = redo batches as plain additions (RLFC_XS_REDO=serial)
   int *xs_stats;            // [B][8] counters of the last serial pass (rlfc_env_field_sum_stats)
   EnvScalars sc;

@@ -1492,8 +1492,12 @@ int launch_psum_tables(const SolverParams& q, cudaStream_t st) {
   if (q.xs_corr) {                        // large domains: two passes, the second with the refined prediction
     k_xsum_tables<1><<<grid, kXsThreads, 0, st>>>(q);
     k_xsum_refine<<<q.B, 1024, 0, st>>>(q);
+    if (q.xs_passes >= 3) {               // very large domains: a third pass (PASS 3 = corrected prediction AND new increments)
+      k_xsum_tables<3><<<grid, kXsThreads, 0, st>>>(q);
+      k_xsum_refine<<<q.B, 1024, 0, st>>>(q);
+    }
     k_xsum_tables<2><<<grid, kXsThreads, 0, st>>>(q);
-    return 3;
+    return q.xs_passes >= 3 ? 5 : 3;
   }
   k_xsum_tables<0><<<grid, kXsThreads, 0, st>>>(q);
   return 1;

@@ -9,7 +9,7 @@ import rlfluidcontrol_b200 as R
 
 res, steps = int(sys.argv[1]), int(sys.argv[2])
 nd = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-t_step = float(np.float32(0.18) / np.float32(res))
+t_step = float(np.float32(float(sys.argv[4]) if len(sys.argv) > 4 else 0.18) / np.float32(res))
 with R.AFCCylinderBatch(1, init_state=None, resolution=res, x_lengths=16, y_lengths=8, t_step=t_step, n_devices=nd) as env:
     for k in range(steps):
         f = env.update2(np.array([[0.5, -0.5]], np.float32) if k == steps // 2 else None)
