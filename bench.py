@@ -593,8 +593,12 @@ def run_wide(args):
 METRIC5 = "solver-steps/sec (single BDIM domain, slab-decomposed over the GPUs of one box)"
 
 
+NVLINK_NOTE = None
+
+
 def nvlink_counters(n):
-    """Cumulative NVLink data bytes (tx + rx) of devices 0..n-1 from NVML, or None."""
+    """Cumulative NVLink data bytes (tx + rx) of devices 0..n-1 from NVML, or None (NVLINK_NOTE says why)."""
+    global NVLINK_NOTE
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -605,10 +609,12 @@ def nvlink_counters(n):
                                                        (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])
             for v in vals:
                 if v.nvmlReturn != 0:
+                    NVLINK_NOTE = f"NVML field {v.fieldId} on device {d}: nvmlReturn {v.nvmlReturn}"
                     return None
                 tot += int(v.value.ullVal) * 1024          # KiB
         return tot
-    except Exception:
+    except Exception as ex:
+        NVLINK_NOTE = f"{type(ex).__name__}: {ex}"
         return None
 
 
@@ -697,7 +703,8 @@ def run_slab(args):
             "e2e": {"value": K / e2e_s, "unit": UNIT3, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": int((2 + 32) * 4)},
             "gpu_launches": int(launches),
             "slab": {"devices": nd, "barriers_per_step": barriers / K, "shared_address_range_bytes": shared,
-                     "nvlink_bytes_per_step_measured": (None if nv0 is None or nv1 is None else (nv1 - nv0) / K)},
+                     "nvlink_bytes_per_step_measured": (None if nv0 is None or nv1 is None else (nv1 - nv0) / K),
+                     "nvlink_counter_note": NVLINK_NOTE},
             "roofline": {"bound": "hbm", "kernel": "whole solver step", "achieved": ach, "peak": peak * nd, "unit": "GB/s",
                          "frac": ach / (peak * nd), "traffic": None, "peak_source": peak_src + f" x {nd} devices",
                          "algorithmic_bytes_per_launch": model_bytes, "avg_launch_ms": ms / K,
