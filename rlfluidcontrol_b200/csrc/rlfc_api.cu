@@ -908,7 +908,10 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   sp.rr_blocks = 0;
   int n_groups = cfg->n_groups;
   if (const char* ev = std::getenv("RLFC_GROUPS")) n_groups = std::atoi(ev);
-  if (n_groups <= 0) n_groups = B >= 128 ? 4 : (B >= 32 ? 2 : 1);
+  // (measured, 256 default-grid envs, round 2: 1 group 6 722, 2 groups 6 713, 4 groups 6 636, 8 groups 5 286 env-steps/s; round 1's
+  // latency-bound kernels gained 6 % from 4 concurrent groups, the present ones do not.  Batches larger than one wave of the
+  // one-CTA-per-environment kernels keep 4 groups.)
+  if (n_groups <= 0) n_groups = B > 256 ? 4 : 1;
   n_groups = std::min(n_groups, B);
   if (slab) n_groups = 1;
   if (const char* ev = std::getenv("RLFC_NO_GRAPH")) E->use_graph = std::atoi(ev) == 0;

@@ -43,7 +43,7 @@
 
 namespace rlfc {
 
-constexpr int kRowsWarps = 7;
+constexpr int kRowsWarps = 8;       // coarse V-cycle kernel: its down / up passes use every warp; the pipeline needs seven
 constexpr int kRowsThreads = 32 * kRowsWarps;
 #ifndef RLFC_ROWS_BULK_WO
 #define RLFC_ROWS_BULK_WO 3        // x rows leave through one shared->global bulk copy in modes >= this (2: also the coarse levels)
@@ -51,7 +51,7 @@ constexpr int kRowsThreads = 32 * kRowsWarps;
 #ifndef RLFC_ROWS_RES_SPLIT
 #define RLFC_ROWS_RES_SPLIT 1      // level 0: the residual stage as two warps (lower / upper half of every lane's columns)
 #endif
-constexpr int kRows0Threads = kRowsThreads;
+constexpr int kRows0Threads = 32 * 7;   // level-0 kernel: the seven pipeline warps
 // warp roles of the row pipeline (a warp's scheduler is warp id mod 4)
 //   level 0 (mode 3):  {residual A, x increment} {residual B, loader} {sweeps 1+2, stage 0} {sweeps 3+4}
 //   modes 1, 2:        {loader, -} {x increment, -} {sweeps 3+4, stage 0} {sweeps 1+2}      (no residual stage)
@@ -197,7 +197,7 @@ __host__ __device__ constexpr int ring_mod(int row) { return ((row % kRowRing) +
 //      floats) for the ghost cells of x.  In this mode `r` is the environment's SKEWED residual array
 //      (rows_skew_floats; written by k_mg_up0): entry tau is one contiguous block that is bulk-copied straight into
 //      the step-indexed ring, and the new residual is written back in place, skewed, as coalesced stores.
-// Warp roles (kRowsThreads = 7 warps, ids in rows_detail_roles): sweeps 1+2, sweeps 3+4, the residual increment of the lower /
+// Warp roles (seven warps, ids in rows_detail_roles; an eighth warp of the coarse kernel idles at the step barrier): sweeps 1+2, sweeps 3+4, the residual increment of the lower /
 // upper half of every lane's columns (mode 3; idle otherwise), x increment, loader, stage 0.  The pipeline is bound by the
 // SM's shared-memory pipe (ncu: 71-76 % of its wavefront peak with one sweep per warp, profiles/r02_rows_balance.md), so a
 // warp runs TWO consecutive sweeps: the second one works two rows behind the first, i.e. on the row the first one
@@ -214,7 +214,7 @@ __device__ __forceinline__ double rows_smooth(const DevLevel& L, float* __restri
   // float offsets inside a lane-entry
   constexpr int F_CY = 0, F_NINV = C + 1, F_CX = 2 * C + 1, F_END = 3 * C + 1;
   constexpr bool SKEW = (XMODE == 3);
-  constexpr int NT = kRowsThreads;
+  constexpr int NT = SKEW ? kRows0Threads : kRowsThreads;
   using Roles = rows_detail_roles<SKEW>;
   constexpr int kWResA = Roles::ResA, kWResB = Roles::ResB, kWSweepA = Roles::SweepA, kWSweepB = Roles::SweepB,
                 kWXinc = Roles::Xinc, kWLoader = Roles::Loader, kWStage0 = Roles::Stage0;
