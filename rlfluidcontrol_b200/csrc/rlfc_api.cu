@@ -906,6 +906,10 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   TRY(E->dmalloc(&E->init_ux, sp.stride)); TRY(E->dmalloc(&E->init_uy, sp.stride)); TRY(E->dmalloc(&E->init_p, sp.stride));
   // per-env scalars
   sp.rr_blocks = 0;
+  sp.resid_march = 1;
+  if (const char* ev = std::getenv("RLFC_RESID")) sp.resid_march = std::strcmp(ev, "tile") != 0;
+  // (odd level-0 sizes cannot pair rows / columns for the restriction: MG.divisible rules them out anyway)
+  if (((g.n - 2) | (g.m - 2)) & 1) sp.resid_march = 0;
   int n_groups = cfg->n_groups;
   if (const char* ev = std::getenv("RLFC_GROUPS")) n_groups = std::atoi(ev);
   // (measured, 256 default-grid envs, round 2: 1 group 6 722, 2 groups 6 713, 4 groups 6 636, 8 groups 5 286 env-steps/s; round 1's

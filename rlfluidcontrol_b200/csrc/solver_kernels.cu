@@ -576,6 +576,125 @@ k_resid_down0(const __grid_constant__ SolverParams q, const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same fused first MG iteration as a MARCHING kernel (the default; k_resid_down0 above is kept as the cross-check,
+// RLFC_RESID=tile): a warp owns kRmCols columns (+2 halo lanes on either side, as k_advdif) and marches down kRmRows
+// rows.  Everything that is shared between neighbouring cells is loaded ONCE: p, ux, lx travel down the rows in
+// registers, the j-neighbours of p, uy, ly and d come from the adjacent lanes by shuffle -- 7 loads, 8 shuffles and
+// ~27 float operations per cell instead of the tile version's 15 + 5 loads and its shared-memory round trip
+// (225 -> ~75 thread instructions per fine cell).  Row i is finalised one iteration after its d is formed, when
+// d of row i+1 exists.  Arithmetic and its order are those of k_resid_down0 / the reference.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRmCols = 28;       // output columns per warp (even: 2x2 restriction pairs start at odd columns)
+#ifndef RLFC_RM_ROWS
+#define RLFC_RM_ROWS 32
+#endif
+#ifndef RLFC_RM_MINB
+#define RLFC_RM_MINB 8
+#endif
+constexpr int kRmRows = RLFC_RM_ROWS;   // rows per chunk (even)
+
+__global__ void __launch_bounds__(128, RLFC_RM_MINB)
+k_resid_down0_march(const __grid_constant__ SolverParams q, const float* __restrict__ ux_all, const float* __restrict__ uy_all,
+                    const float* __restrict__ pin_all, float* __restrict__ pout_all, float* __restrict__ rout_all, int which) {
+  const DevLevel& L = q.lev[0];
+  const DevLevel& C = q.lev[1];
+  const int P = L.P, n = L.n, m = L.m, ni = n - 2, mj = m - 2;
+  const int e = blockIdx.z;
+  if (q.sc.frozen[e]) return;                          // (active[e] is 0 after every completed solve: the MG kernels skip it too)
+  if (slab_skip(blockIdx.y, gridDim.y, q.slab_rank, q.slab_n)) return;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { q.sc.active[e] = 1; q.sc.iters[2 * e + which] = 0; }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int jw0 = 1 + blockIdx.x * kRmCols;                          // first output column of this warp (odd)
+  const int ia = 1 + (blockIdx.y * 4 + warp) * kRmRows;              // first row of this chunk (odd)
+  if (ia > ni) return;
+  const int ib = min(ia + kRmRows - 1, ni);
+  const size_t eo = (size_t)e * L.stride;
+  const float* __restrict__ ux = ux_all + eo;
+  const float* __restrict__ uy = uy_all + eo;
+  const float* __restrict__ pin = pin_all + eo;
+  float* __restrict__ pout = pout_all + eo;
+  float* __restrict__ rout = rout_all + eo;
+  const float* __restrict__ lx = L.lx;
+  const float* __restrict__ ly = L.ly;
+  const float* __restrict__ diag = L.diag;
+  const float* __restrict__ inv = L.inv;
+  const int j = jw0 - 2 + lane;                                      // this lane's column (may be outside the array)
+  const int jl = min(max(j, 0), m - 1);                              // clamped for loads
+  const bool out_lane = lane >= 2 && lane < 2 + kRmCols && j <= mj;
+  const bool jfirst = j == 1, jlast = j == mj;
+  auto rowc = [&](int i) { return min(max(i, 0), n - 1); };
+  // rolling rows: p of rows ir-1, ir, ir+1; ux and lx of rows ir, ir+1
+  int ir = ia - 1;                                                   // the row whose r and d are formed next
+  float p_m = pin[IDX(rowc(ir - 1), jl)], p_c = pin[IDX(rowc(ir), jl)], p_n = pin[IDX(rowc(ir + 1), jl)];
+  float ux_c = ux[IDX(rowc(ir), jl)], lx_c = lx[IDX(rowc(ir), jl)];
+  // what finalising a row needs from the two rows formed before it
+  float d_1 = 0.f, d_2 = 0.f, r_1 = 0.f, pq_1 = 0.f, pq_2 = 0.f, diag_1 = 0.f, lxw_1 = 0.f, ly_1 = 0.f, lyn_1 = 0.f;
+  float acc = 0.f;
+  // forms r and d of row ir (garbage outside the interior, never used there) and advances the rolling rows.  (Issuing the
+  // seven loads one or two rows ahead of their use was measured: 176 -> 241 us -- 88 registers instead of 64, and deep
+  // register-target prefetches serialise on the warp's six load scoreboards.)
+  auto form = [&](float& r_out, float& d_out, float& diag_o, float& lxw_o, float& ly_o, float& lyn_o) {
+    const int k = IDX(rowc(ir), jl), kn = IDX(rowc(ir + 1), jl);
+    const float ux_n = ux[kn], lx_n = lx[kn];
+    const float uy_c = uy[k], ly_c = ly[k], dg = diag[k], iv = inv[k];
+    const float p_s = __shfl_up_sync(0xffffffffu, p_c, 1), p_nn = __shfl_down_sync(0xffffffffu, p_c, 1);
+    const float uy_n = __shfl_down_sync(0xffffffffu, uy_c, 1), ly_n = __shfl_down_sync(0xffffffffu, ly_c, 1);
+    const float sdiv = ux_n - ux_c + uy_n - uy_c;                    // VectorField.pde:56-65
+    const float Ap = p_c * dg + p_m * lx_c + p_n * lx_n + p_s * ly_c + p_nn * ly_n;   // PoissonMatrix.pde:56-61
+    r_out = sdiv - Ap;
+    d_out = r_out * iv;                                              // MG.pde:80
+    diag_o = dg; lxw_o = lx_c; ly_o = ly_c; lyn_o = ly_n;
+    // advance: ir -> ir + 1
+    ux_c = ux_n; lx_c = lx_n;
+    p_m = p_c; p_c = p_n;
+    ir++;
+    p_n = pin[IDX(rowc(ir + 1), jl)];
+  };
+  // finalises row i = ir - 2 (its d is d_1, the rows around it d_2 and d_0): smooth(0) increment, new p, restriction
+  auto finish = [&](int i, float d_0, float lxe, float p_e, bool odd) {
+    const float dc = d_1;
+    const float dW = (i == 1) ? dc : d_2, dE = (i == ni) ? dc : d_0;             // d.setBC: ghost = adjacent interior value
+    const float dSs = __shfl_up_sync(0xffffffffu, dc, 1), dNs = __shfl_down_sync(0xffffffffu, dc, 1);
+    const float dS = jfirst ? dc : dSs, dN = jlast ? dc : dNs;
+    const float Ad = dc * diag_1 + dW * lxw_1 + dE * lxe + dS * ly_1 + dN * lyn_1;
+    const float rn = r_1 - Ad;
+    const float rnN = __shfl_down_sync(0xffffffffu, rn, 1);
+    acc = odd ? rn + rnN : (acc + rn) + rnN;                         // MG.restrict(Field) MG.pde:128-133: rn00 + rn01 + rn10 + rn11
+    if (out_lane) {
+      const int k = IDX(i, j);
+      rout[k] = rn;
+      pout[k] = pq_1 + dc;
+      // ghosts of x receive the clamped d (x.plusEq(d) runs over all cells, MG.pde:95); p's ghosts are live data
+      const int di = (i == 1) ? -1 : (i == ni ? 1 : 0), dj = jfirst ? -1 : (jlast ? 1 : 0);
+      if (di) pout[IDX(i + di, j)] = ((di < 0) ? pq_2 : p_e) + dc;
+      if (dj) pout[IDX(i, j + dj)] = pin[IDX(i, j + dj)] + dc;
+      if (di && dj) pout[IDX(i + di, j + dj)] = pin[IDX(i + di, j + dj)] + dc;
+      if (!odd && !(lane & 1)) C.r[(size_t)e * C.stride + (i >> 1) * C.P + ((j + 1) >> 1)] = acc;
+    }
+  };
+  // prologue: rows ia-1 and ia
+  {
+    float r0, d0, g0, w0, y0, yn0;
+    pq_2 = p_m;                                                       // (p of row ia - 2: only used as a ghost row, never)
+    form(r0, d0, g0, w0, y0, yn0);                                    // row ia - 1
+    d_2 = d0; pq_2 = p_m;                                             // p_m is now p of row ia - 1
+    form(r_1, d_1, diag_1, lxw_1, ly_1, lyn_1);                       // row ia
+    pq_1 = p_m;                                                       // p of row ia
+  }
+  for (int i = ia; i <= ib; i += 2) {
+    float r0, d0, g0, w0, y0, yn0;
+    // ---- row i (odd): needs d of row i + 1
+    form(r0, d0, g0, w0, y0, yn0);                                    // row i + 1; afterwards p_m = p(i+1), lx_c = lx(i+2)
+    finish(i, d0, w0, p_m, true);                                     // lxe = lx(i+1) = w0, p_e = p(i+1)
+    d_2 = d_1; d_1 = d0; r_1 = r0; pq_2 = pq_1; pq_1 = p_m; diag_1 = g0; lxw_1 = w0; ly_1 = y0; lyn_1 = yn0;
+    // ---- row i + 1 (even)
+    form(r0, d0, g0, w0, y0, yn0);                                    // row i + 2
+    finish(i + 1, d0, w0, p_m, false);
+    d_2 = d_1; d_1 = d0; r_1 = r0; pq_2 = pq_1; pq_1 = p_m; diag_1 = g0; lxw_1 = w0; ly_1 = y0; lyn_1 = yn0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // levels >= 1: the rest of the V-cycle, one CTA per environment (MG.pde:68-77).  Per level the residual
 // ping-pongs between the level's `r` and `d` arrays: down writes the smoothed residual to `d`, the
 // up pass updates it in place and the strip smoother consumes it, adding its result straight into x.
@@ -1286,6 +1405,12 @@ int launch_residual(const SolverParams& q, const float* ux, const float* uy, flo
 int launch_resid_down0(const SolverParams& q, const float* ux, const float* uy, const float* p_in, float* p_out, float* r_out,
                        int which, cudaStream_t st) {
   const DevLevel& L1 = q.lev[1];
+  if (q.resid_march) {
+    const int ni = q.n - 2, mj = q.m - 2;
+    dim3 grid((mj + kRmCols - 1) / kRmCols, ((ni + kRmRows - 1) / kRmRows + 3) / 4, q.B);
+    k_resid_down0_march<<<grid, 128, 0, st>>>(q, ux, uy, p_in, p_out, r_out, which);
+    return 1;
+  }
   dim3 blk(kRdJ, kRdI);
   dim3 grid((L1.m - 2 + kRdJ - 1) / kRdJ, (L1.n - 2 + kRdI - 1) / kRdI, q.B);
   k_resid_down0<<<grid, blk, 0, st>>>(q, ux, uy, p_in, p_out, r_out, which);

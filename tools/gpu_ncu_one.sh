@@ -10,7 +10,7 @@ rm -f $O/rep.ncu-rep
 python - <<P
 import csv
 rows=list(csv.reader(open("$O/raw.csv"))); hdr=rows[0]; idx={h:i for i,h in enumerate(hdr)}
-want=["gpu__time_duration.sum","l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed","l1tex__data_pipe_lsu_wavefronts.max.pct_of_peak_sustained_elapsed","l1tex__data_pipe_lsu_wavefronts_mem_shared.sum","l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum","sm__issue_active.avg.pct_of_peak_sustained_elapsed","smsp__issue_active.max.pct_of_peak_sustained_active","smsp__inst_executed.sum","launch__registers_per_thread","sm__warps_active.avg.pct_of_peak_sustained_active"]
+want=["gpu__time_duration.sum","l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed","l1tex__data_pipe_lsu_wavefronts.max.pct_of_peak_sustained_elapsed","l1tex__data_pipe_lsu_wavefronts_mem_shared.sum","l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum","sm__issue_active.avg.pct_of_peak_sustained_elapsed","smsp__issue_active.max.pct_of_peak_sustained_active","smsp__inst_executed.sum","launch__registers_per_thread","sm__warps_active.avg.pct_of_peak_sustained_active","dram__bytes_read.sum","dram__bytes_write.sum","sm__throughput.avg.pct_of_peak_sustained_elapsed","lts__t_sector_hit_rate.pct","l1tex__t_sector_hit_rate.pct","smsp__cycles_active.avg","achieved_occupancy","sm__maximum_warps_per_active_cycle_pct","launch__occupancy_limit_registers","launch__waves_per_multiprocessor"]
 for r in rows[2:]:
-    print(r[idx["Kernel Name"]][:50], {w.split(".")[0][-28:]+"."+w.split(".")[-1][:20]: r[idx[w]] for w in want if w in idx})
+    print(r[idx["Kernel Name"]][:50], {w: r[idx[w]] for w in want if w in idx})
 P
