@@ -878,8 +878,11 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
       }
     sp.nband_x = (int)bx.size(); sp.nband_y = (int)by.size();
     // the two-phase setBC kernel fetches rows 1, n-2 and columns 1, m-2 before the band is blended: no band face may
-    // sit on them, and one 1024-thread CTA must cover a row and a column
-    sp.fast_bc = (g.n <= 1024 && g.m <= 1024) ? 1 : 0;
+    // sit on them, and the shared-memory image of the lines (+ the blended band) must fit one CTA.  The kernel strides over
+    // longer lines too, but ONE CTA blending the band of a 2048x1024 domain is slower than the grid-wide k_band_blend + the
+    // literal kernels (measured: 122 vs 52 us), so large grids keep those.
+    sp.fast_bc = (g.n <= 1024 && g.m <= 1024 &&
+                  sizeof(float) * (2 * (3 * (size_t)g.m + 2 * (size_t)g.n) + bx.size() + by.size()) <= 200 * 1024) ? 1 : 0;
     for (const auto* v : {&bx, &by})
       for (const BandFace& f : *v)
         if (f.i <= 1 || f.i >= g.n - 2 || f.j <= 1 || f.j >= g.m - 2) sp.fast_bc = 0;
@@ -908,8 +911,10 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   sp.rr_blocks = 0;
   sp.resid_march = 1;
   if (const char* ev = std::getenv("RLFC_RESID")) sp.resid_march = std::strcmp(ev, "tile") != 0;
-  // (odd level-0 sizes cannot pair rows / columns for the restriction: MG.divisible rules them out anyway)
-  if (((g.n - 2) | (g.m - 2)) & 1) sp.resid_march = 0;
+  // (odd level-0 sizes cannot pair rows / columns for the restriction: MG.divisible rules them out anyway; a batch of fewer
+  // than ~8 Mi cells does not give the marching kernel enough warps -- one 2048x1024 domain: 38 vs 31 us)
+  if ((((g.n - 2) | (g.m - 2)) & 1) || (long long)B * (g.n - 2) * (g.m - 2) < (8ll << 20)) sp.resid_march = 0;
+  if (const char* ev = std::getenv("RLFC_RESID")) if (std::strcmp(ev, "march") == 0 && !(((g.n - 2) | (g.m - 2)) & 1)) sp.resid_march = 1;
   int n_groups = cfg->n_groups;
   if (const char* ev = std::getenv("RLFC_GROUPS")) n_groups = std::atoi(ev);
   // (measured, 256 default-grid envs, round 2: 1 group 6 722, 2 groups 6 713, 4 groups 6 636, 8 groups 5 286 env-steps/s; round 1's

@@ -296,22 +296,23 @@ struct BcLines {            // shared-memory image of one component's boundary l
   float *c1, *cm2;          // columns 1 and m-2 as loaded    [n]
 };
 
-// rows: thread j < m holds a[1][j], a[n-2][j]; cols: thread i < n holds a[i][1], a[i][m-2]
-__device__ __forceinline__ void bc_stage(const BcLines& s, int tid, int n, int m, int btype, float bval, bool gexit, float row1,
-                                         float rown2, float col1, float colm2) {
-  if (tid < m) {
-    s.r0[tid] = row1;                                   // a[0][j] = a[1][j]
-    s.rn1[tid] = (btype == 1 && !gexit) ? bval : rown2; // a[n-1][j] = a[n-2][j]; btype 1 without gradientExit: = bval
-    s.r1[tid] = (btype == 1) ? bval : row1;             // btype 1: a[1][j] = bval
+// phase 1 of one component: rows 1 and n-2, columns 1 and m-2 are read and the shared-memory image is formed (the CTA
+// strides over the lines, so they may be longer than the CTA)
+__device__ __forceinline__ void bc_stage(const BcLines& s, const float* a, int tid, int nt, int n, int m, int P, int btype,
+                                         float bval, bool gexit) {
+  for (int j = tid; j < m; j += nt) {
+    const float row1 = a[IDX(1, j)], rown2 = a[IDX(n - 2, j)];
+    s.r0[j] = row1;                                     // a[0][j] = a[1][j]
+    s.rn1[j] = (btype == 1 && !gexit) ? bval : rown2;   // a[n-1][j] = a[n-2][j]; btype 1 without gradientExit: = bval
+    s.r1[j] = (btype == 1) ? bval : row1;               // btype 1: a[1][j] = bval
   }
-  if (tid < n) { s.c1[tid] = col1; s.cm2[tid] = colm2; }
+  for (int i = tid; i < n; i += nt) { s.c1[i] = a[IDX(i, 1)]; s.cm2[i] = a[IDX(i, m - 2)]; }
 }
 
 // final values after the column loop and the outflow correction; `mean` = s/(m-2) of the gradientExit sum
-__device__ __forceinline__ void bc_store(const BcLines& s, float* a, int tid, int n, int m, int P, int btype, float bval, bool gexit,
-                                         float mean) {
-  if (tid >= 1 && tid <= m - 2) {                       // rows 0, 1, n-1, interior columns
-    const int j = tid;
+__device__ __forceinline__ void bc_store(const BcLines& s, float* a, int tid, int nt, int n, int m, int P, int btype, float bval,
+                                         bool gexit, float mean) {
+  for (int j = 1 + tid; j <= m - 2; j += nt) {          // rows 0, 1, n-1, interior columns
     const bool b2 = btype == 2 && j == 1;               // btype 2: a[i][1] = bval on every row
     a[IDX(0, j)] = b2 ? bval : s.r0[j];
     if (btype == 1 || b2) a[IDX(1, j)] = b2 ? bval : s.r1[j];
@@ -319,8 +320,7 @@ __device__ __forceinline__ void bc_store(const BcLines& s, float* a, int tid, in
     if (gexit) v += bval - mean;                        // a[n-1][j] += bval - s for interior j
     a[IDX(n - 1, j)] = b2 ? bval : v;
   }
-  if (tid < n) {                                        // columns 0, (1), m-1 on every row, corners included
-    const int i = tid;
+  for (int i = tid; i < n; i += nt) {                   // columns 0, (1), m-1 on every row, corners included
     const float src1 = (i == 0) ? s.r0[1] : (i == 1) ? s.r1[1] : (i == n - 1) ? s.rn1[1] : s.c1[i];
     const float src2 = (i == 0) ? s.r0[m - 2] : (i == 1) ? s.r1[m - 2] : (i == n - 1) ? s.rn1[m - 2] : s.cm2[i];
     a[IDX(i, 0)] = src1;                                // a[i][0] = a[i][1]
@@ -347,9 +347,9 @@ k_bc2(const __grid_constant__ SolverParams q, float* ux_all, float* uy_all, cons
   float* tmp = w;                                        // [nband_x + nband_y] blended band values
   __shared__ float s_mean;
   // ---- phase 1: every load ----
-  float xr1 = 0, xrn2 = 0, xc1 = 0, xcm2 = 0, yr1 = 0, yrn2 = 0, yc1 = 0, ycm2 = 0;
-  if (tid < m) { xr1 = ux[IDX(1, tid)]; xrn2 = ux[IDX(n - 2, tid)]; yr1 = uy[IDX(1, tid)]; yrn2 = uy[IDX(n - 2, tid)]; }
-  if (tid < n) { xc1 = ux[IDX(tid, 1)]; xcm2 = ux[IDX(tid, m - 2)]; yc1 = uy[IDX(tid, 1)]; ycm2 = uy[IDX(tid, m - 2)]; }
+  // u.x: btype 1, bval 1, gradientExit (BDIM.pde:52); u.y: btype 2, bval 0
+  bc_stage(sx, ux, tid, blockDim.x, n, m, P, 1, 1.f, true);
+  bc_stage(sy, uy, tid, blockDim.x, n, m, P, 2, 0.f, false);
   if (BAND) {
     // BDIM.updateUP blend on the body band (BDIM.pde:109-122), identical arithmetic to k_band_bc
     const float xi1_m = q.action_scale * q.sc.xi[2 * e], xi2_m = q.action_scale * q.sc.xi[2 * e + 1];
@@ -375,9 +375,6 @@ k_bc2(const __grid_constant__ SolverParams q, float* ux_all, float* uy_all, cons
       tmp[q.nband_x + b] = v + f.del1 * g;
     }
   }
-  // u.x: btype 1, bval 1, gradientExit (BDIM.pde:52); u.y: btype 2, bval 0
-  bc_stage(sx, tid, n, m, 1, 1.f, true, xr1, xrn2, xc1, xcm2);
-  bc_stage(sy, tid, n, m, 2, 0.f, false, yr1, yrn2, yc1, ycm2);
   __syncthreads();
   if (tid == 0) {
     float s = 0;
@@ -390,8 +387,8 @@ k_bc2(const __grid_constant__ SolverParams q, float* ux_all, float* uy_all, cons
     for (int b = tid; b < q.nband_y; b += blockDim.x) uy[IDX(q.band_y[b].i, q.band_y[b].j)] = tmp[q.nband_x + b];
   }
   __syncthreads();
-  bc_store(sx, ux, tid, n, m, P, 1, 1.f, true, s_mean);
-  bc_store(sy, uy, tid, n, m, P, 2, 0.f, false, 0.f);
+  bc_store(sx, ux, tid, blockDim.x, n, m, P, 1, 1.f, true, s_mean);
+  bc_store(sy, uy, tid, blockDim.x, n, m, P, 2, 0.f, false, 0.f);
   if (HEUN) {
     // u = (u + us) * 0.5 on the zone k_project_shift<true> left to us (rows 0, 1, n-2, n-1; the first float4 of every
     // row; the float4s from the one holding column m-2 on): the values the boundary conditions just produced
