@@ -89,14 +89,14 @@ template <bool PREDICTOR>
 __global__ void __launch_bounds__(128)
 k_advdif(const float* __restrict__ srcx, const float* __restrict__ srcy, const float* __restrict__ u0x,
          const float* __restrict__ u0y, float* __restrict__ dstx, float* __restrict__ dsty, int n, int m, int P,
-         size_t stride, float dt, float nu, const int* __restrict__ frozen, int slab_rank, int slab_n) {
+         size_t stride, float dt, float nu, const int* __restrict__ frozen, int slab_rank, int slab_n, int chunk_rows) {
   if (frozen[blockIdx.z] || slab_skip(blockIdx.y, gridDim.y, slab_rank, slab_n)) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ni = n - 2, mj = m - 2;
   const int jw0 = 1 + blockIdx.x * kAdvCols;                         // first output column of this warp
-  const int ia = 1 + (blockIdx.y * 4 + warp) * kAdvRows;             // first row of this chunk
+  const int ia = 1 + (blockIdx.y * 4 + warp) * chunk_rows;           // first row of this chunk
   if (ia > ni) return;
-  const int ib = min(ia + kAdvRows - 1, ni);
+  const int ib = min(ia + chunk_rows - 1, ni);
   const size_t eo = (size_t)blockIdx.z * stride;
   const float* __restrict__ x = srcx + eo;
   const float* __restrict__ y = srcy + eo;
@@ -175,6 +175,22 @@ k_advdif(const float* __restrict__ srcx, const float* __restrict__ srcy, const f
   }
 }
 
+// Serial float sum of v[1 .. m-2] in index order (the outflow mean of Field.setBC, Field.pde:216-217) by ONE thread: the
+// additions form a dependent chain, the shared-memory loads do not -- sixteen of them are issued ahead of their adds.
+__device__ __forceinline__ float serial_sum_interior(const float* v, int m) {
+  float s = 0;
+  int j = 1;
+  for (; j + 16 <= m - 1; j += 16) {
+    float t[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) t[k] = v[j + k];
+#pragma unroll
+    for (int k = 0; k < 16; k++) s += t[k];
+  }
+  for (; j < m - 1; j++) s += v[j];
+  return s;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Field.setBC executed by one CTA (Field.pde:209-234, loop structure and statement order kept)
 // ------------------------------------------------------------------------------------------------
@@ -192,8 +208,7 @@ __device__ void cta_setBC(float* a, int n, int m, int P, int btype, float bval, 
   }
   __syncthreads();
   if (gexit && tid == 0) {
-    float s = 0;
-    for (int j = 1; j < m - 1; j++) s += scol[j];      // serial float sum in j order
+    const float s = serial_sum_interior(scol, m);       // serial float sum in j order
     s_mean = s / (float)(m - 2);
   }
   for (int i = tid; i < n; i += nt) {
@@ -377,8 +392,7 @@ k_bc2(const __grid_constant__ SolverParams q, float* ux_all, float* uy_all, cons
   }
   __syncthreads();
   if (tid == 0) {
-    float s = 0;
-    for (int j = 1; j < m - 1; j++) s += sx.rn1[j];      // serial float sum in j order (Field.pde:216-217)
+    const float s = serial_sum_interior(sx.rn1, m);      // serial float sum in j order (Field.pde:216-217)
     s_mean = s / (float)(m - 2);
   }
   // ---- phase 2: every store ----
@@ -1367,11 +1381,13 @@ inline dim3 grid2d(int m, int n, int B, dim3 blk) { return dim3((m + blk.x - 1) 
 int launch_advdif(const SolverParams& q, const float* srcx, const float* srcy, const float* u0x, const float* u0y,
                   float* dstx, float* dsty, cudaStream_t st) {
   const int ni = q.n - 2, mj = q.m - 2;
-  dim3 grid((mj + kAdvCols - 1) / kAdvCols, ((ni + kAdvRows - 1) / kAdvRows + 3) / 4, q.B);
+  // rows a warp marches: 48 amortise the 4-row window best; a small batch (one wide domain) needs more warps instead
+  const int rows = (long long)q.B * ni * mj < (8ll << 20) ? 16 : kAdvRows;
+  dim3 grid((mj + kAdvCols - 1) / kAdvCols, ((ni + rows - 1) / rows + 3) / 4, q.B);
   if (srcx == u0x && srcy == u0y)
-    k_advdif<true><<<grid, 128, 0, st>>>(srcx, srcy, u0x, u0y, dstx, dsty, q.n, q.m, q.P, q.stride, q.dt, q.nu, q.sc.frozen, q.slab_rank, q.slab_n);
+    k_advdif<true><<<grid, 128, 0, st>>>(srcx, srcy, u0x, u0y, dstx, dsty, q.n, q.m, q.P, q.stride, q.dt, q.nu, q.sc.frozen, q.slab_rank, q.slab_n, rows);
   else
-    k_advdif<false><<<grid, 128, 0, st>>>(srcx, srcy, u0x, u0y, dstx, dsty, q.n, q.m, q.P, q.stride, q.dt, q.nu, q.sc.frozen, q.slab_rank, q.slab_n);
+    k_advdif<false><<<grid, 128, 0, st>>>(srcx, srcy, u0x, u0y, dstx, dsty, q.n, q.m, q.P, q.stride, q.dt, q.nu, q.sc.frozen, q.slab_rank, q.slab_n, rows);
   return 1;
 }
 
