@@ -304,7 +304,7 @@ def ncu_summary(config=2):
 def ncu_lookup(tab, kernel, key):
     for name, rec in tab.items():
         base = name.split("<")[0]
-        if base == kernel or base.replace("_rows", "").replace("_blk", "") == kernel:
+        if base == kernel or base.replace("_rows", "").replace("_blk", "").replace("_march", "") == kernel:
             if key in rec:
                 return float(rec[key])
     return None
