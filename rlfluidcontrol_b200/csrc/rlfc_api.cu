@@ -909,6 +909,8 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   TRY(E->dmalloc(&E->init_ux, sp.stride)); TRY(E->dmalloc(&E->init_uy, sp.stride)); TRY(E->dmalloc(&E->init_p, sp.stride));
   // per-env scalars
   sp.rr_blocks = 0;
+  sp.tiny = 1;
+  if (const char* ev = std::getenv("RLFC_TINY")) sp.tiny = std::atoi(ev) != 0;
   sp.resid_march = 1;
   if (const char* ev = std::getenv("RLFC_RESID")) sp.resid_march = std::strcmp(ev, "tile") != 0;
   // (odd level-0 sizes cannot pair rows / columns for the restriction: MG.divisible rules them out anyway; a batch of fewer

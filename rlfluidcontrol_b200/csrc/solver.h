@@ -127,6 +127,7 @@ struct SolverParams {
   double *rr_chain;         // [B][rr_chain_n] per-CTA partial sums of r.r of the level-0 chain increment
   unsigned *rr_count;       // [B] CTAs of the increment kernel that have delivered their partial sum
   int   rr_chain_n;
+  int   tiny;               // 1 = levels of at most 32 columns are smoothed by one warp in registers (smooth_tiny.cuh; RLFC_TINY=0: row pipeline)
   int   resid_march;        // 1 = k_resid_down0_march (default), 0 = the shared-memory tile version (RLFC_RESID=tile)
   int   fast_bc;            // 1 = two-phase setBC kernels (no band face on the lines setBC reads; grid fits one CTA)
   int   use_rows;           // 1 = row-pipelined smoother (smooth_rows.cuh), 0 = strip smoother (smooth_strip.cuh)

@@ -929,6 +929,8 @@ k_smooth0(const __grid_constant__ SolverParams q, const float* r_in_all, float* 
 // ------------------------------------------------------------------------------------------------
 // Row-pipelined variants (smooth_rows.cuh): one warp per sweep, C columns per lane.
 // ------------------------------------------------------------------------------------------------
+#include "smooth_tiny.cuh"
+
 template <int XMODE>
 __device__ __forceinline__ void rows_dispatch(const DevLevel& L, float* r, float* x, unsigned char* smem) {
   switch (L.rt.C) {
@@ -971,6 +973,7 @@ k_mg_coarse_rows(const __grid_constant__ SolverParams q, int first) {
     const DevLevel& L = q.lev[last];
     const size_t eo = (size_t)e * L.stride;
     if (L.wave) wave_smooth<1>(L, L.r + eo, L.x + eo, L.d + eo, nullptr, 4);     // L.d is unused on the coarsest level
+    else if (q.tiny && tiny_level(L.n - 2, L.m - 2)) tiny_smooth<1>(L, L.r + eo, L.x + eo, smem_raw);
     else rows_dispatch<1>(L, L.r + eo, L.x + eo, smem_raw);
     TICK("smooth", last);
   }
@@ -984,6 +987,7 @@ k_mg_coarse_rows(const __grid_constant__ SolverParams q, int first) {
     __syncthreads();
     TICK("up", l);
     if (L.wave) wave_smooth<2>(L, r, x, L.r + eo, nullptr, 4);   // the level's restricted residual is dead after the down pass
+    else if (q.tiny && tiny_level(L.n - 2, L.m - 2)) tiny_smooth<2>(L, r, x, smem_raw);
     else rows_dispatch<2>(L, r, x, smem_raw);
     TICK("smooth", l);
   }
@@ -1478,7 +1482,10 @@ static size_t smooth0_smem(const SolverParams& q) {
 static size_t coarse_rows_smem(const SolverParams& q) {
   size_t s = 0;
   for (int l = max(1, q.chain_levels); l < q.nlevels; l++)
-    if (!q.lev[l].wave) s = max(s, rows_smem_bytes(min(q.lev[l].rt.C, 4), q.lev[l].P, false));
+    if (!q.lev[l].wave) {
+      if (q.tiny && tiny_level(q.lev[l].n - 2, q.lev[l].m - 2)) s = max(s, tiny_smem_bytes(q.lev[l].n - 2));
+      else s = max(s, rows_smem_bytes(min(q.lev[l].rt.C, 4), q.lev[l].P, false));
+    }
   return s;
 }
 static size_t smooth0_rows_smem(const SolverParams& q) {

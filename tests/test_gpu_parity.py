@@ -178,7 +178,7 @@ def test_other_grids(rlfc, oracle, resolution, xl, yl):
 @pytest.mark.parametrize("envvar,value", [("RLFC_SMOOTHER", "strip"), ("RLFC_SMOOTHER", "wave"), ("RLFC_SMOOTHER", "chain"),
                                           ("RLFC_NO_GRAPH", "1"), ("RLFC_FUSED", "0"),
                                           ("RLFC_GROUPS", "3"), ("RLFC_GROUPS", "4"), ("RLFC_FAST_BC", "0"), ("RLFC_PSUM", "serial"),
-                                          ("RLFC_RESID", "tile"), ("RLFC_RESID", "march")])
+                                          ("RLFC_RESID", "tile"), ("RLFC_RESID", "march"), ("RLFC_TINY", "0")])
 def test_alternative_execution_paths(rlfc, oracle, init_state, monkeypatch, envvar, value):
     """The strip smoother, the wavefront fallback smoother, eager launches, odd env-group splits, the literal setBC kernels and the plain
     serial Field.sum chain are different
