@@ -854,21 +854,44 @@ k_mg_up0_blk(const __grid_constant__ SolverParams q, const float* __restrict__ r
   for (int a = 0; a < 2; a++)
 #pragma unroll
     for (int b = 0; b < 2; b++) { xo[a][b] = x[IDX(i0 + a, j0 + b)]; ro[a][b] = r[IDX(i0 + a, j0 + b)]; }
+  // the 2x2 block's face coefficients, each loaded once: lx on the three rows i0 .. i0+2, ly on the three columns j0 .. j0+2;
+  // the diagonal is their plain sum (PoissonMatrix.pde:46-48; checked against the host table at create time)
+  // (a single division per thread for the skewed index of both columns was measured: 62 registers instead of 48 and 195 us
+  // instead of 106 -- as with the template-parameter variant of round 1, fewer instructions but slower)
+  float lxv[3][2], lyv[2][3];
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++) lxv[a][b] = L0.lx[IDX(i0 + a, j0 + b)];
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) lyv[a][b] = L0.ly[IDX(i0 + a, j0 + b)];
 #pragma unroll
   for (int a = 0; a < 2; a++)
 #pragma unroll
     for (int b = 0; b < 2; b++) {
       const int i = i0 + a, j = j0 + b, k = IDX(i, j);
       const float dW = a ? dc : dWc, dE = a ? dEc : dc, dS = b ? dc : dSc, dN = b ? dNc : dc;
-      const float Ad = dc * L0.diag[k] + dW * L0.lx[k] + dE * L0.lx[k + P] + dS * L0.ly[k] + dN * L0.ly[k + 1];
+      const float dg = -(lxv[a][b] + lxv[a + 1][b] + lyv[a][b] + lyv[a][b + 1]);
+      const float Ad = dc * dg + dW * lxv[a][b] + dE * lxv[a + 1][b] + dS * lyv[a][b] + dN * lyv[a][b + 1];
       x[k] = xo[a][b] + dc;
       const int ln = (j - 1) / C, c = (j - 1) - ln * C;
       rsk[((size_t)(i + ln) * 32 + ln) * CP + c] = ro[a][b] - Ad;
-      const int di = (i == 1) ? -1 : (i == n - 2 ? 1 : 0), dj = (j == 1) ? -1 : (j == m - 2 ? 1 : 0);
-      if (di) x[IDX(i + di, j)] += dc;
-      if (dj) x[IDX(i, j + dj)] += dc;
-      if (di && dj) x[IDX(i + di, j + dj)] += dc;
     }
+  // ghost cells bordering the block (only the blocks on the rim of the level)
+  if (I == 1 || I == nci || J == 1 || J == ncj) {
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        const int i = i0 + a, j = j0 + b;
+        const int di = (i == 1) ? -1 : (i == n - 2 ? 1 : 0), dj = (j == 1) ? -1 : (j == m - 2 ? 1 : 0);
+        if (di) x[IDX(i + di, j)] += dc;
+        if (dj) x[IDX(i, j + dj)] += dc;
+        if (di && dj) x[IDX(i + di, j + dj)] += dc;
+      }
+  }
 }
 
 // plain level-0 residual <- skewed residual (the row smoother leaves r - A d there); only environments that
