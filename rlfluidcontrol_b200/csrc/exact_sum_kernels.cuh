@@ -482,18 +482,85 @@ k_xsum_condense(const __grid_constant__ SolverParams q) {
 // checked table application.  Records with float additions or serial segments are walked entry by entry as in k_xsum_chain; a run whose
 // composed table does not provably apply is walked record by record.  Exactness is unchanged: a table is only applied
 // when its validity condition holds for the true accumulator.
-__global__ void __launch_bounds__(32)
+// Batches whose record does not apply are rebuilt for the TRUE accumulator.  On very large domains such batches come in long
+// stretches (the running sum of a zero-mean field sits next to a power of two for millions of additions and the records
+// were built for the neighbouring binade: profiles/r02_field_sum_large.md), and rebuilding is 5 200 cycles of one warp per
+// batch.  So the CTA carries kXsBulkWarps - 1 HELPER warps that sleep at a named barrier: when warp 0 meets such a batch b,
+// every warp rebuilds one of the batches b .. b + kXsBulkWarps - 1 for the accumulator's current key (the whole-batch
+// table only), and warp 0 then crosses them one checked application after the other for as long as they apply.  A batch
+// whose whole-batch table does not apply falls back to the single-warp path (prefix tables, element-wise additions).
+constexpr int kXsBulkWarps = 16;
+struct XsBulk {
+  float stage[kXsBulkWarps][32][33];     // a batch's 1024 elements per warp, one segment per row (pitch 33: conflict-free)
+  uint32_t table[kXsBulkWarps][8];       // the whole-batch table each warp built
+  int cmd_batch;                         // first batch of the round, -1 = exit
+  uint32_t cmd_key;
+};
+
+__device__ __forceinline__ void xs_bulk_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kXsBulkWarps) : "memory"); }
+
+// one warp: the table of batch `b` for an accumulator of key `key` (lane 31's result is the whole batch), into out[0..6]
+__device__ __forceinline__ void xs_bulk_build(const float* __restrict__ p, unsigned N, unsigned len, unsigned P, int nb, int b,
+                                              uint32_t key, float (*st)[33], uint32_t* out, int lane) {
+  uint32_t w[7] = {key, 0u, 0u, (uint32_t)xsum::kNever, (uint32_t)(-xsum::kNever), (uint32_t)xsum::kNever, (uint32_t)(-xsum::kNever)};
+  if (b < nb) {                                                    // (warp-uniform)
+    const unsigned K0 = (unsigned)b * 1024u + lane;
+    unsigned row = K0 / len, col = K0 - row * len, K = K0;
+    const float* src = p + (size_t)(1u + row) * P + 1u + col;
+#pragma unroll 4
+    for (int k = 0; k < 32; k++) {
+      if (K < N) xs_cp4(&st[k][lane], src);
+      else st[k][lane] = -0.f;
+      K += 32u; col += 32u; src += 32;
+      while (col >= len) { col -= len; src += P - len; }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    xsum::Run run;
+    run.start(key);
+#pragma unroll 8
+    for (int j = 0; j < 32; j++) run.add(st[lane][j]);
+    if (run.good) { run.store(w); xsum::normalise_table(w); }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t prev[7];
+#pragma unroll
+      for (int k = 0; k < 7; k++) prev[k] = __shfl_up_sync(0xffffffffu, w[k], o);
+      if (lane >= o) xsum::compose_tables(prev, w);
+    }
+  }
+  if (lane == 31) {
+#pragma unroll
+    for (int k = 0; k < 7; k++) out[k] = w[k];
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * kXsBulkWarps)
 k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
-  extern __shared__ __align__(16) uint32_t xs_dyn[];               // [32][32] float stage | [32][33] float stage (redo)
+  extern __shared__ __align__(16) uint32_t xs_dyn[];               // [32][32] float stage | [32][33] float stage (redo) | XsBulk
   float (*stage)[32] = reinterpret_cast<float (*)[32]>(xs_dyn);
   float (*stageP)[33] = reinterpret_cast<float (*)[33]>(xs_dyn + 32 * 32);
-  const int e = blockIdx.x, lane = threadIdx.x;
+  XsBulk& bulk = *reinterpret_cast<XsBulk*>(xs_dyn + 32 * 32 + 32 * 33);
+  const int e = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (q.sc.frozen[e]) return;
   const unsigned len = (unsigned)(q.m - 2), P = (unsigned)q.P;
   const unsigned N = (unsigned)(q.n - 2) * len;
   const int nb = q.xs_nbatches;
   const float* p = q.lev[0].x + (size_t)e * q.stride;
   const uint32_t* recs = q.xs_recs + (size_t)e * nb * kXsRecWords;
+  if (warp != 0) {
+    // ---- helper warps: one batch per round ----
+    for (;;) {
+      xs_bulk_barrier();                                           // a command has been posted
+      const int b0 = *(volatile int*)&bulk.cmd_batch;
+      if (b0 < 0) return;
+      xs_bulk_build(p, N, len, P, nb, b0 + warp, *(volatile uint32_t*)&bulk.cmd_key, bulk.stage[warp], bulk.table[warp], lane);
+      xs_bulk_barrier();                                           // the tables are in shared memory
+    }
+  }
+  int done_upto = 0;                                               // batches below this index have been crossed (bulk rounds run ahead)
   int st_rec = 0, st_walk = 0, st_ent = 0, st_redo = 0, st_km = 0;
   long long tk = clock64(), tacc[4] = {0, 0, 0, 0};                // cycles: [0] block set-up + scan, [1] table runs, [2] record walks, [3] batches redone
 #define XSB_TICK(i) do { const long long n_ = clock64(); tacc[i] += n_ - tk; tk = n_; } while (0)
@@ -524,6 +591,29 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
     st_walk++;
     XSB_TICK(2);
     __syncwarp();
+    if (!(q.xs_flags & 1) && xsum::key_ok(bits >> 23)) {
+      // ---- bulk round: batches b .. b + kXsBulkWarps - 1 rebuilt by all warps for the accumulator's current key ----
+      if (lane == 0) { bulk.cmd_batch = b; bulk.cmd_key = bits >> 23; }
+      xs_bulk_barrier();
+      xs_bulk_build(p, N, len, P, nb, b, bits >> 23, bulk.stage[0], bulk.table[0], lane);
+      xs_bulk_barrier();
+      int crossed = 0;
+      for (int w = 0; w < kXsBulkWarps && b + w < nb; w++) {
+        const uint32_t* T = bulk.table[w];
+        bool ok = true;
+        const uint32_t nbits = xsum::apply_table(bits, T[0], (int32_t)T[1], (int32_t)T[2], (int32_t)T[3], (int32_t)T[4], (int32_t)T[5],
+                                                 (int32_t)T[6], ok);
+        if (!ok) break;
+        bits = nbits;
+        crossed++;
+      }
+      if (crossed > 0) {
+        st_walk += crossed - 1;
+        done_upto = b + crossed;
+        XSB_TICK(3);
+        return;
+      }
+    }
     {
       // element (b*32 + k)*32 + lane for k = 0..31: one division, then 32 elements further per k
       const unsigned K0 = (unsigned)b * 1024u + lane;
@@ -583,6 +673,7 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
     XSB_TICK(3);
   };
   auto walk_batch = [&](int b, const uint32_t* rec) {              // one record, entry by entry (as k_xsum_chain)
+    if (b < done_upto) return;                                     // (crossed by a bulk round already)
     const uint4 hdr = *reinterpret_cast<const uint4*>(rec);
 #ifdef RLFC_XS_DIAG
     if (lane == 0 && b >= 503 && b <= 505) printf("xswalk %d hdr %08x %08x bits %08x\n", b, hdr.x, hdr.y, bits);
@@ -620,8 +711,10 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
   for (int w = 0; w < 8; w++) nxt[w] = cblk[w * 32 + lane];
   // (the records themselves are only read where a run does not apply or a record is more than one table: straight from
   // global memory, a few dozen per pass)
+  bool midrun = false;
   for (int b0 = 0; b0 < nb; b0 += 32) {
     const int kend = min(32, nb - b0);
+    midrun = false;                                                // (runs do not extend across blocks)
     // this block's condensed tables (k_xsum_condense), fetched one block ahead
     uint32_t acc[7];
 #pragma unroll
@@ -641,6 +734,16 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
 #ifdef RLFC_XS_DIAG
       if (lane == 0) printf("xsbat %d bits %08x\n", b0 + k, bits);
 #endif
+      if (b0 + k < done_upto) { k++; midrun = true; continue; }    // crossed by a bulk round
+      if (!((puremask >> k) & 1u)) midrun = false;                 // a record that is more than one table starts the runs afresh
+      if (midrun) {
+        // inside a run of one-table records whose beginning a bulk round consumed: the condensed tables start at the run's
+        // first record, so the rest of the run is crossed record by record
+        walk_batch(b0 + k, recs + (size_t)(b0 + k) * kXsRecWords);
+        k++;
+        XSB_TICK(2);
+        continue;
+      }
       if ((puremask >> k) & 1u) {
         const uint32_t rest = ~(puremask >> k);                    // first non-table record at or after k
         int run = rest ? __ffs(rest) - 1 : 32 - k;
@@ -666,6 +769,8 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (lane == 0) bulk.cmd_batch = -1;                              // release the helper warps
+  xs_bulk_barrier();
   if (lane == 0) {
     q.sc.psum[e] = xsum::u2f(bits);
     q.xs_epoch[e] += 1u;
@@ -675,4 +780,4 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
   }
 #undef XSB_TICK
 }
-constexpr size_t kXsBlocksSmem = (size_t)(32 * 32 + 32 * 33) * 4;
+constexpr size_t kXsBlocksSmem = (size_t)(32 * 32 + 32 * 33) * 4 + sizeof(XsBulk);

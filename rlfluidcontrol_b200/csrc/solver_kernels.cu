@@ -1673,7 +1673,7 @@ int launch_psum_tables(const SolverParams& q, cudaStream_t st) {
 int launch_psum_pass(const SolverParams& q, cudaStream_t st) {
   if (q.xs_blk) {                       // large domains: runs of records condensed first (in parallel), then crossed
     k_xsum_condense<<<dim3((q.xs_nbatches + 31) / 32, q.B), 32, 0, st>>>(q);
-    k_xsum_chain_blocks<<<q.B, 32, kXsBlocksSmem, st>>>(q);
+    k_xsum_chain_blocks<<<q.B, 32 * kXsBulkWarps, kXsBlocksSmem, st>>>(q);
     return 2;
   }
   k_xsum_chain<false><<<q.B, 32, 0, st>>>(q);
