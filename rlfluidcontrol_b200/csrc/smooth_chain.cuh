@@ -402,7 +402,13 @@ k_chain_incr(const __grid_constant__ SolverParams q, int level, float* __restric
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = Lv.n, m = Lv.m, P = Lv.P, ni = n - 2, mj = m - 2, T = ch.T, NS = ch.NS;
   const int s = blockIdx.y;
+#ifndef RLFC_INCR_BY_STRIPS
+  // slab mode: blocks are shared out by ROWS (runs of entries), like the row-distributed x and r they update with scattered
+  // 4-byte accesses; the strip-distributed skewed arrays are read as whole lines, which travel well over NVLink
+  if (slab_skip(blockIdx.x, gridDim.x, q.slab_rank, q.slab_n)) return;
+#else
   if (q.slab_n > 1 && (s < ch.s0 || s >= ch.s0 + ch.ns_loc)) return;          // slab mode: the strips this device sweeps
+#endif
   const int t0 = (blockIdx.x * kChIncWarps + warp) * kChIncEntries + 1;        // first entry of this warp's run
   const int j = 32 * s + lane + 1;
   const size_t eo = (size_t)e * ch.sk_stride;
