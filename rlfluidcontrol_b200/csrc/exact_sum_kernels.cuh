@@ -537,7 +537,8 @@ __device__ __forceinline__ void xs_bulk_build(const float* __restrict__ p, unsig
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(32 * kXsBulkWarps)
+template <bool BULK>               // BULK: launched with kXsBulkWarps warps (helpers); otherwise one warp and none of the bulk code
+__global__ void __launch_bounds__(BULK ? 32 * kXsBulkWarps : 32)
 k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
   extern __shared__ __align__(16) uint32_t xs_dyn[];               // [32][32] float stage | [32][33] float stage (redo) | XsBulk
   float (*stage)[32] = reinterpret_cast<float (*)[32]>(xs_dyn);
@@ -550,7 +551,7 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
   const int nb = q.xs_nbatches;
   const float* p = q.lev[0].x + (size_t)e * q.stride;
   const uint32_t* recs = q.xs_recs + (size_t)e * nb * kXsRecWords;
-  if (warp != 0) {
+  if (BULK && warp != 0) {
     // ---- helper warps: one batch per round ----
     for (;;) {
       xs_bulk_barrier();                                           // a command has been posted
@@ -560,6 +561,7 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
       xs_bulk_barrier();                                           // the tables are in shared memory
     }
   }
+  constexpr bool bulk_on = BULK;
   int done_upto = 0;                                               // batches below this index have been crossed (bulk rounds run ahead)
   int st_rec = 0, st_walk = 0, st_ent = 0, st_redo = 0, st_km = 0;
   long long tk = clock64(), tacc[4] = {0, 0, 0, 0};                // cycles: [0] block set-up + scan, [1] table runs, [2] record walks, [3] batches redone
@@ -591,7 +593,7 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
     st_walk++;
     XSB_TICK(2);
     __syncwarp();
-    if (!(q.xs_flags & 1) && xsum::key_ok(bits >> 23)) {
+    if (bulk_on && !(q.xs_flags & 1) && xsum::key_ok(bits >> 23)) {
       // ---- bulk round: batches b .. b + kXsBulkWarps - 1 rebuilt by all warps for the accumulator's current key ----
       if (lane == 0) { bulk.cmd_batch = b; bulk.cmd_key = bits >> 23; }
       xs_bulk_barrier();
@@ -673,7 +675,7 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
     XSB_TICK(3);
   };
   auto walk_batch = [&](int b, const uint32_t* rec) {              // one record, entry by entry (as k_xsum_chain)
-    if (b < done_upto) return;                                     // (crossed by a bulk round already)
+    if (BULK && b < done_upto) return;                             // (crossed by a bulk round already)
     const uint4 hdr = *reinterpret_cast<const uint4*>(rec);
 #ifdef RLFC_XS_DIAG
     if (lane == 0 && b >= 503 && b <= 505) printf("xswalk %d hdr %08x %08x bits %08x\n", b, hdr.x, hdr.y, bits);
@@ -734,9 +736,9 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
 #ifdef RLFC_XS_DIAG
       if (lane == 0) printf("xsbat %d bits %08x\n", b0 + k, bits);
 #endif
-      if (b0 + k < done_upto) { k++; midrun = true; continue; }    // crossed by a bulk round
-      if (!((puremask >> k) & 1u)) midrun = false;                 // a record that is more than one table starts the runs afresh
-      if (midrun) {
+      if (BULK && b0 + k < done_upto) { k++; midrun = true; continue; }    // crossed by a bulk round
+      if (BULK && !((puremask >> k) & 1u)) midrun = false;         // a record that is more than one table starts the runs afresh
+      if (BULK && midrun) {
         // inside a run of one-table records whose beginning a bulk round consumed: the condensed tables start at the run's
         // first record, so the rest of the run is crossed record by record
         walk_batch(b0 + k, recs + (size_t)(b0 + k) * kXsRecWords);
@@ -769,8 +771,10 @@ k_xsum_chain_blocks(const __grid_constant__ SolverParams q) {
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
-  if (lane == 0) bulk.cmd_batch = -1;                              // release the helper warps
-  xs_bulk_barrier();
+  if (bulk_on) {
+    if (lane == 0) bulk.cmd_batch = -1;                            // release the helper warps
+    xs_bulk_barrier();
+  }
   if (lane == 0) {
     q.sc.psum[e] = xsum::u2f(bits);
     q.xs_epoch[e] += 1u;

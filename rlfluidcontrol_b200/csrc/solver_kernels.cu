@@ -1532,7 +1532,8 @@ int configure_kernels(const SolverParams& q) {
         cudaFuncSetAttribute(k_bc2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc2_smem(q)) != cudaSuccess)
       return -1;
   }
-  if (cudaFuncSetAttribute(k_xsum_chain_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kXsBlocksSmem) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(k_xsum_chain_blocks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kXsBlocksSmem) != cudaSuccess ||
+      cudaFuncSetAttribute(k_xsum_chain_blocks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kXsBlocksSmem) != cudaSuccess) return -1;
   cudaError_t e3 = cudaFuncSetAttribute(k_mg_coarse_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coarse_rows_smem(q));
   if (q.chain_levels > 0 &&
       (cudaFuncSetAttribute(k_chain_sweeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kChMaxWpb * sizeof(ChainRing))) != cudaSuccess ||
@@ -1673,7 +1674,9 @@ int launch_psum_tables(const SolverParams& q, cudaStream_t st) {
 int launch_psum_pass(const SolverParams& q, cudaStream_t st) {
   if (q.xs_blk) {                       // large domains: runs of records condensed first (in parallel), then crossed
     k_xsum_condense<<<dim3((q.xs_nbatches + 31) / 32, q.B), 32, 0, st>>>(q);
-    k_xsum_chain_blocks<<<q.B, 32 * kXsBulkWarps, kXsBlocksSmem, st>>>(q);
+    // (helper warps for rebuilding batches in bulk only where long stretches of them occur: the three-pass sizes)
+    if (q.xs_passes >= 3) k_xsum_chain_blocks<true><<<q.B, 32 * kXsBulkWarps, kXsBlocksSmem, st>>>(q);
+    else k_xsum_chain_blocks<false><<<q.B, 32, kXsBlocksSmem, st>>>(q);
     return 2;
   }
   k_xsum_chain<false><<<q.B, 32, 0, st>>>(q);
