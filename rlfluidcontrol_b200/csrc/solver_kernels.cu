@@ -467,15 +467,28 @@ __device__ __forceinline__ void down_block(const DevLevel& L, const DevLevel& C,
                                            int I, int J) {
   const int P = L.P, n = L.n, m = L.m;
   const int i0 = (I - 1) * 2 + 1, j0 = (J - 1) * 2 + 1;
-  float d[4][4];
+  float d[4][4], rv[2][2];
 #pragma unroll
   for (int a = 0; a < 4; a++)
 #pragma unroll
     for (int b = 0; b < 4; b++) {
       if ((a == 0 || a == 3) && (b == 0 || b == 3)) { d[a][b] = 0.f; continue; }
       int ci = min(max(i0 - 1 + a, 1), n - 2), cj = min(max(j0 - 1 + b, 1), m - 2);
-      d[a][b] = rin[IDX(ci, cj)] * L.inv[IDX(ci, cj)];
+      const float rr = rin[IDX(ci, cj)];
+      d[a][b] = rr * L.inv[IDX(ci, cj)];
+      if (a >= 1 && a <= 2 && b >= 1 && b <= 2) rv[a - 1][b - 1] = rr;       // (the block's own cells are never clamped)
     }
+  // the block's face coefficients, each loaded once: lx on rows i0 .. i0+2, ly on columns j0 .. j0+2; the diagonal is
+  // their plain sum (PoissonMatrix.pde:46-48; checked against the host table at create time)
+  float lxv[3][2], lyv[2][3];
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++) lxv[a][b] = L.lx[IDX(i0 + a, j0 + b)];
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) lyv[a][b] = L.ly[IDX(i0 + a, j0 + b)];
   float rn[2][2];
 #pragma unroll
   for (int a = 0; a < 2; a++)
@@ -483,9 +496,10 @@ __device__ __forceinline__ void down_block(const DevLevel& L, const DevLevel& C,
     for (int b = 0; b < 2; b++) {
       const int i = i0 + a, j = j0 + b, k = IDX(i, j);
       const float dc = d[a + 1][b + 1];
-      float Ad = dc * L.diag[k] + d[a][b + 1] * L.lx[k] + d[a + 2][b + 1] * L.lx[k + P] + d[a + 1][b] * L.ly[k] +
-                 d[a + 1][b + 2] * L.ly[k + 1];
-      rn[a][b] = rin[k] - Ad;
+      const float dg = -(lxv[a][b] + lxv[a + 1][b] + lyv[a][b] + lyv[a][b + 1]);
+      float Ad = dc * dg + d[a][b + 1] * lxv[a][b] + d[a + 2][b + 1] * lxv[a + 1][b] + d[a + 1][b] * lyv[a][b] +
+                 d[a + 1][b + 2] * lyv[a][b + 1];
+      rn[a][b] = rv[a][b] - Ad;
       rout[k] = rn[a][b];
       if (LEVEL0) {
         x[k] += dc;
@@ -721,7 +735,6 @@ __device__ __forceinline__ void coarse_up_pass(const DevLevel& L, const DevLevel
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const float* __restrict__ lx = L.lx;
   const float* __restrict__ ly = L.ly;
-  const float* __restrict__ diag = L.diag;
   constexpr int U = RLFC_UP_ROWS;
   for (int j = 1 + lane; j <= mj; j += 32) {
     const int cj = (j - 1) / 2 + 1, cjm = (max(j - 1, 1) - 1) / 2 + 1, cjp = (min(j + 1, mj) - 1) / 2 + 1;
@@ -741,7 +754,9 @@ __device__ __forceinline__ void coarse_up_pass(const DevLevel& L, const DevLevel
         if (i <= ni) {
           const int k = IDX(i, j);
           x[k] = xo[u] + dc[u];
-          r[k] = ro[u] - (dc[u] * diag[k] + dw[u] * lx[k] + de[u] * lx[k + P] + ds[u] * ly[k] + dn[u] * ly[k + 1]);
+          const float lw = lx[k], le = lx[k + P], ls = ly[k], ln_ = ly[k + 1];
+          const float dg = -(lw + le + ls + ln_);                      // the diagonal is the plain coefficient sum (PoissonMatrix.pde:46-48)
+          r[k] = ro[u] - (dc[u] * dg + dw[u] * lw + de[u] * le + ds[u] * ls + dn[u] * ln_);
         }
       }
     }
