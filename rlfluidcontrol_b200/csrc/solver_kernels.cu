@@ -641,6 +641,7 @@ k_resid_down0_march(const __grid_constant__ SolverParams q, const float* __restr
   float* __restrict__ rout = rout_all + eo;
   const float* __restrict__ lx = L.lx;
   const float* __restrict__ ly = L.ly;
+  const float* __restrict__ diag = L.diag;
   const float* __restrict__ inv = L.inv;
   const int j = jw0 - 2 + lane;                                      // this lane's column (may be outside the array)
   const int jl = min(max(j, 0), m - 1);                              // clamped for loads
@@ -660,10 +661,9 @@ k_resid_down0_march(const __grid_constant__ SolverParams q, const float* __restr
   auto form = [&](float& r_out, float& d_out, float& diag_o, float& lxw_o, float& ly_o, float& lyn_o) {
     const int k = IDX(rowc(ir), jl), kn = IDX(rowc(ir + 1), jl);
     const float ux_n = ux[kn], lx_n = lx[kn];
-    const float uy_c = uy[k], ly_c = ly[k], iv = inv[k];
+    const float uy_c = uy[k], ly_c = ly[k], dg = diag[k], iv = inv[k];
     const float p_s = __shfl_up_sync(0xffffffffu, p_c, 1), p_nn = __shfl_down_sync(0xffffffffu, p_c, 1);
     const float uy_n = __shfl_down_sync(0xffffffffu, uy_c, 1), ly_n = __shfl_down_sync(0xffffffffu, ly_c, 1);
-    const float dg = -(lx_c + lx_n + ly_c + ly_n);                   // the diagonal is the plain coefficient sum (PoissonMatrix.pde:46-48)
     const float sdiv = ux_n - ux_c + uy_n - uy_c;                    // VectorField.pde:56-65
     const float Ap = p_c * dg + p_m * lx_c + p_n * lx_n + p_s * ly_c + p_nn * ly_n;   // PoissonMatrix.pde:56-61
     r_out = sdiv - Ap;
