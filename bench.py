@@ -472,6 +472,9 @@ def run_b200(args):
                     "traffic": ncu_lookup(ncu, top["name"], "dram_traffic_B_per_launch") if B == 256 else None,
                     "peak_source": peak_src, "share_of_step": top["ms"] / tot_ms,
                     "algorithmic_bytes_per_launch": top["bytes_per_launch"], "avg_launch_ms": avg_ms}
+            fp = next((r.get("fp32_issue") for r in table if r["kernel"] == top["name"] and "fp32_issue" in r), None)
+            if fp:   # (k_advdif is bound by fp32 instruction issue under --fmad=false, SURVEY H5: the second roofline it is held to)
+                roof["fp32_issue"] = fp
         # whole-step view against the SURVEY 8d model: 4 B * N_int * (28 + 13 (kP + kC)) per env per solver step
         nint = 384 * 192
         k_sum = float(mg.sum(axis=1).mean())
