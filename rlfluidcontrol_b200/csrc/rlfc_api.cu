@@ -920,10 +920,10 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   if (const char* ev = std::getenv("RLFC_RESID")) if (std::strcmp(ev, "march") == 0 && !(((g.n - 2) | (g.m - 2)) & 1)) sp.resid_march = 1;
   int n_groups = cfg->n_groups;
   if (const char* ev = std::getenv("RLFC_GROUPS")) n_groups = std::atoi(ev);
-  // (measured, 256 default-grid envs, round 2: 1 group 6 722, 2 groups 6 713, 4 groups 6 636, 8 groups 5 286 env-steps/s; round 1's
-  // latency-bound kernels gained 6 % from 4 concurrent groups, the present ones do not.  Batches larger than one wave of the
+  // (measured, 256 default-grid envs, final round-2 kernels: 1 group 7 120, 2 groups 7 333-7 364, 3 groups 7 230, 4 groups 7 242
+  // env-steps/s device-resident, end-to-end figures within 1 % of each other.  Batches larger than one wave of the
   // one-CTA-per-environment kernels keep 4 groups.)
-  if (n_groups <= 0) n_groups = B > 256 ? 4 : 1;
+  if (n_groups <= 0) n_groups = B > 256 ? 4 : (B >= 128 ? 2 : 1);
   n_groups = std::min(n_groups, B);
   if (slab) n_groups = 1;
   if (const char* ev = std::getenv("RLFC_NO_GRAPH")) E->use_graph = std::atoi(ev) == 0;
