@@ -85,8 +85,11 @@ __device__ __forceinline__ float face_value(float uf, float bLL, float bL, float
   return (pos ? plain_pos : plain_neg) ? bf : lim;
 }
 
+#ifndef RLFC_ADV_MINB
+#define RLFC_ADV_MINB 9      // 56 registers, 9 CTAs per SM: 202 -> 193 us (8: 198, 10 and 12 spill: 201, 217)
+#endif
 template <bool PREDICTOR>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, RLFC_ADV_MINB)
 k_advdif(const float* __restrict__ srcx, const float* __restrict__ srcy, const float* __restrict__ u0x,
          const float* __restrict__ u0y, float* __restrict__ dstx, float* __restrict__ dsty, int n, int m, int P,
          size_t stride, float dt, float nu, const int* __restrict__ frozen, int slab_rank, int slab_n, int chunk_rows) {
@@ -843,7 +846,10 @@ k_mg_up0(const __grid_constant__ SolverParams q, float* __restrict__ r_all) {
 // xc[I][J]; their outward neighbours take the adjacent coarse cell's value, or -- at the domain edge, where
 // d.setBC copies the adjacent interior value (MG.pde:139-152) -- the cell's own.  x += d on the children and on the
 // ghost cells they border, r -= A d written to the smoother's skewed array.
-__global__ void __launch_bounds__(256)
+#ifndef RLFC_UP0_MINB
+#define RLFC_UP0_MINB 1
+#endif
+__global__ void __launch_bounds__(256, RLFC_UP0_MINB)
 k_mg_up0_blk(const __grid_constant__ SolverParams q, const float* __restrict__ r_all) {
   const int e = blockIdx.z;
   if (!q.sc.active[e]) return;
