@@ -923,7 +923,8 @@ int rlfc_env_create(const rlfc_config* cfg, rlfc_env** out) {
   // (measured, 256 default-grid envs, final round-2 kernels: 1 group 7 120, 2 groups 7 333-7 364, 3 groups 7 230, 4 groups 7 242
   // env-steps/s device-resident, end-to-end figures within 1 % of each other.  Batches larger than one wave of the
   // one-CTA-per-environment kernels keep 4 groups.)
-  if (n_groups <= 0) n_groups = B > 256 ? 4 : (B >= 128 ? 2 : 1);
+  // 512 envs: 2 groups 8 230, 4 groups 8 078 env-steps/s; larger batches were only measured with 4 groups.
+  if (n_groups <= 0) n_groups = B > 512 ? 4 : (B >= 128 ? 2 : 1);
   n_groups = std::min(n_groups, B);
   if (slab) n_groups = 1;
   if (const char* ev = std::getenv("RLFC_NO_GRAPH")) E->use_graph = std::atoi(ev) == 0;
