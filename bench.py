@@ -621,6 +621,30 @@ def nvlink_counters(n):
         return None
 
 
+def slab_traffic_model(n, m, nd, k_sum):
+    """Bytes that cross device boundaries per solver step in slab mode -- a MODEL (the pool's NVML has no NVLink byte
+    counters), stated with its assumptions:
+    * stencil halos of the row-slab-distributed plain arrays, per internal boundary and solver step: advection-diffusion reads
+      2 rows of ux, uy on either side in both half steps (16 rows), the first MG iteration reads p two rows deep and ux one
+      row (5 rows per solve), the projection reads p one row (1 row per solve), the coarse grid-wide levels add about a third
+      of level 0's MG halo (geometric sum); one row = 4 (m) bytes;
+    * layout conversions between the row-distributed plain arrays and the STRIP-distributed skewed arrays of the chained
+      smoother, per MG iteration and level-0 cell: the up pass writes r (4 B) and the tagged sweep-0 value (8 B), the increment
+      reads the tagged result (8 B), the coefficient entry (16 B) and r (4 B): 40 B, x 4/3 for the coarser chained levels; a
+      fraction (nd - 1)/nd of it is remote."""
+    try:
+        if nd <= 1:
+            return {"halo_bytes_per_step_model": 0, "layout_conversion_bytes_per_step_model": 0}
+        row = 4.0 * m
+        solves = 2.0
+        halo_rows = 16.0 + solves * (5.0 * (k_sum / 2.0) * (4.0 / 3.0) + 1.0)
+        halo = (nd - 1) * halo_rows * row
+        conv = 40.0 * (4.0 / 3.0) * (n - 2) * (m - 2) * k_sum * (nd - 1) / nd
+        return {"halo_bytes_per_step_model": int(halo), "layout_conversion_bytes_per_step_model": int(conv)}
+    except Exception:
+        return {}
+
+
 def run_slab(args):
     """Config 5: ONE domain (default 8192x4096, resolution 512) advanced by --gpus devices through the library's slab mode
     (rlfc_config.n_devices): the devices are driven by ONE host process -- rank 0 -- which owns all of them (shared address
@@ -686,6 +710,7 @@ def run_slab(args):
                 its.append(env.mg_iters()[0].tolist())
             prof = env.get_profile()
             env.set_profiling(False)
+        env_n, env_m = env.n, env.m
         env.close()
         peak, peak_src = measured_peak()
         kern, tot_ms, table = kernel_table(prof, args.profile_steps, peak, clk.get("sm_mhz") if clk else None, {})
@@ -706,6 +731,7 @@ def run_slab(args):
             "e2e": {"value": K / e2e_s, "unit": UNIT3, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": int((2 + 32) * 4)},
             "gpu_launches": int(launches),
             "slab": {"devices": nd, "barriers_per_step": barriers / K, "shared_address_range_bytes": shared,
+                     **slab_traffic_model(env_n, env_m, nd, k_sum),
                      "nvlink_bytes_per_step_measured": (None if nv0 is None or nv1 is None else (nv1 - nv0) / K),
                      "nvlink_counter_note": NVLINK_NOTE},
             "roofline": {"bound": "hbm", "kernel": "whole solver step", "achieved": ach, "peak": peak * nd, "unit": "GB/s",
